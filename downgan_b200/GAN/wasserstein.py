@@ -1,0 +1,209 @@
+"""B200 WGAN-GP trainer: drop-in for ``DoWnGAN/GAN/wasserstein.py:16-189``.
+
+Same class name, constructor and method names as the reference trainer;
+``_critic_train_iteration`` / ``_generator_train_iteration`` return ``None``
+and mutate parameters and optimizer state.  Underneath, each iteration is ONE
+call into ``libdowngan_b200.so`` (``dg_critic_step`` / ``dg_generator_step``)
+followed by an optional NCCL all-reduce of the flat gradient buffer (data
+parallel, one process per GPU) and one fused Adam launch (``dg_adam_step``).
+
+Differences from the reference that do not change results:
+  * the generator backward of the critic iteration (wasserstein.py:52) is
+    skipped — the reference discards those gradients at :65;
+  * the gradient penalty uses the closed-form double backward instead of
+    ``autograd.grad(create_graph=True)`` (wasserstein.py:100-106);
+  * ``alpha`` can be injected (parity tests); the default draws it on the
+    device with ``torch.rand`` exactly like wasserstein.py:91;
+  * the flattened gradient uses the actual batch size, not ``hp.batch_size``
+    (the reference mis-shapes ragged batches, wasserstein.py:110);
+  * mlflow logging / plotting (wasserstein.py:140-179) is out of scope; loss
+    scalars stay on the device in ``last_critic`` / ``last_generator``.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import _lib
+from ..config import hyperparams as hp
+from ..networks.critic import Critic
+from ..networks.generator import Generator
+
+CRITIC_SCALARS = ("critic_loss", "c_real_mean", "c_fake_mean", "gp", "penalty")
+GENERATOR_SCALARS = ("g_loss", "c_fake_mean", "l1")
+
+
+class _FlatAdam:
+    """torch.optim.Adam semantics (stage.py:63-64) as one fused launch over the flat buffer.
+    Hyper-parameters are read from the caller's optimizer every step."""
+
+    def __init__(self, module, optimizer):
+        self.module = module
+        self.optimizer = optimizer
+        self.exp_avg: Optional[torch.Tensor] = None
+        self.exp_avg_sq: Optional[torch.Tensor] = None
+        self.step_count = 0
+
+    def _group(self):
+        if self.optimizer is None:
+            return {"lr": hp.lr, "betas": (0.9, 0.99), "eps": 1e-8}
+        if len(self.optimizer.param_groups) != 1:
+            raise _lib.DgError("the fused Adam step supports a single param group")
+        g = self.optimizer.param_groups[0]
+        if g.get("weight_decay", 0) or g.get("amsgrad", False) or g.get("maximize", False):
+            raise _lib.DgError("fused Adam: weight_decay / amsgrad / maximize are not supported")
+        return g
+
+    def step(self, grads: torch.Tensor, grad_scale: float = 1.0) -> None:
+        flat = self.module.flat_params()
+        if self.exp_avg is None or self.exp_avg.data_ptr() == 0 or self.exp_avg.numel() != flat.numel():
+            self.exp_avg = torch.zeros_like(flat)
+            self.exp_avg_sq = torch.zeros_like(flat)
+        g = self._group()
+        self.step_count += 1
+        b1, b2 = g["betas"]
+        _lib.check(_lib.load().dg_adam_step(flat.data_ptr(), grads.data_ptr(), self.exp_avg.data_ptr(),
+                                            self.exp_avg_sq.data_ptr(), flat.numel(), float(g["lr"]), float(b1),
+                                            float(b2), float(g["eps"]), self.step_count, float(grad_scale),
+                                            _lib.stream_ptr()))
+        self.module.mark_params_changed()
+
+    def sync_to_optimizer(self) -> None:
+        """Mirror the fused state into ``optimizer.state`` so ``optimizer.state_dict()`` is meaningful."""
+        if self.optimizer is None or self.exp_avg is None:
+            return
+        offs = self.module.param_offsets()
+        for p, o in zip(self.module._param_list(), offs):
+            self.optimizer.state[p] = {
+                "step": torch.tensor(float(self.step_count)),
+                "exp_avg": self.exp_avg[o:o + p.numel()].view(p.shape),
+                "exp_avg_sq": self.exp_avg_sq[o:o + p.numel()].view(p.shape),
+            }
+
+
+class WassersteinGAN:
+    """Implements Wasserstein GAN with gradient penalty (B200-native iteration)."""
+
+    def __init__(self, G: Generator, C: Critic, G_optimizer, C_optimizer) -> None:
+        if not isinstance(G, Generator) or not isinstance(C, Critic):
+            raise TypeError("WassersteinGAN needs downgan_b200.networks.Generator / Critic modules")
+        self.G = G
+        self.C = C
+        self.G_optimizer = G_optimizer
+        self.C_optimizer = C_optimizer
+        self.num_steps = 0
+        self._g_adam = _FlatAdam(G, G_optimizer)
+        self._c_adam = _FlatAdam(C, C_optimizer)
+        self.last_critic: Optional[torch.Tensor] = None     # 8 floats on device, see CRITIC_SCALARS
+        self.last_generator: Optional[torch.Tensor] = None  # 8 floats on device, see GENERATOR_SCALARS
+        self._c_scal = None
+        self._g_scal = None
+
+    # ---- helpers -------------------------------------------------------------
+    @property
+    def device(self) -> torch.device:
+        return self.G.conv1.weight.device
+
+    def _hyper(self) -> _lib.Hyper:
+        return _lib.Hyper(float(hp.gp_lambda), float(hp.gamma), float(hp.content_lambda))
+
+    def _prep(self, t: torch.Tensor) -> torch.Tensor:
+        return t.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+
+    def _handles(self, coarse: torch.Tensor):
+        b, _, h, _ = coarse.shape
+        g = self.G.native(h, b)
+        c = self.C.native(b)
+        self.G.ensure_packed(g)
+        self.C.ensure_packed(c)
+        return g, c
+
+    @staticmethod
+    def _world() -> int:
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _allreduce(self, grads: torch.Tensor) -> float:
+        """Sum-all-reduce the flat gradient bucket over NCCL; returns the 1/world scale for Adam."""
+        w = self._world()
+        if w > 1:
+            dist.all_reduce(grads, op=dist.ReduceOp.SUM)
+            return 1.0 / w
+        return 1.0
+
+    # ---- iterations ------------------------------------------------------------
+    def _critic_train_iteration(self, coarse, fine, alpha: Optional[torch.Tensor] = None):
+        """One critic update (wasserstein.py:27-55)."""
+        coarse, fine = self._prep(coarse), self._prep(fine)
+        b = coarse.shape[0]
+        with torch.cuda.device(self.device):
+            if alpha is None:
+                alpha = torch.rand(b, 1, 1, 1, device=self.device)  # wasserstein.py:91
+            alpha = self._prep(alpha).reshape(b)
+            g, c = self._handles(coarse)
+            if self._c_scal is None or self._c_scal.device != self.device:
+                self._c_scal = torch.zeros(8, device=self.device)
+            grads = self.C.flat_grads()
+            hyp = self._hyper()
+            _lib.check(_lib.load().dg_critic_step(g, c, hyp, coarse.data_ptr(), fine.data_ptr(), alpha.data_ptr(), b,
+                                                  grads.data_ptr(), self._c_scal.data_ptr(), _lib.stream_ptr()))
+            scale = self._allreduce(grads)
+            self._c_adam.step(grads, scale)
+        self.last_critic = self._c_scal
+
+    def _generator_train_iteration(self, coarse, fine):
+        """One generator update (wasserstein.py:58-83)."""
+        coarse, fine = self._prep(coarse), self._prep(fine)
+        b = coarse.shape[0]
+        with torch.cuda.device(self.device):
+            g, c = self._handles(coarse)
+            if self._g_scal is None or self._g_scal.device != self.device:
+                self._g_scal = torch.zeros(8, device=self.device)
+            grads = self.G.flat_grads()
+            hyp = self._hyper()
+            _lib.check(_lib.load().dg_generator_step(g, c, hyp, coarse.data_ptr(), fine.data_ptr(), b,
+                                                     grads.data_ptr(), self._g_scal.data_ptr(), _lib.stream_ptr()))
+            scale = self._allreduce(grads)
+            self._g_adam.step(grads, scale)
+        self.last_generator = self._g_scal
+
+    def _gp(self, real, fake, critic, alpha: Optional[torch.Tensor] = None, want_grads: bool = False):
+        """Gradient penalty value ``hp.gp_lambda * mean((||grad||-1)^2)`` (wasserstein.py:87-117).
+        With ``want_grads`` also returns d(hp.gp_lambda * value)/d(critic params) as a flat tensor."""
+        real, fake = self._prep(real), self._prep(fake.detach())
+        b = real.shape[0]
+        with torch.cuda.device(self.device):
+            if alpha is None:
+                alpha = torch.rand(b, 1, 1, 1, device=self.device)
+            alpha = self._prep(alpha).reshape(b)
+            c = critic.native(b)
+            critic.ensure_packed(c)
+            out = torch.zeros(1, device=self.device)
+            norms = torch.empty(b, device=self.device)
+            grads = torch.empty_like(critic.flat_params()) if want_grads else None
+            hyp = self._hyper()
+            _lib.check(_lib.load().dg_gp(c, hyp, real.data_ptr(), fake.data_ptr(), alpha.data_ptr(), b, out.data_ptr(),
+                                         norms.data_ptr(), grads.data_ptr() if grads is not None else None,
+                                         _lib.stream_ptr()))
+        self.last_gp_norms = norms
+        return (out[0], grads) if want_grads else out[0]
+
+    # ---- epoch loop (wasserstein.py:120-189, logging/plotting out of scope) ----
+    def _train_epoch(self, dataloader, testdataloader=None, epoch: int = 0):
+        for data in dataloader:
+            coarse, fine = data[0], data[1]
+            self._critic_train_iteration(coarse, fine)
+            if self.num_steps % hp.critic_iterations == 0:
+                self._generator_train_iteration(coarse, fine)
+            self.num_steps += 1
+
+    def train(self, dataloader, testdataloader=None):
+        self.num_steps = 0
+        for epoch in range(hp.epochs):
+            self._train_epoch(dataloader, testdataloader, epoch)
+        self.sync_optimizer_state()
+
+    def sync_optimizer_state(self) -> None:
+        self._g_adam.sync_to_optimizer()
+        self._c_adam.sync_to_optimizer()

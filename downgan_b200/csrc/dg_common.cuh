@@ -1,0 +1,166 @@
+// Shared declarations for libdowngan_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/downgan_b200.h"
+
+namespace dg {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing -------------------------------------------------------
+void set_error(const char* fmt, ...);
+const char* last_error();
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define DG_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      dg::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+      return DG_ERR_CUDA;                                                               \
+    }                                                                                   \
+  } while (0)
+
+#define DG_CHECK(cond, ...)                 \
+  do {                                      \
+    if (!(cond)) {                          \
+      dg::set_error(__VA_ARGS__);           \
+      return DG_ERR_INVALID;                \
+    }                                       \
+  } while (0)
+
+#define DG_TRY(expr)              \
+  do {                            \
+    int s__ = (expr);             \
+    if (s__ != 0) return s__;     \
+  } while (0)
+
+#define DG_LAUNCH_CHECK()                                                                \
+  do {                                                                                   \
+    dg::count_launch();                                                                  \
+    cudaError_t e__ = cudaPeekAtLastError();                                             \
+    if (e__ != cudaSuccess) {                                                            \
+      dg::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return DG_ERR_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+// ---- tensor views ---------------------------------------------------------
+// NHWC activation view: element (n,y,x,c) lives at p[((n*H + y)*W + x)*pitch + coff + c].
+// A dense-block concat buffer is ONE allocation with pitch = 5F; each conv
+// writes its output slice through a view with a different coff.
+struct TV {
+  void* p = nullptr;
+  int bf = 0;     // 1: bf16 storage, 0: fp32
+  int pitch = 0;  // channels per pixel in the allocation
+  int coff = 0;   // first channel of this view
+};
+inline TV tv(void* p, int bf, int pitch, int coff = 0) {
+  TV t; t.p = p; t.bf = bf; t.pitch = pitch; t.coff = coff; return t;
+}
+inline TV tv_batch(const TV& t, size_t pixels_per_sample, int n0) {  // view starting at sample n0
+  TV r = t;
+  size_t off = (size_t)n0 * pixels_per_sample * t.pitch;
+  r.p = t.bf ? (void*)((bf16*)t.p + off) : (void*)((float*)t.p + off);
+  return r;
+}
+
+enum Act { ACT_NONE = 0, ACT_LRELU = 1, ACT_MASK = 2 };
+enum Shuf { SHUF_NONE = 0, SHUF_PIXEL = 1, SHUF_UNPIXEL = 2 };
+
+// One 3x3 / pad 1 convolution (or its data-gradient) with a fused epilogue:
+//   v = s_acc*(acc + bias) + s1*r1 + s2*r2 ; act ; store (optionally pixel-(un)shuffled)
+struct ConvOp {
+  TV x; int Hin = 0, Win = 0, Ci = 0;
+  TV y; int Hout = 0, Wout = 0, Co = 0;
+  int B = 0;
+  const float* w = nullptr;   // packed [9][Ci][CoP] fp32, CoP = round_up(Co,16)
+  const float* bias = nullptr;
+  int stride = 1;
+  int transposed = 0;         // 1: data-gradient of a stride-2 conv (scatter expressed as gather)
+  float s_acc = 1.f;
+  TV r1; float s1 = 0.f;
+  TV r2; float s2 = 0.f;
+  int act = ACT_NONE; float slope = 0.f;
+  TV mask;                    // ACT_MASK: v *= (mask > 0 ? 1 : slope); indexed like the STORE location
+  int shuffle = SHUF_NONE;
+  // tcgen05 path extras (bf16 mode)
+  const void* w_umma = nullptr;  // packed bf16 weights for the tcgen05 kernel (null -> direct kernel)
+};
+
+struct WgradOp {
+  TV x; int Hin = 0, Win = 0, Ci = 0;
+  TV dy; int Hout = 0, Wout = 0, Co = 0;
+  int B = 0;
+  int stride = 1;
+  float* dw = nullptr;   // packed [9][Ci][CoP] fp32, accumulated with atomics
+  float* dbias = nullptr;  // [Co] accumulated, may be null
+};
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+inline size_t packed_w_elems(int ci, int co) { return (size_t)9 * ci * round_up(co, 16); }
+
+// ---- kernels (dg_kernels.cu) ------------------------------------------------
+int conv_direct(const ConvOp& op, cudaStream_t st);
+int wgrad_direct(const WgradOp& op, cudaStream_t st);
+
+// packing: table-driven, one launch per network
+struct PackDesc {
+  long long src_off;   // offset of OIHW weight in flat params (or flat grads for unpack)
+  long long dst_off;   // offset in packed buffer
+  int Ci, Co, CoP;
+  int mode;            // 0: fwd [tap][ci][co] = W[co][ci][tap]
+                       // 1: dgrad stride-1 (flipped, transposed): [tap][co][ci'] = W[co][ci][8-tap], packed as Ci_op=Co, Co_op=Ci
+                       // 2: dgrad stride-2 gather form (not flipped): [tap][co][ci]
+  // dense-block dgrad (mode 3): source slice of W_j feeding input slice k
+  int slice_off;       // first input channel of the slice inside W (k*F)
+  int src_ci_total;    // Ci of the source weight (j*F)
+  int dst_row_off;     // row (input channel of the dgrad op) where this slice starts
+  int dst_CoP;         // CoP of the destination op
+};
+int pack_weights(const float* params, float* packed, const PackDesc* table_dev, int n, int max_elems, cudaStream_t st);
+int unpack_wgrads(const float* packed, float* grads, const PackDesc* table_dev, int n, int max_elems, cudaStream_t st);
+
+int nchw_to_nhwc(const float* src, TV dst, int B, int C, int H, int W, cudaStream_t st);
+int nhwc_to_nchw(TV src, float* dst, int B, int C, int H, int W, cudaStream_t st);
+// dst = s * src (+ s2 * src2)   over B*H*W pixels x C channels of NHWC views
+int scale_add(TV dst, TV a, float sa, TV b, float sb, size_t pixels, int C, cudaStream_t st);
+// critic input batch [real ; fake ; alpha*real + (1-alpha)*fake] from NCHW real and NHWC/NCHW fake
+int build_critic_input(const float* real_nchw, const float* fake, int fake_is_nchw, const float* alpha,
+                       float* dst_nhwc, int B, int C, int H, int W, int with_interp, cudaStream_t st);
+int colsum(TV dy, size_t pixels, int C, float* out, cudaStream_t st);
+
+// linear layers (critic classifier)
+int fc_fwd(const void* x, int x_bf, const float* w, const float* bias, float* y, int NB, int K, int N,
+           int act, float slope, const float* mask, cudaStream_t st);   // y = act(x W^T + b) or mask*(x W^T)
+int fc_dgrad(const float* dz, const float* w, void* dx, int dx_bf, int NB, int K, int N,
+             const void* mask, int mask_bf, float slope, cudaStream_t st);  // dx = (dz W) * lrelu'(mask)
+int fc_wgrad(const float* dz, const void* x, int x_bf, float* dw, int NB, int K, int N, cudaStream_t st);  // dw += dz^T x
+int fc2_fwd(const float* a, const float* w, const float* bias, float* s, int NB, int K, cudaStream_t st);
+int fc2_seed(const float* a9, const float* w2, const float* seed, float* dz9, int NB, int K, float slope, cudaStream_t st);
+
+int critic_means(const float* scores, int B, float* scalars, cudaStream_t st);
+int gp_norms(const float* g, int B, size_t per_sample, float* sumsq, cudaStream_t st);
+int gp_finish(const float* sumsq, int B, float gp_lambda, float* norms, float* coef, float* scalars, int write_loss, cudaStream_t st);
+int gp_scale(const float* g, const float* coef, float* u, int B, size_t per_sample, cudaStream_t st);
+int l1_loss(const float* a, const float* b, long long n, float scale, float* loss_out, float* d_a,
+            const float* d_add, cudaStream_t st);
+int adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+         int step, float gscale, cudaStream_t st);
+int fill(float* p, float v, long long n, cudaStream_t st);
+int gen_scalars(const float* scores, int B, const float* l1, float gamma, float content_lambda, float* scalars, cudaStream_t st);
+
+// tcgen05 path (dg_umma.cu)
+bool umma_supported(const ConvOp& op);
+int conv_umma(const ConvOp& op, cudaStream_t st);
+
+}  // namespace dg

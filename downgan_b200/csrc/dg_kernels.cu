@@ -1,0 +1,673 @@
+// CUDA-core kernels of libdowngan_b200.so: direct 3x3 convolutions (the fp32
+// parity mode and the HBM-bound skinny layers of the bf16 mode), the critic's
+// linear layers, weight packing, gradient-penalty / loss reductions and Adam.
+// Everything accumulates in fp32.  sm_100a only.
+#include <stdarg.h>
+
+#include "dg_common.cuh"
+
+namespace dg {
+
+static thread_local char g_err[1024] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+// ---------------------------------------------------------------------------
+// typed access through a TV
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float ldv(const void* p, int bf, size_t i) {
+  return bf ? __bfloat162float(((const bf16*)p)[i]) : ((const float*)p)[i];
+}
+__device__ __forceinline__ void stv(void* p, int bf, size_t i, float v) {
+  if (bf) ((bf16*)p)[i] = __float2bfloat16_rn(v);
+  else ((float*)p)[i] = v;
+}
+__device__ __forceinline__ float lrelu_d(float a, float slope) { return a > 0.f ? 1.f : slope; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float block_sum(float v, float* sh) {  // sh: >= 32 floats
+  v = warp_sum(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) v = warp_sum(v);
+  return v;  // valid in warp 0
+}
+
+// ---------------------------------------------------------------------------
+// direct 3x3 convolution, one output pixel x 16 output channels per thread
+// ---------------------------------------------------------------------------
+constexpr int CONV_THREADS = 128;
+
+__global__ void __launch_bounds__(CONV_THREADS) conv_direct_kernel(ConvOp op) {
+  __shared__ __align__(16) float sw[9][16][16];
+  const int CoP = (op.Co + 15) & ~15;
+  const int co0 = blockIdx.y * 16;
+  const long long total = (long long)op.B * op.Hout * op.Wout;
+  const long long p = (long long)blockIdx.x * CONV_THREADS + threadIdx.x;
+  const bool valid = p < total;
+  int n = 0, yo = 0, xo = 0;
+  if (valid) {
+    xo = (int)(p % op.Wout);
+    long long t = p / op.Wout;
+    yo = (int)(t % op.Hout);
+    n = (int)(t / op.Hout);
+  }
+  // per-tap input pixel (or -1)
+  long long off[9];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ky = tap / 3, kx = tap % 3;
+    int yi, xi;
+    bool ok = valid;
+    if (op.transposed) {
+      const int ty = yo + 1 - ky, tx = xo + 1 - kx;
+      ok = ok && ty >= 0 && tx >= 0 && !(ty & 1) && !(tx & 1);
+      yi = ty >> 1; xi = tx >> 1;
+      ok = ok && yi < op.Hin && xi < op.Win;
+    } else {
+      yi = yo * op.stride + ky - 1; xi = xo * op.stride + kx - 1;
+      ok = ok && yi >= 0 && xi >= 0 && yi < op.Hin && xi < op.Win;
+    }
+    off[tap] = ok ? (((long long)n * op.Hin + yi) * op.Win + xi) * op.x.pitch + op.x.coff : -1;
+  }
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+
+  for (int ci0 = 0; ci0 < op.Ci; ci0 += 16) {
+    const int cn = min(16, op.Ci - ci0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * cn * 16; i += CONV_THREADS) {
+      const int tap = i / (cn * 16), r = i % (cn * 16), ci = r >> 4, j = r & 15;
+      sw[tap][ci][j] = op.w[((size_t)tap * op.Ci + ci0 + ci) * CoP + co0 + j];
+    }
+    __syncthreads();
+    if (!valid) continue;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      if (off[tap] < 0) continue;
+      const size_t base = (size_t)off[tap] + ci0;
+      if (cn == 16) {
+        float xs[16];
+#pragma unroll
+        for (int ci = 0; ci < 16; ++ci) xs[ci] = ldv(op.x.p, op.x.bf, base + ci);
+#pragma unroll
+        for (int ci = 0; ci < 16; ++ci) {
+          const float4* wr = reinterpret_cast<const float4*>(&sw[tap][ci][0]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 wv = wr[q];
+            acc[4 * q + 0] = fmaf(xs[ci], wv.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(xs[ci], wv.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(xs[ci], wv.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(xs[ci], wv.w, acc[4 * q + 3]);
+          }
+        }
+      } else {
+        for (int ci = 0; ci < cn; ++ci) {
+          const float xv = ldv(op.x.p, op.x.bf, base + ci);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = fmaf(xv, sw[tap][ci][j], acc[j]);
+        }
+      }
+    }
+  }
+  if (!valid) return;
+  // epilogue
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int co = co0 + j;
+    if (co >= op.Co) break;
+    float v = acc[j];
+    if (op.bias) v += op.bias[co];
+    v *= op.s_acc;
+    if (op.r1.p) v = fmaf(op.s1, ldv(op.r1.p, op.r1.bf, (size_t)p * op.r1.pitch + op.r1.coff + co), v);
+    if (op.r2.p) v = fmaf(op.s2, ldv(op.r2.p, op.r2.bf, (size_t)p * op.r2.pitch + op.r2.coff + co), v);
+    if (op.act == ACT_LRELU) v = v > 0.f ? v : v * op.slope;
+    else if (op.act == ACT_MASK)
+      v *= lrelu_d(ldv(op.mask.p, op.mask.bf, (size_t)p * op.mask.pitch + op.mask.coff + co), op.slope);
+    size_t idx;
+    if (op.shuffle == SHUF_NONE) {
+      idx = (size_t)p * op.y.pitch + op.y.coff + co;
+    } else if (op.shuffle == SHUF_PIXEL) {
+      // out[n, 2y+i, 2x+j, c] = v[n, y, x, 4c+2i+j]   (nn.PixelShuffle(2), generator.py:73)
+      const int c = co >> 2, i = (co >> 1) & 1, jj = co & 1;
+      const size_t q = ((size_t)n * (2 * op.Hout) + 2 * yo + i) * (2 * op.Wout) + 2 * xo + jj;
+      idx = q * op.y.pitch + op.y.coff + c;
+    } else {
+      // inverse addressing for the data-gradient of a pixel-shuffled activation
+      const size_t q = ((size_t)n * (op.Hout >> 1) + (yo >> 1)) * (op.Wout >> 1) + (xo >> 1);
+      idx = q * op.y.pitch + op.y.coff + 4 * co + 2 * (yo & 1) + (xo & 1);
+    }
+    stv(op.y.p, op.y.bf, idx, v);
+  }
+}
+
+int conv_direct(const ConvOp& op, cudaStream_t st) {
+  DG_CHECK(op.x.p && op.y.p && op.w, "conv_direct: null tensor");
+  DG_CHECK(op.stride == 1 || op.stride == 2, "conv_direct: stride %d", op.stride);
+  const long long total = (long long)op.B * op.Hout * op.Wout;
+  dim3 grid((unsigned)((total + CONV_THREADS - 1) / CONV_THREADS), (unsigned)((op.Co + 15) / 16));
+  conv_direct_kernel<<<grid, CONV_THREADS, 0, st>>>(op);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// direct weight gradient: thread = (tap, ci) x 16 output channels
+// ---------------------------------------------------------------------------
+constexpr int WG_THREADS = 144;
+constexpr int WG_SUB = 16;
+
+__global__ void __launch_bounds__(WG_THREADS) wgrad_direct_kernel(WgradOp op, int pix_per_block) {
+  __shared__ __align__(16) float sdy[WG_SUB][16];
+  const int CoP = (op.Co + 15) & ~15;
+  const int tap = threadIdx.x >> 4, cil = threadIdx.x & 15;
+  const int ci = blockIdx.y * 16 + cil;
+  const int co0 = blockIdx.z * 16;
+  const int ky = tap / 3, kx = tap % 3;
+  const long long total = (long long)op.B * op.Hout * op.Wout;
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  const long long p1 = min(total, p0 + pix_per_block);
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  for (long long ps = p0; ps < p1; ps += WG_SUB) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < WG_SUB * 16; i += WG_THREADS) {
+      const int q = i >> 4, j = i & 15;
+      const long long p = ps + q;
+      float v = 0.f;
+      if (p < p1 && co0 + j < op.Co) v = ldv(op.dy.p, op.dy.bf, (size_t)p * op.dy.pitch + op.dy.coff + co0 + j);
+      sdy[q][j] = v;
+    }
+    __syncthreads();
+    if (ci >= op.Ci) continue;
+    const int qn = (int)min((long long)WG_SUB, p1 - ps);
+    for (int q = 0; q < qn; ++q) {
+      const long long p = ps + q;
+      const int xo = (int)(p % op.Wout);
+      const long long t = p / op.Wout;
+      const int yo = (int)(t % op.Hout);
+      const int n = (int)(t / op.Hout);
+      const int yi = yo * op.stride + ky - 1, xi = xo * op.stride + kx - 1;
+      if (yi < 0 || xi < 0 || yi >= op.Hin || xi >= op.Win) continue;
+      const float xv = ldv(op.x.p, op.x.bf, (((size_t)n * op.Hin + yi) * op.Win + xi) * op.x.pitch + op.x.coff + ci);
+      const float4* dr = reinterpret_cast<const float4*>(&sdy[q][0]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 d = dr[k];
+        acc[4 * k + 0] = fmaf(xv, d.x, acc[4 * k + 0]);
+        acc[4 * k + 1] = fmaf(xv, d.y, acc[4 * k + 1]);
+        acc[4 * k + 2] = fmaf(xv, d.z, acc[4 * k + 2]);
+        acc[4 * k + 3] = fmaf(xv, d.w, acc[4 * k + 3]);
+      }
+    }
+  }
+  if (ci >= op.Ci) return;
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (co0 + j < op.Co) atomicAdd(&op.dw[((size_t)tap * op.Ci + ci) * CoP + co0 + j], acc[j]);
+}
+
+int wgrad_direct(const WgradOp& op, cudaStream_t st) {
+  DG_CHECK(op.x.p && op.dy.p && op.dw, "wgrad_direct: null tensor");
+  const long long total = (long long)op.B * op.Hout * op.Wout;
+  const int cic = (op.Ci + 15) / 16, coc = (op.Co + 15) / 16;
+  // aim for ~8 blocks per SM overall
+  long long want = (148LL * 8 + cic * coc - 1) / (cic * coc);
+  long long ppb = (total + want - 1) / want;
+  ppb = ((ppb + WG_SUB - 1) / WG_SUB) * WG_SUB;
+  if (ppb < 64) ppb = 64;
+  if (ppb > 4096) ppb = 4096;
+  dim3 grid((unsigned)((total + ppb - 1) / ppb), (unsigned)cic, (unsigned)coc);
+  wgrad_direct_kernel<<<grid, WG_THREADS, 0, st>>>(op, (int)ppb);
+  DG_LAUNCH_CHECK();
+  if (op.dbias) DG_TRY(colsum(op.dy, (size_t)total, op.Co, op.dbias, st));
+  return 0;
+}
+
+// column sums over pixels (bias gradients); accumulates with atomics
+__global__ void colsum_kernel(TV dy, size_t pixels, int C, float* out, size_t pix_per_block) {
+  __shared__ float sh[8][33];
+  const size_t p0 = (size_t)blockIdx.x * pix_per_block;
+  const size_t p1 = min(pixels, p0 + pix_per_block);
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int c = c0 + threadIdx.x;
+    float s = 0.f;
+    if (c < C)
+      for (size_t p = p0 + threadIdx.y; p < p1; p += 8) s += ldv(dy.p, dy.bf, p * dy.pitch + dy.coff + c);
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x];
+      atomicAdd(&out[c], t);
+    }
+    __syncthreads();
+  }
+}
+int colsum(TV dy, size_t pixels, int C, float* out, cudaStream_t st) {
+  size_t ppb = (pixels + 148 * 4 - 1) / (148 * 4);
+  if (ppb < 64) ppb = 64;
+  unsigned grid = (unsigned)((pixels + ppb - 1) / ppb);
+  colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(dy, pixels, C, out, ppb);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// table-driven packing (one launch per network)
+// ---------------------------------------------------------------------------
+__global__ void pack_kernel(const float* __restrict__ src, float* __restrict__ dst, const PackDesc* __restrict__ tab,
+                            int unpack) {
+  const PackDesc d = tab[blockIdx.y];
+  long long n;
+  if (d.mode == 5) n = d.Co;
+  else if (d.mode == 4) n = (long long)d.Co * d.Ci;
+  else n = (long long)d.Co * d.Ci * 9;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    if (d.mode == 5) {  // bias copy
+      if (unpack) dst[d.src_off + e] = src[d.dst_off + e];
+      else dst[d.dst_off + e] = src[d.src_off + e];
+      continue;
+    }
+    if (d.mode == 4) {
+      // linear weight (Co=N rows, Ci=K cols) with NCHW->NHWC column permutation: K = C*HW, C = slice_off
+      const int C = d.slice_off, HW = d.Ci / C;
+      const int j = (int)(e / d.Ci), k = (int)(e % d.Ci);  // k in NCHW order: c*HW + hw
+      const int c = k / HW, hw = k % HW;
+      const long long pk = (long long)j * d.Ci + (long long)hw * C + c;
+      if (unpack) dst[d.src_off + e] = src[d.dst_off + pk];
+      else dst[d.dst_off + pk] = src[d.src_off + e];
+      continue;
+    }
+    const int tap = (int)(e % 9);
+    const long long r = e / 9;
+    long long s_idx, p_idx;
+    if (d.mode == 3) {
+      // slice of a dense-block weight W_j[co][slice_off+ci][tap] -> row dst_row_off+co, col ci, flipped tap
+      const int ci = (int)(r % d.Ci), co = (int)(r / d.Ci);
+      s_idx = ((long long)co * d.src_ci_total + d.slice_off + ci) * 9 + tap;
+      p_idx = ((long long)(8 - tap) * d.CoP /*rows_total*/ + d.dst_row_off + co) * d.dst_CoP + ci;
+    } else {
+      const int ci = (int)(r % d.Ci), co = (int)(r / d.Ci);
+      s_idx = ((long long)co * d.Ci + ci) * 9 + tap;
+      if (d.mode == 0) p_idx = ((long long)tap * d.Ci + ci) * d.CoP + co;
+      else if (d.mode == 1) p_idx = ((long long)(8 - tap) * d.Co + co) * d.CoP + ci;   // CoP = round16(Ci)
+      else p_idx = ((long long)tap * d.Co + co) * d.CoP + ci;                          // mode 2
+    }
+    if (unpack) dst[d.src_off + s_idx] = src[d.dst_off + p_idx];
+    else dst[d.dst_off + p_idx] = src[d.src_off + s_idx];
+  }
+}
+int pack_weights(const float* params, float* packed, const PackDesc* tab, int n, int max_elems, cudaStream_t st) {
+  if (n == 0) return 0;
+  int bx = (max_elems + 255) / 256;
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  pack_kernel<<<dim3(bx, n), 256, 0, st>>>(params, packed, tab, 0);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+int unpack_wgrads(const float* packed, float* grads, const PackDesc* tab, int n, int max_elems, cudaStream_t st) {
+  if (n == 0) return 0;
+  int bx = (max_elems + 255) / 256;
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  pack_kernel<<<dim3(bx, n), 256, 0, st>>>(packed, grads, tab, 1);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// layout + elementwise
+// ---------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, TV dst, int C, size_t HW, size_t total_pix) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_pix; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / HW, hw = i % HW;
+    for (int c = 0; c < C; ++c) stv(dst.p, dst.bf, i * dst.pitch + dst.coff + c, src[(n * C + c) * HW + hw]);
+  }
+}
+__global__ void nhwc_to_nchw_kernel(TV src, float* __restrict__ dst, int C, size_t HW, size_t total_pix) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_pix; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / HW, hw = i % HW;
+    for (int c = 0; c < C; ++c) dst[(n * C + c) * HW + hw] = ldv(src.p, src.bf, i * src.pitch + src.coff + c);
+  }
+}
+static inline unsigned ew_grid(size_t n, int threads = 256) {
+  size_t b = (n + threads - 1) / threads;
+  if (b > 148 * 16) b = 148 * 16;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+int nchw_to_nhwc(const float* src, TV dst, int B, int C, int H, int W, cudaStream_t st) {
+  const size_t HW = (size_t)H * W, tot = HW * B;
+  nchw_to_nhwc_kernel<<<ew_grid(tot), 256, 0, st>>>(src, dst, C, HW, tot);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+int nhwc_to_nchw(TV src, float* dst, int B, int C, int H, int W, cudaStream_t st) {
+  const size_t HW = (size_t)H * W, tot = HW * B;
+  nhwc_to_nchw_kernel<<<ew_grid(tot), 256, 0, st>>>(src, dst, C, HW, tot);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void scale_add_kernel(TV dst, TV a, float sa, TV b, float sb, size_t pixels, int C) {
+  const size_t n = pixels * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t p = i / C;
+    const int c = (int)(i % C);
+    float v = sa * ldv(a.p, a.bf, p * a.pitch + a.coff + c);
+    if (b.p) v = fmaf(sb, ldv(b.p, b.bf, p * b.pitch + b.coff + c), v);
+    stv(dst.p, dst.bf, p * dst.pitch + dst.coff + c, v);
+  }
+}
+int scale_add(TV dst, TV a, float sa, TV b, float sb, size_t pixels, int C, cudaStream_t st) {
+  scale_add_kernel<<<ew_grid(pixels * C), 256, 0, st>>>(dst, a, sa, b, sb, pixels, C);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+// [real ; fake ; alpha*real + (1-alpha)*fake]  (wasserstein.py:91-94), NHWC fp32 out
+__global__ void build_critic_input_kernel(const float* __restrict__ real, const float* __restrict__ fake, int fake_nchw,
+                                          const float* __restrict__ alpha, float* __restrict__ dst, int B, int C,
+                                          size_t HW, int mode) {
+  const size_t tot = (size_t)B * HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / HW, hw = i % HW;
+    const float a = alpha ? alpha[n] : 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float r = real[(n * C + c) * HW + hw];
+      const float f = fake_nchw ? fake[(n * C + c) * HW + hw] : fake[i * C + c];
+      const float x = a * r + (1.f - a) * f;
+      if (mode == 0) {
+        dst[i * C + c] = r;
+        dst[(tot + i) * C + c] = f;
+        dst[(2 * tot + i) * C + c] = x;
+      } else {
+        dst[i * C + c] = x;
+      }
+    }
+  }
+}
+int build_critic_input(const float* real, const float* fake, int fake_is_nchw, const float* alpha, float* dst, int B,
+                       int C, int H, int W, int mode, cudaStream_t st) {
+  const size_t HW = (size_t)H * W;
+  build_critic_input_kernel<<<ew_grid(HW * B), 256, 0, st>>>(real, fake, fake_is_nchw, alpha, dst, B, C, HW, mode);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void fill_kernel(float* p, float v, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+int fill(float* p, float v, long long n, cudaStream_t st) {
+  fill_kernel<<<ew_grid((size_t)n), 256, 0, st>>>(p, v, n);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// critic classifier (critic.py:94-99)
+// ---------------------------------------------------------------------------
+// y[b][j] = act(sum_k x[b][k] w[j][k] + bias[j]); one warp per (b, j)
+__global__ void fc_fwd_kernel(const void* __restrict__ x, int x_bf, const float* __restrict__ w,
+                              const float* __restrict__ bias, float* __restrict__ y, int NB, int K, int N, int act,
+                              float slope, const float* __restrict__ mask) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= NB * N) return;
+  const int b = warp / N, j = warp % N;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s = fmaf(ldv(x, x_bf, (size_t)b * K + k), w[(size_t)j * K + k], s);
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (bias) s += bias[j];
+    if (act == ACT_LRELU) s = s > 0.f ? s : s * slope;
+    else if (act == ACT_MASK) s *= lrelu_d(mask[(size_t)b * N + j], slope);
+    y[(size_t)b * N + j] = s;
+  }
+}
+int fc_fwd(const void* x, int x_bf, const float* w, const float* bias, float* y, int NB, int K, int N, int act,
+           float slope, const float* mask, cudaStream_t st) {
+  const long long threads = (long long)NB * N * 32;
+  fc_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, x_bf, w, bias, y, NB, K, N, act, slope, mask);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+// dx[b][k] = (sum_j dz[b][j] w[j][k]) * lrelu'(mask[b][k])
+__global__ void fc_dgrad_kernel(const float* __restrict__ dz, const float* __restrict__ w, void* __restrict__ dx,
+                                int dx_bf, int K, int N, const void* __restrict__ mask, int mask_bf, float slope) {
+  extern __shared__ float sdz[];
+  const int b = blockIdx.y;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) sdz[j] = dz[(size_t)b * N + j];
+  __syncthreads();
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float s = 0.f;
+  for (int j = 0; j < N; ++j) s = fmaf(sdz[j], w[(size_t)j * K + k], s);
+  if (mask) s *= lrelu_d(ldv(mask, mask_bf, (size_t)b * K + k), slope);
+  stv(dx, dx_bf, (size_t)b * K + k, s);
+}
+int fc_dgrad(const float* dz, const float* w, void* dx, int dx_bf, int NB, int K, int N, const void* mask, int mask_bf,
+             float slope, cudaStream_t st) {
+  fc_dgrad_kernel<<<dim3((K + 255) / 256, NB), 256, N * sizeof(float), st>>>(dz, w, dx, dx_bf, K, N, mask, mask_bf, slope);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+// dw[j][k] += sum_b dz[b][j] x[b][k]
+__global__ void fc_wgrad_kernel(const float* __restrict__ dz, const void* __restrict__ x, int x_bf,
+                                float* __restrict__ dw, int NB, int K, int N) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (k >= K) return;
+  float s = 0.f;
+  for (int b = 0; b < NB; ++b) s = fmaf(dz[(size_t)b * N + j], ldv(x, x_bf, (size_t)b * K + k), s);
+  dw[(size_t)j * K + k] += s;
+}
+int fc_wgrad(const float* dz, const void* x, int x_bf, float* dw, int NB, int K, int N, cudaStream_t st) {
+  fc_wgrad_kernel<<<dim3((K + 255) / 256, N), 256, 0, st>>>(dz, x, x_bf, dw, NB, K, N);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void fc2_fwd_kernel(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
+                               float* __restrict__ s, int NB, int K) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= NB) return;
+  float v = 0.f;
+  for (int k = lane; k < K; k += 32) v = fmaf(a[(size_t)warp * K + k], w[k], v);
+  v = warp_sum(v);
+  if (lane == 0) s[warp] = v + (bias ? bias[0] : 0.f);
+}
+int fc2_fwd(const float* a, const float* w, const float* bias, float* s, int NB, int K, cudaStream_t st) {
+  fc2_fwd_kernel<<<(NB * 32 + 255) / 256, 256, 0, st>>>(a, w, bias, s, NB, K);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+// dz9[b][j] = seed[b] * w2[j] * lrelu'(a9[b][j])
+__global__ void fc2_seed_kernel(const float* __restrict__ a9, const float* __restrict__ w2, const float* __restrict__ seed,
+                                float* __restrict__ dz9, int NB, int K, float slope) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NB * K) return;
+  const int b = i / K, j = i % K;
+  dz9[i] = seed[b] * w2[j] * lrelu_d(a9[i], slope);
+}
+int fc2_seed(const float* a9, const float* w2, const float* seed, float* dz9, int NB, int K, float slope, cudaStream_t st) {
+  fc2_seed_kernel<<<(NB * K + 255) / 256, 256, 0, st>>>(a9, w2, seed, dz9, NB, K, slope);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// losses and gradient-penalty reductions
+// ---------------------------------------------------------------------------
+// scalars[1] = mean(scores[0:B]) (real), scalars[2] = mean(scores[B:2B]) (fake)
+__global__ void critic_means_kernel(const float* __restrict__ scores, int B, float* __restrict__ scalars) {
+  __shared__ float sh[32];
+  float r = 0.f, f = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) { r += scores[i]; f += scores[B + i]; }
+  r = block_sum(r, sh);
+  f = block_sum(f, sh);
+  if (threadIdx.x == 0) { scalars[1] = r / B; scalars[2] = f / B; }
+}
+int critic_means(const float* scores, int B, float* scalars, cudaStream_t st) {
+  critic_means_kernel<<<1, 256, 0, st>>>(scores, B, scalars);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+// sumsq[b] += sum over the sample of g^2 (vectorised, one atomic per block)
+__global__ void gp_norms_kernel(const float* __restrict__ g, size_t per_sample, float* __restrict__ sumsq) {
+  __shared__ float sh[32];
+  const int b = blockIdx.y;
+  const float4* gp = reinterpret_cast<const float4*>(g + (size_t)b * per_sample);
+  const size_t n4 = per_sample >> 2;
+  float s = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = gp[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (size_t i = n4 << 2; i < per_sample; ++i) { const float v = g[(size_t)b * per_sample + i]; s += v * v; }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) atomicAdd(&sumsq[b], s);
+}
+int gp_norms(const float* g, int B, size_t per_sample, float* sumsq, cudaStream_t st) {
+  DG_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * B, st));
+  unsigned bx = (unsigned)((per_sample / 4 + 1023) / 1024);
+  if (bx < 1) bx = 1;
+  if (bx > 32) bx = 32;
+  gp_norms_kernel<<<dim3(bx, B), 256, 0, st>>>(g, per_sample, sumsq);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+// norms, GP value, and dGP/dg coefficient  lam^2 * (2/B) * (n-1)/n   (wasserstein.py:110-117,40)
+__global__ void gp_finish_kernel(const float* __restrict__ sumsq, int B, float lam, float* __restrict__ norms,
+                                 float* __restrict__ coef, float* __restrict__ scalars, int write_loss) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const float n = sqrtf(sumsq[i] + 1e-12f);
+    if (norms) norms[i] = n;
+    if (coef) coef[i] = lam * lam * (2.f / B) * (n - 1.f) / n;
+    acc += (n - 1.f) * (n - 1.f);
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) {
+    const float gp = lam * acc / B;
+    scalars[3] = gp;
+    scalars[4] = lam * gp;
+    if (write_loss) scalars[0] = scalars[2] - scalars[1] + lam * gp;
+  }
+}
+int gp_finish(const float* sumsq, int B, float lam, float* norms, float* coef, float* scalars, int write_loss,
+              cudaStream_t st) {
+  gp_finish_kernel<<<1, 256, 0, st>>>(sumsq, B, lam, norms, coef, scalars, write_loss);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+__global__ void gp_scale_kernel(const float* __restrict__ g, const float* __restrict__ coef, float* __restrict__ u,
+                                size_t per_sample, size_t total) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    u[i] = coef[i / per_sample] * g[i];
+}
+int gp_scale(const float* g, const float* coef, float* u, int B, size_t per_sample, cudaStream_t st) {
+  gp_scale_kernel<<<ew_grid(per_sample * B), 256, 0, st>>>(g, coef, u, per_sample, per_sample * B);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+// mean |a-b| (+ seed scale*sign(a-b)/n [+ d_add])   (losses.py:51-53)
+__global__ void l1_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float scale,
+                          float* __restrict__ loss, float* __restrict__ d_a, const float* __restrict__ d_add) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  const float k = scale / (float)n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float d = a[i] - b[i];
+    s += fabsf(d);
+    if (d_a) {
+      float gsign = d > 0.f ? k : (d < 0.f ? -k : 0.f);
+      if (d_add) gsign += d_add[i];
+      d_a[i] = gsign;
+    }
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) atomicAdd(loss, s / (float)n);
+}
+int l1_loss(const float* a, const float* b, long long n, float scale, float* loss_out, float* d_a, const float* d_add,
+            cudaStream_t st) {
+  DG_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+  l1_kernel<<<ew_grid((size_t)n), 256, 0, st>>>(a, b, n, scale, loss_out, d_a, d_add);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+// g_loss = -gamma*mean(c_fake) + content_lambda*l1   (wasserstein.py:74,78)
+__global__ void gen_scalars_kernel(const float* __restrict__ scores, int B, const float* __restrict__ l1, float gamma,
+                                   float clam, float* __restrict__ scalars) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) s += scores[i];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) {
+    const float m = s / B;
+    scalars[1] = m;
+    scalars[2] = l1[0];
+    scalars[0] = -gamma * m + clam * l1[0];
+  }
+}
+int gen_scalars(const float* scores, int B, const float* l1, float gamma, float clam, float* scalars, cudaStream_t st) {
+  gen_scalars_kernel<<<1, 256, 0, st>>>(scores, B, l1, gamma, clam, scalars);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// fused Adam over a flat buffer (torch.optim.Adam semantics, no amsgrad/decay)
+// ---------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float b1, float b2, float eps, float step_size,
+                            float inv_sqrt_bc2, float gscale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  }
+}
+int adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int step,
+         float gscale, cudaStream_t st) {
+  const double bc1 = 1.0 - pow((double)b1, (double)step);
+  const double bc2 = 1.0 - pow((double)b2, (double)step);
+  adam_kernel<<<ew_grid((size_t)n), 256, 0, st>>>(p, g, m, v, n, b1, b2, eps, (float)(lr / bc1),
+                                                   (float)(1.0 / sqrt(bc2)), gscale);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dg
+
+extern "C" const char* dg_last_error(void) { return dg::last_error(); }
+extern "C" int64_t dg_launch_count(void) { return (int64_t)dg::g_launches.load(); }

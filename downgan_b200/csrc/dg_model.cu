@@ -1,0 +1,950 @@
+// Host-side orchestration of the generator, the critic and the fused WGAN-GP
+// iterations, plus the extern "C" surface declared in include/downgan_b200.h.
+// Reference statements replaced are cited per function (paths under
+// /root/reference/DoWnGAN).
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "dg_common.cuh"
+
+using namespace dg;
+
+namespace {
+
+constexpr float G_SLOPE = 0.01f;   // nn.LeakyReLU() default, networks/generator.py:26,72,79
+constexpr float C_SLOPE = 0.2f;    // networks/critic.py:24..87,97
+constexpr float RES_SCALE = 0.2f;  // networks/generator.py:19,45
+constexpr int FC_HIDDEN = 100;     // networks/critic.py:95
+
+struct Layer {
+  int Ci = 0, Co = 0, stride = 1;
+  long long w_off = 0, b_off = -1;    // offsets in the flat parameter buffer
+  long long pk_off = 0, pkb_off = -1; // offsets in the packed buffers (weights / bias area)
+  long long pkd_off = -1;             // packed data-gradient weights
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+int dev_alloc(std::vector<void*>& pool, void** out, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes) -> %s", bytes, cudaGetErrorString(e));
+    return DG_ERR_NOMEM;
+  }
+  e = cudaMemset(p, 0, bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaMemset -> %s", cudaGetErrorString(e));
+    return DG_ERR_CUDA;
+  }
+  pool.push_back(p);
+  *out = p;
+  return 0;
+}
+
+int run_conv(const ConvOp& op, cudaStream_t st) {
+  if (op.w_umma && umma_supported(op)) return conv_umma(op, st);
+  return conv_direct(op, st);
+}
+
+}  // namespace
+
+// ===========================================================================
+// Generator
+// ===========================================================================
+struct dg_generator {
+  dg_generator_config cfg{};
+  int bf = 0, F = 0, Hc = 0, R = 0, U = 0, Cin = 0, Cout = 0, Hf = 0, maxB = 0;
+  size_t esz = 4;
+  std::vector<Layer> layers;  // state_dict order: conv1, R*3*5 dense convs, conv2, U upsample convs, conv3.0, conv3.2
+  long long n_params = 0;
+  std::vector<void*> pool;
+  // packed parameters
+  float* pk = nullptr;       // forward weights + bias area
+  float* pkd = nullptr;      // data-gradient weights
+  float* gpk = nullptr;      // packed gradients (same offsets as pk)
+  long long pk_elems = 0, pkd_elems = 0;
+  PackDesc *tab_fwd = nullptr, *tab_dgrad = nullptr;
+  int n_fwd = 0, n_dgrad = 0, max_fwd = 0, max_dgrad = 0;
+  std::vector<long long> db_dgrad_off;  // [(r*3+d)*5 + k] packed offset of Wt_k
+  bool packed = false;
+  // activations
+  void* x0 = nullptr;
+  std::vector<void*> db;  // R*3 concat buffers (B,Hc,Hc,5F)
+  void *trunk_out = nullptr, *t1 = nullptr, *c30 = nullptr;
+  std::vector<void*> up;  // U post-shuffle activations
+  float* fake = nullptr;  // (B,Hf,Hf,Cout) NHWC fp32
+  // backward workspaces
+  void *D = nullptr, *gR = nullptr, *gx0 = nullptr, *gx1 = nullptr, *gT1 = nullptr, *gA = nullptr, *gB = nullptr;
+  float* dfake = nullptr;  // NHWC fp32
+  float* fine_nhwc = nullptr;
+  float* l1 = nullptr;
+  int saved_batch = 0;
+
+  int idx_conv1() const { return 0; }
+  int idx_db(int r, int d, int k) const { return 1 + (r * 3 + d) * 5 + (k - 1); }
+  int idx_conv2() const { return 1 + 15 * R; }
+  int idx_up(int u) const { return 2 + 15 * R + u; }
+  int idx_c30() const { return 2 + 15 * R + U; }
+  int idx_c32() const { return 3 + 15 * R + U; }
+  TV act(void* p, int pitch, int coff = 0) const { return tv(p, bf, pitch, coff); }
+};
+
+static void gen_enumerate(const dg_generator_config& c, std::vector<Layer>& L, long long& n_params) {
+  L.clear();
+  long long off = 0;
+  auto add = [&](int ci, int co) {
+    Layer l;
+    l.Ci = ci; l.Co = co; l.stride = 1;
+    l.w_off = off; off += (long long)co * ci * 9;
+    l.b_off = off; off += co;
+    L.push_back(l);
+  };
+  const int F = c.filters;
+  add(c.channels, F);
+  for (int r = 0; r < c.num_res_blocks; ++r)
+    for (int d = 0; d < 3; ++d)
+      for (int k = 1; k <= 5; ++k) add(k * F, F);
+  add(F, F);
+  for (int u = 0; u < c.num_upsample; ++u) add(F, 4 * F);
+  add(F, F);
+  add(F, c.n_predictands);
+  n_params = off;
+}
+
+extern "C" int64_t dg_generator_param_count(const dg_generator_config* cfg) {
+  if (!cfg) return -1;
+  std::vector<Layer> L; long long n;
+  gen_enumerate(*cfg, L, n);
+  return n;
+}
+extern "C" int64_t dg_generator_param_offset(const dg_generator_config* cfg, int index) {
+  if (!cfg || index < 0) return -1;
+  std::vector<Layer> L; long long n;
+  gen_enumerate(*cfg, L, n);
+  const int li = index / 2;
+  if (li >= (int)L.size()) return -1;
+  return (index & 1) ? L[li].b_off : L[li].w_off;
+}
+
+static int upload_table(std::vector<void*>& pool, const std::vector<PackDesc>& t, PackDesc** dev) {
+  DG_TRY(dev_alloc(pool, (void**)dev, sizeof(PackDesc) * std::max<size_t>(t.size(), 1)));
+  if (!t.empty()) DG_CUDA(cudaMemcpy(*dev, t.data(), sizeof(PackDesc) * t.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator** out) {
+  DG_CHECK(cfg && out, "dg_generator_create: null argument");
+  DG_CHECK(cfg->filters >= 1 && cfg->channels >= 1 && cfg->n_predictands >= 1 && cfg->num_res_blocks >= 0 &&
+               cfg->num_upsample >= 0 && cfg->num_upsample <= 5 && cfg->coarse_dim >= 1 && cfg->max_batch >= 1,
+           "dg_generator_create: bad config");
+  DG_CHECK(cfg->precision == DG_FP32 || cfg->precision == DG_BF16, "dg_generator_create: precision %d", cfg->precision);
+  dg_generator* g = new dg_generator();
+  g->cfg = *cfg;
+  g->bf = cfg->precision == DG_BF16;
+  g->esz = g->bf ? 2 : 4;
+  g->F = cfg->filters; g->Hc = cfg->coarse_dim; g->R = cfg->num_res_blocks; g->U = cfg->num_upsample;
+  g->Cin = cfg->channels; g->Cout = cfg->n_predictands; g->Hf = g->Hc << g->U; g->maxB = cfg->max_batch;
+  gen_enumerate(*cfg, g->layers, g->n_params);
+  const int F = g->F;
+  // ---- packed layouts + tables
+  std::vector<PackDesc> tf, td;
+  long long pk = 0, pkd = 0;
+  int maxf = 1, maxd = 1;
+  for (auto& l : g->layers) {
+    l.pk_off = pk; pk += (long long)packed_w_elems(l.Ci, l.Co);
+    PackDesc d{}; d.src_off = l.w_off; d.dst_off = l.pk_off; d.Ci = l.Ci; d.Co = l.Co; d.CoP = round_up(l.Co, 16); d.mode = 0;
+    tf.push_back(d);
+    maxf = std::max(maxf, l.Ci * l.Co * 9);
+  }
+  for (auto& l : g->layers) {
+    l.pkb_off = pk; pk += round_up(l.Co, 16);
+    PackDesc d{}; d.src_off = l.b_off; d.dst_off = l.pkb_off; d.Co = l.Co; d.Ci = 1; d.mode = 5;
+    tf.push_back(d);
+  }
+  g->pk_elems = pk;
+  // data-gradient weights: plain layers (flipped + transposed)
+  auto add_dgrad = [&](int li) {
+    Layer& l = g->layers[li];
+    l.pkd_off = pkd; pkd += (long long)packed_w_elems(l.Co, l.Ci);
+    PackDesc d{}; d.src_off = l.w_off; d.dst_off = l.pkd_off; d.Ci = l.Ci; d.Co = l.Co; d.CoP = round_up(l.Ci, 16); d.mode = 1;
+    td.push_back(d);
+    maxd = std::max(maxd, l.Ci * l.Co * 9);
+  };
+  add_dgrad(g->idx_conv1());
+  add_dgrad(g->idx_conv2());
+  for (int u = 0; u < g->U; ++u) add_dgrad(g->idx_up(u));
+  add_dgrad(g->idx_c30());
+  add_dgrad(g->idx_c32());
+  // dense blocks: Wt_k (k = 0..4) gathers slice k of W_j for j = k+1..5; rows ordered [dz5, dz4, ..., dz_{k+1}]
+  g->db_dgrad_off.assign((size_t)g->R * 3 * 5, 0);
+  for (int r = 0; r < g->R; ++r)
+    for (int dd = 0; dd < 3; ++dd)
+      for (int k = 0; k < 5; ++k) {
+        const int rows = (5 - k) * F;
+        const long long base = pkd;
+        g->db_dgrad_off[(size_t)(r * 3 + dd) * 5 + k] = base;
+        pkd += (long long)packed_w_elems(rows, F);
+        for (int j = k + 1; j <= 5; ++j) {
+          const Layer& l = g->layers[g->idx_db(r, dd, j)];
+          PackDesc d{};
+          d.src_off = l.w_off; d.dst_off = base; d.Ci = F; d.Co = F; d.CoP = rows; d.mode = 3;
+          d.slice_off = k * F; d.src_ci_total = j * F; d.dst_row_off = (5 - j) * F; d.dst_CoP = round_up(F, 16);
+          td.push_back(d);
+          maxd = std::max(maxd, F * F * 9);
+        }
+      }
+  g->pkd_elems = pkd;
+  g->n_fwd = (int)tf.size(); g->n_dgrad = (int)td.size(); g->max_fwd = maxf; g->max_dgrad = maxd;
+  int s = 0;
+#define GA(ptr, bytes) if ((s = dev_alloc(g->pool, (void**)&(ptr), (bytes))) != 0) { dg_generator_destroy(g); return s; }
+  GA(g->pk, sizeof(float) * pk);
+  GA(g->gpk, sizeof(float) * pk);
+  GA(g->pkd, sizeof(float) * std::max<long long>(pkd, 1));
+  if ((s = upload_table(g->pool, tf, &g->tab_fwd)) != 0) { dg_generator_destroy(g); return s; }
+  if ((s = upload_table(g->pool, td, &g->tab_dgrad)) != 0) { dg_generator_destroy(g); return s; }
+  // ---- activations
+  const size_t B = g->maxB, pc = (size_t)g->Hc * g->Hc, pf = (size_t)g->Hf * g->Hf;
+  GA(g->x0, B * pc * g->Cin * g->esz);
+  const int ndb = std::max(1, g->R * 3);
+  g->db.assign(ndb, nullptr);
+  for (int i = 0; i < ndb; ++i) GA(g->db[i], B * pc * 5 * F * g->esz);
+  GA(g->trunk_out, B * pc * F * g->esz);
+  GA(g->t1, B * pc * F * g->esz);
+  g->up.assign(g->U, nullptr);
+  for (int u = 0; u < g->U; ++u) GA(g->up[u], B * (pc << (2 * (u + 1))) * F * g->esz);
+  GA(g->c30, B * pf * F * g->esz);
+  GA(g->fake, B * pf * g->Cout * sizeof(float));
+  GA(g->dfake, B * pf * g->Cout * sizeof(float));
+  GA(g->fine_nhwc, B * pf * g->Cout * sizeof(float));
+  GA(g->l1, 64);
+  // backward
+  GA(g->D, B * pc * 5 * F * g->esz);
+  GA(g->gR, B * pc * F * g->esz);
+  GA(g->gx0, B * pc * F * g->esz);
+  GA(g->gx1, B * pc * F * g->esz);
+  GA(g->gT1, B * pc * F * g->esz);
+  GA(g->gA, B * pf * F * g->esz);   // also holds 4F channels at quarter resolution
+  GA(g->gB, B * pf * F * g->esz);
+#undef GA
+  *out = g;
+  return 0;
+}
+
+extern "C" int dg_generator_destroy(dg_generator* g) {
+  if (!g) return 0;
+  for (void* p : g->pool) cudaFree(p);
+  delete g;
+  return 0;
+}
+
+extern "C" int dg_generator_pack(dg_generator* g, const float* params, void* stream) {
+  DG_CHECK(g && params, "dg_generator_pack: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(pack_weights(params, g->pk, g->tab_fwd, g->n_fwd, g->max_fwd, st));
+  DG_TRY(pack_weights(params, g->pkd, g->tab_dgrad, g->n_dgrad, g->max_dgrad, st));
+  g->packed = true;
+  return 0;
+}
+
+// Generator.forward, networks/generator.py:83-90 (dense block :36-41, RRDB :52-53).
+// Input already in g->x0 (NHWC); output in g->fake (NHWC fp32).
+static int gen_forward_internal(dg_generator* g, int B, cudaStream_t st) {
+  const int F = g->F, Hc = g->Hc;
+  auto conv = [&](int li, TV x, int H, TV y) {
+    const Layer& l = g->layers[li];
+    ConvOp op;
+    op.x = x; op.Hin = H; op.Win = H; op.Ci = l.Ci;
+    op.y = y; op.Hout = H; op.Wout = H; op.Co = l.Co;
+    op.B = B; op.w = g->pk + l.pk_off; op.bias = g->pk + l.pkb_off;
+    return op;
+  };
+  void* first = g->R > 0 ? g->db[0] : g->trunk_out;
+  const int first_pitch = g->R > 0 ? 5 * F : F;
+  {
+    ConvOp op = conv(g->idx_conv1(), g->act(g->x0, g->Cin), Hc, g->act(first, first_pitch));
+    DG_TRY(run_conv(op, st));
+  }
+  for (int r = 0; r < g->R; ++r)
+    for (int d = 0; d < 3; ++d) {
+      void* buf = g->db[r * 3 + d];
+      for (int k = 1; k <= 4; ++k) {
+        ConvOp op = conv(g->idx_db(r, d, k), g->act(buf, 5 * F), Hc, g->act(buf, 5 * F, k * F));
+        op.act = ACT_LRELU; op.slope = G_SLOPE;
+        DG_TRY(run_conv(op, st));
+      }
+      const bool last_db = (r == g->R - 1 && d == 2);
+      void* nxt = last_db ? g->trunk_out : g->db[r * 3 + d + 1];
+      const int npitch = last_db ? F : 5 * F;
+      ConvOp op = conv(g->idx_db(r, d, 5), g->act(buf, 5 * F), Hc, g->act(nxt, npitch));
+      if (d < 2) {  // 0.2*o5 + x
+        op.s_acc = RES_SCALE; op.r1 = g->act(buf, 5 * F); op.s1 = 1.f;
+      } else {      // 0.2*(0.2*o5 + x_db) + x_rrdb
+        op.s_acc = RES_SCALE * RES_SCALE; op.r1 = g->act(buf, 5 * F); op.s1 = RES_SCALE;
+        op.r2 = g->act(g->db[r * 3], 5 * F); op.s2 = 1.f;
+      }
+      DG_TRY(run_conv(op, st));
+    }
+  {  // out1 + conv2(trunk)
+    ConvOp op = conv(g->idx_conv2(), g->act(g->trunk_out, F), Hc, g->act(g->t1, F));
+    if (g->R > 0) { op.r1 = g->act(g->db[0], 5 * F); op.s1 = 1.f; }
+    else { op.s_acc = 1.f; op.r1 = g->act(g->trunk_out, F); op.s1 = 1.f; }
+    DG_TRY(run_conv(op, st));
+  }
+  void* cur = g->t1;
+  int H = Hc;
+  for (int u = 0; u < g->U; ++u) {  // conv -> LeakyReLU -> PixelShuffle(2)
+    ConvOp op = conv(g->idx_up(u), g->act(cur, F), H, g->act(g->up[u], F));
+    op.act = ACT_LRELU; op.slope = G_SLOPE; op.shuffle = SHUF_PIXEL;
+    DG_TRY(run_conv(op, st));
+    cur = g->up[u];
+    H *= 2;
+  }
+  {
+    ConvOp op = conv(g->idx_c30(), g->act(cur, F), H, g->act(g->c30, F));
+    op.act = ACT_LRELU; op.slope = G_SLOPE;
+    DG_TRY(run_conv(op, st));
+  }
+  {
+    ConvOp op = conv(g->idx_c32(), g->act(g->c30, F), H, tv(g->fake, 0, g->Cout));
+    DG_TRY(run_conv(op, st));
+  }
+  g->saved_batch = B;
+  return 0;
+}
+
+extern "C" int dg_generator_fwd(dg_generator* g, const float* coarse, int batch, float* fake, int save, void* stream) {
+  (void)save;
+  DG_CHECK(g && coarse, "dg_generator_fwd: null argument");
+  DG_CHECK(batch >= 1 && batch <= g->maxB, "dg_generator_fwd: batch %d outside [1,%d]", batch, g->maxB);
+  if (!g->packed) { set_error("dg_generator_fwd: dg_generator_pack has not been called"); return DG_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), batch, g->Cin, g->Hc, g->Hc, st));
+  DG_TRY(gen_forward_internal(g, batch, st));
+  if (fake) DG_TRY(nhwc_to_nchw(tv(g->fake, 0, g->Cout), fake, batch, g->Cout, g->Hf, g->Hf, st));
+  return 0;
+}
+
+// Backward of Generator.forward given g->dfake (NHWC fp32); fills g->gpk and unpacks into grads_flat.
+static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_coarse, cudaStream_t st) {
+  const int B = g->saved_batch, F = g->F, Hc = g->Hc, Hf = g->Hf;
+  if (B <= 0) { set_error("generator backward without a saved forward"); return DG_ERR_STATE; }
+  DG_CUDA(cudaMemsetAsync(g->gpk, 0, sizeof(float) * g->pk_elems, st));
+  auto wgrad = [&](int li, TV x, int H, TV dy) {
+    const Layer& l = g->layers[li];
+    WgradOp w;
+    w.x = x; w.Hin = H; w.Win = H; w.Ci = l.Ci; w.dy = dy; w.Hout = H; w.Wout = H; w.Co = l.Co; w.B = B; w.stride = 1;
+    w.dw = g->gpk + l.pk_off; w.dbias = g->gpk + l.pkb_off;
+    return wgrad_direct(w, st);
+  };
+  auto dconv = [&](int li, TV dy, int H, TV dx) {  // data-gradient op of plain layer li: Ci_op = Co, Co_op = Ci
+    const Layer& l = g->layers[li];
+    ConvOp op;
+    op.x = dy; op.Hin = H; op.Win = H; op.Ci = l.Co;
+    op.y = dx; op.Hout = H; op.Wout = H; op.Co = l.Ci;
+    op.B = B; op.w = g->pkd + l.pkd_off;
+    return op;
+  };
+  void* last_up = g->U > 0 ? g->up[g->U - 1] : g->t1;
+  // conv3.2
+  DG_TRY(wgrad(g->idx_c32(), g->act(g->c30, F), Hf, tv(g->dfake, 0, g->Cout)));
+  {
+    ConvOp op = dconv(g->idx_c32(), tv(g->dfake, 0, g->Cout), Hf, g->act(g->gA, F));
+    op.act = ACT_MASK; op.slope = G_SLOPE; op.mask = g->act(g->c30, F);
+    DG_TRY(run_conv(op, st));
+  }
+  // conv3.0
+  DG_TRY(wgrad(g->idx_c30(), g->act(last_up, F), Hf, g->act(g->gA, F)));
+  void* gcur = nullptr;  // gradient w.r.t. the input of the layer just processed
+  {
+    ConvOp op = dconv(g->idx_c30(), g->act(g->gA, F), Hf, g->U > 0 ? g->act(g->gB, 4 * F) : g->act(g->gT1, F));
+    if (g->U > 0) {  // store un-shuffled and masked by the pre-shuffle LeakyReLU (sign taken from the shuffled copy)
+      op.shuffle = SHUF_UNPIXEL; op.act = ACT_MASK; op.slope = G_SLOPE; op.mask = g->act(last_up, F);
+    }
+    DG_TRY(run_conv(op, st));
+    gcur = g->U > 0 ? g->gB : g->gT1;
+  }
+  // upsample stages, last to first; gcur holds dz of stage u as (B, H, H, 4F)
+  void* ping = g->gA;
+  for (int u = g->U - 1; u >= 0; --u) {
+    const int H = Hc << u;
+    void* xin = u > 0 ? g->up[u - 1] : g->t1;
+    DG_TRY(wgrad(g->idx_up(u), g->act(xin, F), H, g->act(gcur, 4 * F)));
+    void* dst = u > 0 ? ping : g->gT1;
+    ConvOp op = dconv(g->idx_up(u), g->act(gcur, 4 * F), H, u > 0 ? g->act(dst, 4 * F) : g->act(dst, F));
+    if (u > 0) { op.shuffle = SHUF_UNPIXEL; op.act = ACT_MASK; op.slope = G_SLOPE; op.mask = g->act(xin, F); }
+    DG_TRY(run_conv(op, st));
+    ping = gcur;
+    gcur = dst;
+  }
+  // gT1 = dL/d(out1 + conv2(trunk))
+  DG_TRY(wgrad(g->idx_conv2(), g->act(g->trunk_out, F), Hc, g->act(g->gT1, F)));
+  {
+    ConvOp op = dconv(g->idx_conv2(), g->act(g->gT1, F), Hc, g->act(g->gR, F));
+    DG_TRY(run_conv(op, st));
+  }
+  const size_t pix = (size_t)B * Hc * Hc;
+  // trunk, RRDB by RRDB
+  void* gxs[2] = {g->gx0, g->gx1};
+  for (int r = g->R - 1; r >= 0; --r) {
+    // g->gR holds dL/d(RRDB_r output)
+    void* gin = g->gR;
+    float s_in = RES_SCALE;
+    for (int d = 2; d >= 0; --d) {
+      void* buf = g->db[r * 3 + d];
+      // dz5 = 0.2 * s_in * gin
+      DG_TRY(scale_add(g->act(g->D, 5 * F, 0), g->act(gin, F), RES_SCALE * s_in, TV(), 0.f, pix, F, st));
+      for (int k = 4; k >= 1; --k) {
+        ConvOp op;
+        op.x = g->act(g->D, 5 * F, 0); op.Hin = Hc; op.Win = Hc; op.Ci = (5 - k) * F;
+        op.y = g->act(g->D, 5 * F, (5 - k) * F); op.Hout = Hc; op.Wout = Hc; op.Co = F;
+        op.B = B; op.w = g->pkd + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + k];
+        op.act = ACT_MASK; op.slope = G_SLOPE; op.mask = g->act(buf, 5 * F, k * F);
+        DG_TRY(run_conv(op, st));
+      }
+      // weight gradients of b1..b5: x = buf[0:kF], dy = dz_k
+      for (int k = 1; k <= 5; ++k)
+        DG_TRY(wgrad(g->idx_db(r, d, k), g->act(buf, 5 * F, 0), Hc, g->act(g->D, 5 * F, (5 - k) * F)));
+      // gx = conv(D, Wt_0) + s_in*gin (+ gR when this is the RRDB's first block)
+      void* gout = (d == 0) ? g->gR : gxs[d & 1];
+      ConvOp op;
+      op.x = g->act(g->D, 5 * F, 0); op.Hin = Hc; op.Win = Hc; op.Ci = 5 * F;
+      op.y = g->act(gout, F); op.Hout = Hc; op.Wout = Hc; op.Co = F;
+      op.B = B; op.w = g->pkd + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + 0];
+      op.r1 = g->act(gin, F); op.s1 = s_in;
+      if (d == 0) { op.r2 = g->act(g->gR, F); op.s2 = 1.f; }
+      DG_TRY(run_conv(op, st));
+      gin = gout;
+      s_in = 1.f;
+    }
+  }
+  // dL/d(out1) = gR (through the trunk / conv2) + gT1 (long skip)
+  DG_TRY(scale_add(g->act(g->gx0, F), g->act(g->gR, F), 1.f, g->act(g->gT1, F), 1.f, pix, F, st));
+  DG_TRY(wgrad(g->idx_conv1(), g->act(g->x0, g->Cin), Hc, g->act(g->gx0, F)));
+  if (d_coarse) {
+    ConvOp op = dconv(g->idx_conv1(), g->act(g->gx0, F), Hc, g->act(g->gx1, g->Cin));
+    DG_TRY(run_conv(op, st));
+    DG_TRY(nhwc_to_nchw(g->act(g->gx1, g->Cin), d_coarse, B, g->Cin, Hc, Hc, st));
+  }
+  DG_TRY(unpack_wgrads(g->gpk, grads_flat, g->tab_fwd, g->n_fwd, g->max_fwd, st));
+  return 0;
+}
+
+extern "C" int dg_generator_bwd(dg_generator* g, const float* d_fake, float* grads_flat, float* d_coarse, void* stream) {
+  DG_CHECK(g && d_fake && grads_flat, "dg_generator_bwd: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g->saved_batch <= 0) { set_error("dg_generator_bwd: no saved forward"); return DG_ERR_STATE; }
+  DG_TRY(nchw_to_nhwc(d_fake, tv(g->dfake, 0, g->Cout), g->saved_batch, g->Cout, g->Hf, g->Hf, st));
+  return gen_backward_internal(g, grads_flat, d_coarse, st);
+}
+
+// ===========================================================================
+// Critic
+// ===========================================================================
+struct dg_critic {
+  dg_critic_config cfg{};
+  int bf = 0, W = 0, Hf = 0, nc = 0, maxB = 0, NBmax = 0, fc_in = 0, Hlast = 0, Clast = 0;
+  size_t esz = 4;
+  Layer L[8];
+  int Hin[8], Hout[8];
+  long long n_params = 0;
+  long long fc1w_off = 0, fc1b_off = 0, fc2w_off = 0, fc2b_off = 0;          // flat
+  long long pk_fc1w = 0, pk_fc1b = 0, pk_fc2w = 0, pk_fc2b = 0, pk_b0 = 0;   // packed
+  std::vector<void*> pool;
+  float *pk = nullptr, *pkd = nullptr, *gpk = nullptr;
+  long long pk_elems = 0, pkd_elems = 0;
+  PackDesc *tab_fwd = nullptr, *tab_dgrad = nullptr;
+  int n_fwd = 0, n_dgrad = 0, max_fwd = 0, max_dgrad = 0;
+  bool packed = false;
+  // activations for up to NBmax samples
+  float* a0 = nullptr;       // NHWC fp32 input batch
+  void* a[9] = {nullptr};    // a[1..8]
+  float *a9 = nullptr, *scores = nullptr, *seed = nullptr, *dz9 = nullptr, *vfc = nullptr;
+  void* dz[9] = {nullptr};   // dz[1..8]
+  float *g = nullptr, *u = nullptr;        // (maxB,Hf,Hf,nc) fp32
+  void *v0 = nullptr, *v1 = nullptr;       // JVP ping-pong
+  float *sumsq = nullptr, *coef = nullptr, *norms = nullptr, *scal = nullptr;
+  int saved_batch = 0;
+  TV act(void* p, int pitch, int coff = 0) const { return tv(p, bf, pitch, coff); }
+  size_t pix(int l) const { return (size_t)Hout[l] * Hout[l]; }  // l = 0..7 -> a[l+1]
+};
+
+static void critic_enumerate(const dg_critic_config& c, Layer* L, long long& fc1w, long long& fc1b, long long& fc2w,
+                             long long& fc2b, long long& n_params, int& fc_in) {
+  const int w = c.coarse_dim;
+  const int ci[8] = {c.nc, w, w, 2 * w, 2 * w, 4 * w, 4 * w, 8 * w};
+  const int co[8] = {w, w, 2 * w, 2 * w, 4 * w, 4 * w, 8 * w, 8 * w};
+  long long off = 0;
+  for (int i = 0; i < 8; ++i) {
+    L[i].Ci = ci[i]; L[i].Co = co[i]; L[i].stride = (i & 1) ? 2 : 1;
+    L[i].w_off = off; off += (long long)co[i] * ci[i] * 9;
+    if (i == 0) { L[i].b_off = off; off += co[i]; } else L[i].b_off = -1;
+  }
+  const int hl = c.fine_dim / 16;
+  fc_in = 8 * w * hl * hl;
+  fc1w = off; off += (long long)FC_HIDDEN * fc_in;
+  fc1b = off; off += FC_HIDDEN;
+  fc2w = off; off += FC_HIDDEN;
+  fc2b = off; off += 1;
+  n_params = off;
+}
+extern "C" int64_t dg_critic_param_count(const dg_critic_config* cfg) {
+  if (!cfg) return -1;
+  Layer L[8]; long long a, b, c, d, n; int k;
+  critic_enumerate(*cfg, L, a, b, c, d, n, k);
+  return n;
+}
+extern "C" int64_t dg_critic_param_offset(const dg_critic_config* cfg, int index) {
+  if (!cfg || index < 0) return -1;
+  Layer L[8]; long long a, b, c, d, n; int k;
+  critic_enumerate(*cfg, L, a, b, c, d, n, k);
+  // order: features.0.weight, features.0.bias, features.2.weight ... features.14.weight, classifier.0.{w,b}, classifier.2.{w,b}
+  if (index == 0) return L[0].w_off;
+  if (index == 1) return L[0].b_off;
+  if (index <= 8) return L[index - 1].w_off;
+  if (index == 9) return a;
+  if (index == 10) return b;
+  if (index == 11) return c;
+  if (index == 12) return d;
+  return -1;
+}
+
+extern "C" int dg_critic_create(const dg_critic_config* cfg, dg_critic** out) {
+  DG_CHECK(cfg && out, "dg_critic_create: null argument");
+  DG_CHECK(cfg->coarse_dim >= 1 && cfg->nc >= 1 && cfg->max_batch >= 1 && cfg->fine_dim >= 16 && cfg->fine_dim % 16 == 0,
+           "dg_critic_create: bad config (fine_dim must be a multiple of 16)");
+  DG_CHECK(cfg->precision == DG_FP32 || cfg->precision == DG_BF16, "dg_critic_create: precision %d", cfg->precision);
+  dg_critic* c = new dg_critic();
+  c->cfg = *cfg;
+  c->bf = cfg->precision == DG_BF16;
+  c->esz = c->bf ? 2 : 4;
+  c->W = cfg->coarse_dim; c->Hf = cfg->fine_dim; c->nc = cfg->nc; c->maxB = cfg->max_batch; c->NBmax = 3 * cfg->max_batch;
+  critic_enumerate(*cfg, c->L, c->fc1w_off, c->fc1b_off, c->fc2w_off, c->fc2b_off, c->n_params, c->fc_in);
+  int H = c->Hf;
+  for (int i = 0; i < 8; ++i) { c->Hin[i] = H; H = (c->L[i].stride == 2) ? H / 2 : H; c->Hout[i] = H; }
+  c->Hlast = H; c->Clast = 8 * c->W;
+  std::vector<PackDesc> tf, td;
+  long long pk = 0, pkd = 0;
+  int maxf = 1, maxd = 1;
+  for (int i = 0; i < 8; ++i) {
+    Layer& l = c->L[i];
+    l.pk_off = pk; pk += (long long)packed_w_elems(l.Ci, l.Co);
+    PackDesc d{}; d.src_off = l.w_off; d.dst_off = l.pk_off; d.Ci = l.Ci; d.Co = l.Co; d.CoP = round_up(l.Co, 16); d.mode = 0;
+    tf.push_back(d);
+    maxf = std::max(maxf, l.Ci * l.Co * 9);
+    l.pkd_off = pkd; pkd += (long long)packed_w_elems(l.Co, l.Ci);
+    PackDesc e{}; e.src_off = l.w_off; e.dst_off = l.pkd_off; e.Ci = l.Ci; e.Co = l.Co; e.CoP = round_up(l.Ci, 16);
+    e.mode = (l.stride == 2) ? 2 : 1;
+    td.push_back(e);
+    maxd = std::max(maxd, l.Ci * l.Co * 9);
+  }
+  auto add_copy = [&](long long src, long long& dst, int n) {
+    dst = pk; pk += round_up(n, 16);
+    PackDesc d{}; d.src_off = src; d.dst_off = dst; d.Co = n; d.Ci = 1; d.mode = 5;
+    tf.push_back(d);
+  };
+  add_copy(c->L[0].b_off, c->pk_b0, c->L[0].Co);
+  c->L[0].pkb_off = c->pk_b0;
+  {  // classifier.0.weight with NCHW -> NHWC column permutation (critic.py:103 flattens NCHW)
+    c->pk_fc1w = pk; pk += (long long)FC_HIDDEN * c->fc_in;
+    PackDesc d{}; d.src_off = c->fc1w_off; d.dst_off = c->pk_fc1w; d.Co = FC_HIDDEN; d.Ci = c->fc_in; d.mode = 4;
+    d.slice_off = c->Clast;
+    tf.push_back(d);
+    maxf = std::max(maxf, FC_HIDDEN * c->fc_in);
+  }
+  add_copy(c->fc1b_off, c->pk_fc1b, FC_HIDDEN);
+  add_copy(c->fc2w_off, c->pk_fc2w, FC_HIDDEN);
+  add_copy(c->fc2b_off, c->pk_fc2b, 1);
+  c->pk_elems = pk; c->pkd_elems = pkd;
+  c->n_fwd = (int)tf.size(); c->n_dgrad = (int)td.size(); c->max_fwd = maxf; c->max_dgrad = maxd;
+  int s = 0;
+#define CA(ptr, bytes) if ((s = dev_alloc(c->pool, (void**)&(ptr), (bytes))) != 0) { dg_critic_destroy(c); return s; }
+  CA(c->pk, sizeof(float) * pk);
+  CA(c->gpk, sizeof(float) * pk);
+  CA(c->pkd, sizeof(float) * pkd);
+  if ((s = upload_table(c->pool, tf, &c->tab_fwd)) != 0) { dg_critic_destroy(c); return s; }
+  if ((s = upload_table(c->pool, td, &c->tab_dgrad)) != 0) { dg_critic_destroy(c); return s; }
+  const size_t NB = c->NBmax, B = c->maxB, pf = (size_t)c->Hf * c->Hf;
+  CA(c->a0, NB * pf * c->nc * sizeof(float));
+  size_t vmax = 0;
+  for (int i = 0; i < 8; ++i) {
+    const size_t e = c->pix(i) * c->L[i].Co;
+    CA(c->a[i + 1], NB * e * c->esz);
+    CA(c->dz[i + 1], NB * e * c->esz);
+    vmax = std::max(vmax, e);
+  }
+  CA(c->a9, NB * FC_HIDDEN * sizeof(float));
+  CA(c->dz9, NB * FC_HIDDEN * sizeof(float));
+  CA(c->vfc, NB * FC_HIDDEN * sizeof(float));
+  CA(c->scores, NB * sizeof(float));
+  CA(c->seed, NB * sizeof(float));
+  CA(c->g, B * pf * c->nc * sizeof(float));
+  CA(c->u, B * pf * c->nc * sizeof(float));
+  CA(c->v0, B * vmax * c->esz);
+  CA(c->v1, B * vmax * c->esz);
+  CA(c->sumsq, B * sizeof(float));
+  CA(c->coef, B * sizeof(float));
+  CA(c->norms, B * sizeof(float));
+  CA(c->scal, 64);
+#undef CA
+  *out = c;
+  return 0;
+}
+extern "C" int dg_critic_destroy(dg_critic* c) {
+  if (!c) return 0;
+  for (void* p : c->pool) cudaFree(p);
+  delete c;
+  return 0;
+}
+extern "C" int dg_critic_pack(dg_critic* c, const float* params, void* stream) {
+  DG_CHECK(c && params, "dg_critic_pack: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(pack_weights(params, c->pk, c->tab_fwd, c->n_fwd, c->max_fwd, st));
+  DG_TRY(pack_weights(params, c->pkd, c->tab_dgrad, c->n_dgrad, c->max_dgrad, st));
+  c->packed = true;
+  return 0;
+}
+
+// Critic.forward (critic.py:101-106) over samples [0, NB) of c->a0.
+static int critic_forward_internal(dg_critic* c, int NB, cudaStream_t st) {
+  TV x = tv(c->a0, 0, c->nc);
+  for (int i = 0; i < 8; ++i) {
+    const Layer& l = c->L[i];
+    ConvOp op;
+    op.x = x; op.Hin = c->Hin[i]; op.Win = c->Hin[i]; op.Ci = l.Ci;
+    op.y = c->act(c->a[i + 1], l.Co); op.Hout = c->Hout[i]; op.Wout = c->Hout[i]; op.Co = l.Co;
+    op.B = NB; op.w = c->pk + l.pk_off; op.bias = (i == 0) ? c->pk + c->pk_b0 : nullptr;
+    op.stride = l.stride; op.act = ACT_LRELU; op.slope = C_SLOPE;
+    DG_TRY(run_conv(op, st));
+    x = op.y;
+  }
+  DG_TRY(fc_fwd(c->a[8], c->bf, c->pk + c->pk_fc1w, c->pk + c->pk_fc1b, c->a9, NB, c->fc_in, FC_HIDDEN, ACT_LRELU, C_SLOPE,
+                nullptr, st));
+  DG_TRY(fc2_fwd(c->a9, c->pk + c->pk_fc2w, c->pk + c->pk_fc2b, c->scores, NB, FC_HIDDEN, st));
+  return 0;
+}
+
+// Input-gradient chain for samples [0, NB) seeded by c->seed; layer-1 data
+// gradient only for samples [n0, n0+n1) into g_out (NHWC fp32) when n1 > 0.
+static int critic_backward_chain(dg_critic* c, int NB, int n0, int n1, float* g_out, cudaStream_t st) {
+  DG_TRY(fc2_seed(c->a9, c->pk + c->pk_fc2w, c->seed, c->dz9, NB, FC_HIDDEN, C_SLOPE, st));
+  DG_TRY(fc_dgrad(c->dz9, c->pk + c->pk_fc1w, c->dz[8], c->bf, NB, c->fc_in, FC_HIDDEN, c->a[8], c->bf, C_SLOPE, st));
+  for (int i = 7; i >= 1; --i) {  // dz[i] = dgrad_{i+1}(dz[i+1]) * lrelu'(a[i])
+    const Layer& l = c->L[i];
+    ConvOp op;
+    op.x = c->act(c->dz[i + 1], l.Co); op.Hin = c->Hout[i]; op.Win = c->Hout[i]; op.Ci = l.Co;
+    op.y = c->act(c->dz[i], l.Ci); op.Hout = c->Hin[i]; op.Wout = c->Hin[i]; op.Co = l.Ci;
+    op.B = NB; op.w = c->pkd + l.pkd_off;
+    op.transposed = (l.stride == 2);
+    op.act = ACT_MASK; op.slope = C_SLOPE; op.mask = c->act(c->a[i], l.Ci);
+    DG_TRY(run_conv(op, st));
+  }
+  if (n1 > 0) {
+    const Layer& l = c->L[0];
+    ConvOp op;
+    op.x = tv_batch(c->act(c->dz[1], l.Co), c->pix(0), n0); op.Hin = c->Hout[0]; op.Win = c->Hout[0]; op.Ci = l.Co;
+    op.y = tv(g_out, 0, l.Ci); op.Hout = c->Hin[0]; op.Wout = c->Hin[0]; op.Co = l.Ci;
+    op.B = n1; op.w = c->pkd + l.pkd_off;
+    DG_TRY(run_conv(op, st));
+  }
+  return 0;
+}
+
+// Weight gradients with x = saved activations, dy = dz, samples [n0, n0+n).
+static int critic_wgrads_acts(dg_critic* c, int n0, int n, cudaStream_t st) {
+  for (int i = 0; i < 8; ++i) {
+    const Layer& l = c->L[i];
+    WgradOp w;
+    const size_t pin = (size_t)c->Hin[i] * c->Hin[i];
+    w.x = (i == 0) ? tv_batch(tv(c->a0, 0, c->nc), pin, n0) : tv_batch(c->act(c->a[i], l.Ci), pin, n0);
+    w.Hin = c->Hin[i]; w.Win = c->Hin[i]; w.Ci = l.Ci;
+    w.dy = tv_batch(c->act(c->dz[i + 1], l.Co), c->pix(i), n0); w.Hout = c->Hout[i]; w.Wout = c->Hout[i]; w.Co = l.Co;
+    w.B = n; w.stride = l.stride;
+    w.dw = c->gpk + l.pk_off; w.dbias = (i == 0) ? c->gpk + c->pk_b0 : nullptr;
+    DG_TRY(wgrad_direct(w, st));
+  }
+  const size_t e8 = (size_t)c->fc_in;
+  const void* a8 = c->bf ? (const void*)((bf16*)c->a[8] + (size_t)n0 * e8) : (const void*)((float*)c->a[8] + (size_t)n0 * e8);
+  DG_TRY(fc_wgrad(c->dz9 + (size_t)n0 * FC_HIDDEN, a8, c->bf, c->gpk + c->pk_fc1w, n, c->fc_in, FC_HIDDEN, st));
+  DG_TRY(colsum(tv(c->dz9 + (size_t)n0 * FC_HIDDEN, 0, FC_HIDDEN), (size_t)n, FC_HIDDEN, c->gpk + c->pk_fc1b, st));
+  // classifier.2: dW2 = sum_b seed[b] * a9[b], db2 = sum_b seed[b]   (expressed as a 1-row fc_wgrad / colsum)
+  DG_TRY(fc_wgrad(c->seed + n0, c->a9 + (size_t)n0 * FC_HIDDEN, 0, c->gpk + c->pk_fc2w, n, FC_HIDDEN, 1, st));
+  DG_TRY(colsum(tv(c->seed + n0, 0, 1), (size_t)n, 1, c->gpk + c->pk_fc2b, st));
+  return 0;
+}
+
+// Gradient-penalty double backward: v_0 = u, dW_l += wgrad(v_{l-1}, dz_l),
+// v_l = m_l * conv_l(v_{l-1}); the interpolates are samples [n0, n0+B) of the saved batch.
+static int critic_gp_second_order(dg_critic* c, int n0, int B, cudaStream_t st) {
+  TV v = tv(c->u, 0, c->nc);
+  void* pp[2] = {c->v0, c->v1};
+  for (int i = 0; i < 8; ++i) {
+    const Layer& l = c->L[i];
+    WgradOp w;
+    w.x = v; w.Hin = c->Hin[i]; w.Win = c->Hin[i]; w.Ci = l.Ci;
+    w.dy = tv_batch(c->act(c->dz[i + 1], l.Co), c->pix(i), n0); w.Hout = c->Hout[i]; w.Wout = c->Hout[i]; w.Co = l.Co;
+    w.B = B; w.stride = l.stride; w.dw = c->gpk + l.pk_off; w.dbias = nullptr;
+    DG_TRY(wgrad_direct(w, st));
+    ConvOp op;
+    op.x = v; op.Hin = c->Hin[i]; op.Win = c->Hin[i]; op.Ci = l.Ci;
+    op.y = c->act(pp[i & 1], l.Co); op.Hout = c->Hout[i]; op.Wout = c->Hout[i]; op.Co = l.Co;
+    op.B = B; op.w = c->pk + l.pk_off; op.bias = nullptr; op.stride = l.stride;
+    op.act = ACT_MASK; op.slope = C_SLOPE; op.mask = tv_batch(c->act(c->a[i + 1], l.Co), c->pix(i), n0);
+    DG_TRY(run_conv(op, st));
+    v = op.y;
+  }
+  DG_TRY(fc_wgrad(c->dz9 + (size_t)n0 * FC_HIDDEN, v.p, c->bf, c->gpk + c->pk_fc1w, B, c->fc_in, FC_HIDDEN, st));
+  DG_TRY(fc_fwd(v.p, c->bf, c->pk + c->pk_fc1w, nullptr, c->vfc, B, c->fc_in, FC_HIDDEN, ACT_MASK, C_SLOPE,
+                c->a9 + (size_t)n0 * FC_HIDDEN, st));
+  DG_TRY(colsum(tv(c->vfc, 0, FC_HIDDEN), (size_t)B, FC_HIDDEN, c->gpk + c->pk_fc2w, st));
+  return 0;
+}
+
+static int critic_gp_first_order(dg_critic* c, const dg_hyper* hp, int n0, int B, float* scalars, int write_loss,
+                                 float* norms_out, cudaStream_t st) {
+  const size_t per = (size_t)c->Hf * c->Hf * c->nc;
+  DG_TRY(gp_norms(c->g, B, per, c->sumsq, st));
+  DG_TRY(gp_finish(c->sumsq, B, hp->gp_lambda, norms_out ? norms_out : c->norms, c->coef, scalars, write_loss, st));
+  DG_TRY(gp_scale(c->g, c->coef, c->u, B, per, st));
+  (void)n0;
+  return 0;
+}
+
+extern "C" int dg_critic_fwd(dg_critic* c, const float* x, int batch, float* scores, void* stream) {
+  DG_CHECK(c && x && scores, "dg_critic_fwd: null argument");
+  DG_CHECK(batch >= 1 && batch <= c->NBmax, "dg_critic_fwd: batch %d outside [1,%d]", batch, c->NBmax);
+  if (!c->packed) { set_error("dg_critic_fwd: dg_critic_pack has not been called"); return DG_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(nchw_to_nhwc(x, tv(c->a0, 0, c->nc), batch, c->nc, c->Hf, c->Hf, st));
+  DG_TRY(critic_forward_internal(c, batch, st));
+  DG_CUDA(cudaMemcpyAsync(scores, c->scores, sizeof(float) * batch, cudaMemcpyDeviceToDevice, st));
+  c->saved_batch = batch;
+  return 0;
+}
+
+extern "C" int dg_critic_bwd(dg_critic* c, const float* d_scores, float* grads_flat, float* d_x, void* stream) {
+  DG_CHECK(c && d_scores, "dg_critic_bwd: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = c->saved_batch;
+  if (B <= 0) { set_error("dg_critic_bwd: no saved forward"); return DG_ERR_STATE; }
+  DG_CHECK(!d_x || B <= c->maxB, "dg_critic_bwd: d_x needs batch <= max_batch");
+  DG_CUDA(cudaMemcpyAsync(c->seed, d_scores, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+  DG_TRY(critic_backward_chain(c, B, 0, d_x ? B : 0, c->g, st));
+  if (d_x) DG_TRY(nhwc_to_nchw(tv(c->g, 0, c->nc), d_x, B, c->nc, c->Hf, c->Hf, st));
+  if (grads_flat) {
+    DG_CUDA(cudaMemsetAsync(c->gpk, 0, sizeof(float) * c->pk_elems, st));
+    DG_TRY(critic_wgrads_acts(c, 0, B, st));
+    DG_TRY(unpack_wgrads(c->gpk, grads_flat, c->tab_fwd, c->n_fwd, c->max_fwd, st));
+  }
+  return 0;
+}
+
+// WassersteinGAN._gp (wasserstein.py:87-117).
+extern "C" int dg_gp(dg_critic* c, const dg_hyper* hp, const float* real, const float* fake, const float* alpha, int batch,
+                     float* gp_out, float* norms, float* grads_flat, void* stream) {
+  DG_CHECK(c && hp && real && fake && alpha && gp_out, "dg_gp: null argument");
+  DG_CHECK(batch >= 1 && batch <= c->maxB, "dg_gp: batch %d outside [1,%d]", batch, c->maxB);
+  if (!c->packed) { set_error("dg_gp: dg_critic_pack has not been called"); return DG_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(build_critic_input(real, fake, 1, alpha, c->a0, batch, c->nc, c->Hf, c->Hf, 1, st));
+  DG_TRY(critic_forward_internal(c, batch, st));
+  DG_TRY(fill(c->seed, 1.f, batch, st));
+  DG_TRY(critic_backward_chain(c, batch, 0, batch, c->g, st));
+  DG_TRY(critic_gp_first_order(c, hp, 0, batch, c->scal, 0, norms, st));
+  DG_CUDA(cudaMemcpyAsync(gp_out, c->scal + 3, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (grads_flat) {
+    DG_CUDA(cudaMemsetAsync(c->gpk, 0, sizeof(float) * c->pk_elems, st));
+    DG_TRY(critic_gp_second_order(c, 0, batch, st));
+    DG_TRY(unpack_wgrads(c->gpk, grads_flat, c->tab_fwd, c->n_fwd, c->max_fwd, st));
+  }
+  c->saved_batch = 0;
+  return 0;
+}
+
+// ===========================================================================
+// fused iterations
+// ===========================================================================
+__global__ void critic_seed_kernel(float* seed, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 3 * B) seed[i] = i < B ? -1.f / B : (i < 2 * B ? 1.f / B : 1.f);
+}
+
+// _critic_train_iteration, wasserstein.py:35-52 (everything except C_optimizer.step()).
+extern "C" int dg_critic_step(dg_generator* g, dg_critic* c, const dg_hyper* hp, const float* coarse, const float* fine,
+                              const float* alpha, int batch, float* c_grads_flat, float* scalars, void* stream) {
+  DG_CHECK(g && c && hp && coarse && fine && alpha && c_grads_flat && scalars, "dg_critic_step: null argument");
+  DG_CHECK(batch >= 1 && batch <= g->maxB && batch <= c->maxB, "dg_critic_step: batch %d too large", batch);
+  DG_CHECK(g->Hf == c->Hf && g->Cout == c->nc, "dg_critic_step: generator output does not match critic input");
+  if (!g->packed || !c->packed) { set_error("dg_critic_step: weights not packed"); return DG_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = batch;
+  DG_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(float), st));
+  // fake = G(coarse): the reference keeps the graph (:35) but discards the generator gradients (:65)
+  DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), B, g->Cin, g->Hc, g->Hc, st));
+  DG_TRY(gen_forward_internal(g, B, st));
+  g->saved_batch = 0;
+  // one 3B critic batch: [real ; fake ; alpha*real + (1-alpha)*fake]   (:37-38, :91-97)
+  DG_TRY(build_critic_input(fine, g->fake, 0, alpha, c->a0, B, c->nc, c->Hf, c->Hf, 0, st));
+  DG_TRY(critic_forward_internal(c, 3 * B, st));
+  DG_TRY(critic_means(c->scores, B, scalars, st));
+  critic_seed_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(c->seed, B);
+  DG_LAUNCH_CHECK();
+  DG_TRY(critic_backward_chain(c, 3 * B, 2 * B, B, c->g, st));
+  DG_TRY(critic_gp_first_order(c, hp, 2 * B, B, scalars, 1, nullptr, st));
+  DG_CUDA(cudaMemsetAsync(c->gpk, 0, sizeof(float) * c->pk_elems, st));
+  DG_TRY(critic_wgrads_acts(c, 0, 2 * B, st));
+  DG_TRY(critic_gp_second_order(c, 2 * B, B, st));
+  DG_TRY(unpack_wgrads(c->gpk, c_grads_flat, c->tab_fwd, c->n_fwd, c->max_fwd, st));
+  c->saved_batch = 0;
+  return 0;
+}
+
+// _generator_train_iteration, wasserstein.py:65-80 (everything except G_optimizer.step()).
+extern "C" int dg_generator_step(dg_generator* g, dg_critic* c, const dg_hyper* hp, const float* coarse, const float* fine,
+                                 int batch, float* g_grads_flat, float* scalars, void* stream) {
+  DG_CHECK(g && c && hp && coarse && fine && g_grads_flat && scalars, "dg_generator_step: null argument");
+  DG_CHECK(batch >= 1 && batch <= g->maxB && batch <= c->maxB, "dg_generator_step: batch %d too large", batch);
+  DG_CHECK(g->Hf == c->Hf && g->Cout == c->nc, "dg_generator_step: generator output does not match critic input");
+  if (!g->packed || !c->packed) { set_error("dg_generator_step: weights not packed"); return DG_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = batch;
+  const long long n = (long long)B * g->Hf * g->Hf * g->Cout;
+  DG_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(float), st));
+  DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), B, g->Cin, g->Hc, g->Hc, st));
+  DG_TRY(gen_forward_internal(g, B, st));
+  // c_fake = C(fake); adversarial seed d(-gamma*mean)/dscore = -gamma/B
+  DG_CUDA(cudaMemcpyAsync(c->a0, g->fake, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  DG_TRY(critic_forward_internal(c, B, st));
+  DG_TRY(fill(c->seed, -hp->gamma / B, B, st));
+  DG_TRY(critic_backward_chain(c, B, 0, B, c->g, st));
+  // content loss + its seed, added to the adversarial input-gradient   (wasserstein.py:78, losses.py:51-53)
+  DG_TRY(nchw_to_nhwc(fine, tv(g->fine_nhwc, 0, g->Cout), B, g->Cout, g->Hf, g->Hf, st));
+  DG_TRY(l1_loss(g->fake, g->fine_nhwc, n, hp->content_lambda, g->l1, g->dfake, c->g, st));
+  DG_TRY(gen_scalars(c->scores, B, g->l1, hp->gamma, hp->content_lambda, scalars, st));
+  DG_TRY(gen_backward_internal(g, g_grads_flat, nullptr, st));
+  c->saved_batch = 0;
+  return 0;
+}
+
+// ===========================================================================
+// misc exports
+// ===========================================================================
+extern "C" int dg_abi_version(void) { return DG_ABI_VERSION; }
+
+extern "C" int dg_l1_loss(const float* a, const float* b, int64_t n, float scale, float* loss_out, float* d_a, void* stream) {
+  DG_CHECK(a && b && loss_out && n > 0, "dg_l1_loss: bad argument");
+  return l1_loss(a, b, n, scale, loss_out, d_a, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int dg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                            float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+  DG_CHECK(params && grads && exp_avg && exp_avg_sq && n > 0 && step >= 1, "dg_adam_step: bad argument");
+  return adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, (cudaStream_t)stream);
+}
+
+// ---- conv primitives on NCHW fp32 tensors (unit tests) ---------------------
+namespace {
+struct Scratch {
+  std::vector<void*> pool;
+  ~Scratch() { for (void* p : pool) cudaFree(p); }
+};
+}  // namespace
+
+static int prim_setup(Scratch& s, int precision, const float* w, int ci, int co, int mode, float** pk, cudaStream_t st) {
+  (void)precision;
+  const bool dgrad = mode != 0;
+  const size_t elems = dgrad ? packed_w_elems(co, ci) : packed_w_elems(ci, co);
+  DG_TRY(dev_alloc(s.pool, (void**)pk, elems * sizeof(float)));
+  PackDesc d{}; d.src_off = 0; d.dst_off = 0; d.Ci = ci; d.Co = co; d.mode = mode;
+  d.CoP = dgrad ? round_up(ci, 16) : round_up(co, 16);
+  PackDesc* dev;
+  DG_TRY(dev_alloc(s.pool, (void**)&dev, sizeof(PackDesc)));
+  DG_CUDA(cudaMemcpyAsync(dev, &d, sizeof(d), cudaMemcpyHostToDevice, st));
+  DG_CUDA(cudaStreamSynchronize(st));
+  DG_TRY(pack_weights(w, *pk, dev, 1, ci * co * 9, st));
+  return 0;
+}
+
+extern "C" int dg_conv3x3_fwd(const float* x, const float* w, const float* bias, float* y, int batch, int ci, int co,
+                              int hin, int win, int stride, float slope, int precision, void* stream) {
+  DG_CHECK(x && w && y && (stride == 1 || stride == 2), "dg_conv3x3_fwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  Scratch s;
+  const int bf = precision == DG_BF16;
+  const size_t esz = bf ? 2 : 4;
+  const int ho = (hin - 1) / stride + 1, wo = (win - 1) / stride + 1;
+  float* pk; void *xi, *yo;
+  DG_TRY(prim_setup(s, precision, w, ci, co, 0, &pk, st));
+  DG_TRY(dev_alloc(s.pool, &xi, (size_t)batch * hin * win * ci * esz));
+  DG_TRY(dev_alloc(s.pool, &yo, (size_t)batch * ho * wo * co * esz));
+  DG_TRY(nchw_to_nhwc(x, tv(xi, bf, ci), batch, ci, hin, win, st));
+  ConvOp op;
+  op.x = tv(xi, bf, ci); op.Hin = hin; op.Win = win; op.Ci = ci;
+  op.y = tv(yo, bf, co); op.Hout = ho; op.Wout = wo; op.Co = co;
+  op.B = batch; op.w = pk; op.bias = bias; op.stride = stride;
+  if (slope != 1.f) { op.act = ACT_LRELU; op.slope = slope; }
+  DG_TRY(run_conv(op, st));
+  DG_TRY(nhwc_to_nchw(tv(yo, bf, co), y, batch, co, ho, wo, st));
+  DG_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int dg_conv3x3_dgrad(const float* dy, const float* w, float* dx, int batch, int ci, int co, int hin, int win,
+                                int stride, int precision, void* stream) {
+  DG_CHECK(dy && w && dx && (stride == 1 || stride == 2), "dg_conv3x3_dgrad: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  Scratch s;
+  const int bf = precision == DG_BF16;
+  const size_t esz = bf ? 2 : 4;
+  const int ho = (hin - 1) / stride + 1, wo = (win - 1) / stride + 1;
+  float* pk; void *dyi, *dxo;
+  DG_TRY(prim_setup(s, precision, w, ci, co, stride == 2 ? 2 : 1, &pk, st));
+  DG_TRY(dev_alloc(s.pool, &dyi, (size_t)batch * ho * wo * co * esz));
+  DG_TRY(dev_alloc(s.pool, &dxo, (size_t)batch * hin * win * ci * esz));
+  DG_TRY(nchw_to_nhwc(dy, tv(dyi, bf, co), batch, co, ho, wo, st));
+  ConvOp op;
+  op.x = tv(dyi, bf, co); op.Hin = ho; op.Win = wo; op.Ci = co;
+  op.y = tv(dxo, bf, ci); op.Hout = hin; op.Wout = win; op.Co = ci;
+  op.B = batch; op.w = pk; op.transposed = (stride == 2);
+  DG_TRY(run_conv(op, st));
+  DG_TRY(nhwc_to_nchw(tv(dxo, bf, ci), dx, batch, ci, hin, win, st));
+  DG_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int dg_conv3x3_wgrad(const float* x, const float* dy, float* dw, float* dbias, int batch, int ci, int co, int hin,
+                                int win, int stride, int precision, void* stream) {
+  DG_CHECK(x && dy && dw && (stride == 1 || stride == 2), "dg_conv3x3_wgrad: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  Scratch s;
+  const int bf = precision == DG_BF16;
+  const size_t esz = bf ? 2 : 4;
+  const int ho = (hin - 1) / stride + 1, wo = (win - 1) / stride + 1;
+  void *xi, *dyi; float *gpk, *gb;
+  DG_TRY(dev_alloc(s.pool, &xi, (size_t)batch * hin * win * ci * esz));
+  DG_TRY(dev_alloc(s.pool, &dyi, (size_t)batch * ho * wo * co * esz));
+  DG_TRY(dev_alloc(s.pool, (void**)&gpk, packed_w_elems(ci, co) * sizeof(float)));
+  DG_TRY(dev_alloc(s.pool, (void**)&gb, round_up(co, 16) * sizeof(float)));
+  DG_TRY(nchw_to_nhwc(x, tv(xi, bf, ci), batch, ci, hin, win, st));
+  DG_TRY(nchw_to_nhwc(dy, tv(dyi, bf, co), batch, co, ho, wo, st));
+  WgradOp w;
+  w.x = tv(xi, bf, ci); w.Hin = hin; w.Win = win; w.Ci = ci;
+  w.dy = tv(dyi, bf, co); w.Hout = ho; w.Wout = wo; w.Co = co; w.B = batch; w.stride = stride;
+  w.dw = gpk; w.dbias = dbias ? gb : nullptr;
+  DG_TRY(wgrad_direct(w, st));
+  PackDesc d{}; d.src_off = 0; d.dst_off = 0; d.Ci = ci; d.Co = co; d.CoP = round_up(co, 16); d.mode = 0;
+  PackDesc* dev;
+  DG_TRY(dev_alloc(s.pool, (void**)&dev, sizeof(PackDesc)));
+  DG_CUDA(cudaMemcpyAsync(dev, &d, sizeof(d), cudaMemcpyHostToDevice, st));
+  DG_CUDA(cudaStreamSynchronize(st));
+  DG_TRY(unpack_wgrads(gpk, dw, dev, 1, ci * co * 9, st));
+  if (dbias) DG_CUDA(cudaMemcpyAsync(dbias, gb, sizeof(float) * co, cudaMemcpyDeviceToDevice, st));
+  DG_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}

@@ -1,0 +1,173 @@
+/*
+ * downgan_b200.h — C ABI of libdowngan_b200.so
+ *
+ * B200 (sm_100a) implementation of the DoWnGAN WGAN-GP training iteration.
+ * The reference (nannau/DoWnGAN) has no FFI layer: its boundary is the Python
+ * class surface.  Each entry point below names the reference statement(s) it
+ * replaces (paths under /root/reference/DoWnGAN).  The Python host in
+ * downgan_b200/ binds these with ctypes; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative dg_status otherwise;
+ *     dg_last_error() returns a thread-local message for the last failure.
+ *   - no exceptions cross the ABI, no hidden device synchronisation, every
+ *     call enqueues on the cudaStream_t passed as `void* stream`.
+ *   - the caller owns all tensors handed in (device pointers unless stated);
+ *     handles own only packed weights and activation workspaces.
+ *   - user-facing tensors are contiguous NCHW fp32 (the reference layout);
+ *     parameters / gradients are ONE flat fp32 buffer per network holding the
+ *     tensors in the reference's state_dict() order, each OIHW / (out,in).
+ *   - one handle per device and per Python module; not thread-safe per handle.
+ */
+#ifndef DOWNGAN_B200_H
+#define DOWNGAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DG_ABI_VERSION 1
+
+typedef enum dg_status {
+  DG_OK = 0,
+  DG_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  DG_ERR_CUDA = -2,      /* CUDA runtime / driver error      */
+  DG_ERR_STATE = -3,     /* call order (e.g. bwd without saved fwd) */
+  DG_ERR_NOMEM = -4
+} dg_status;
+
+typedef enum dg_precision {
+  DG_FP32 = 0,  /* fp32 storage, CUDA-core FFMA convs: the <=1e-3 parity mode */
+  DG_BF16 = 1   /* bf16 storage, tcgen05/TMEM convs, fp32 accumulate          */
+} dg_precision;
+
+/* Constructor arguments of Generator (networks/generator.py:58). */
+typedef struct dg_generator_config {
+  int filters;         /* F; the reference passes the coarse grid edge (GAN/stage.py:60) */
+  int channels;        /* input covariates */
+  int n_predictands;   /* output channels (2: u10, v10) */
+  int num_res_blocks;  /* RRDB count, default 16 */
+  int num_upsample;    /* x2 pixel-shuffle stages, default 3 */
+  int coarse_dim;      /* H = W of the coarse grid */
+  int max_batch;
+  int precision;       /* dg_precision */
+} dg_generator_config;
+
+/* Constructor arguments of Critic (networks/critic.py:12). */
+typedef struct dg_critic_config {
+  int coarse_dim;      /* base width (GAN/stage.py:59) */
+  int fine_dim;        /* H = W of the fine grid, multiple of 16 */
+  int nc;              /* input channels */
+  int max_batch;       /* per-call batch; the fused critic step runs 3x this internally */
+  int precision;       /* dg_precision */
+} dg_critic_config;
+
+/* Hyper-parameters (config/hyperparams.py:16-22). */
+typedef struct dg_hyper {
+  float gp_lambda;       /* 10; applied twice as in wasserstein.py:40,117 */
+  float gamma;           /* 0.01 */
+  float content_lambda;  /* 5 */
+} dg_hyper;
+
+typedef struct dg_generator dg_generator;
+typedef struct dg_critic dg_critic;
+
+const char* dg_last_error(void);
+int dg_abi_version(void);
+/* 1 if the library was compiled with the tcgen05 conv path for sm_100a. */
+int dg_has_tcgen05(void);
+
+/* ---- handles ---------------------------------------------------------- */
+int dg_generator_create(const dg_generator_config* cfg, dg_generator** out);
+int dg_generator_destroy(dg_generator* g);
+int dg_critic_create(const dg_critic_config* cfg, dg_critic** out);
+int dg_critic_destroy(dg_critic* c);
+
+/* Number of fp32 elements of the flat parameter buffer, and the offset of
+ * the i-th state_dict tensor in it (i in reference order; returns -1 past the end). */
+int64_t dg_generator_param_count(const dg_generator_config* cfg);
+int64_t dg_generator_param_offset(const dg_generator_config* cfg, int index);
+int64_t dg_critic_param_count(const dg_critic_config* cfg);
+int64_t dg_critic_param_offset(const dg_critic_config* cfg, int index);
+
+/* Re-pack flat OIHW fp32 parameters into the kernels' layouts.  Must be
+ * called after every parameter change (optimizer step / load_state_dict). */
+int dg_generator_pack(dg_generator* g, const float* params_flat, void* stream);
+int dg_critic_pack(dg_critic* c, const float* params_flat, void* stream);
+
+/* ---- Generator.forward (networks/generator.py:83-90) -------------------
+ * coarse: (B, channels, H, H) NCHW fp32 -> fake: (B, n_predictands, 8H, 8H).
+ * save_for_backward != 0 keeps every dense-block buffer for dg_generator_bwd. */
+int dg_generator_fwd(dg_generator* g, const float* coarse, int batch, float* fake,
+                     int save_for_backward, void* stream);
+/* autograd of the above: d_fake NCHW fp32 -> grads_flat (overwritten, same
+ * layout as params_flat); d_coarse may be NULL. */
+int dg_generator_bwd(dg_generator* g, const float* d_fake, float* grads_flat,
+                     float* d_coarse, void* stream);
+
+/* ---- Critic.forward (networks/critic.py:101-106) -----------------------
+ * x: (B, nc, fine, fine) NCHW fp32 -> scores: (B) fp32. */
+int dg_critic_fwd(dg_critic* c, const float* x, int batch, float* scores, void* stream);
+/* autograd of the above: d_scores (B) -> grads_flat (overwritten), d_x NCHW (may be NULL). */
+int dg_critic_bwd(dg_critic* c, const float* d_scores, float* grads_flat, float* d_x, void* stream);
+
+/* ---- WassersteinGAN._gp (GAN/wasserstein.py:87-117) --------------------
+ * real, fake NCHW fp32, alpha (B) fp32 (injectable; the reference draws it
+ * with torch.rand).  Writes gp_out[0] = gp_lambda * mean((||g||-1)^2) (ONE
+ * lambda, as _gp returns), norms (B, may be NULL), and — when grads_flat is
+ * not NULL — d(gp_lambda * gp_out)/dparams (both lambdas, i.e. the term that
+ * enters critic_loss at wasserstein.py:40,49), via the closed-form
+ * double-backward (no autograd graph). */
+int dg_gp(dg_critic* c, const dg_hyper* hp, const float* real, const float* fake, const float* alpha,
+          int batch, float* gp_out, float* norms, float* grads_flat, void* stream);
+
+/* ---- content_loss (GAN/losses.py:40-55) --------------------------------
+ * loss_out[0] = mean |a-b| over n elements; if d_a != NULL writes
+ * scale * sign(a-b) / n  (the seed of hp.content_lambda * content_loss). */
+int dg_l1_loss(const float* a, const float* b, int64_t n, float scale, float* loss_out, float* d_a, void* stream);
+
+/* ---- torch.optim.Adam.step (GAN/stage.py:63-64; wasserstein.py:55,83) --
+ * one fused launch over a flat buffer; step is the 1-based step count.
+ * grad_scale multiplies the gradient first (1/world_size after a sum-allreduce). */
+int dg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+
+/* ---- fused iterations ---------------------------------------------------
+ * _critic_train_iteration (wasserstein.py:27-52, up to but excluding
+ * C_optimizer.step): generator forward (no graph), critic on real / fake /
+ * interpolates as one 3B batch, GP closed form, all critic gradients.
+ * scalars_out (device, 8 floats): [0] critic_loss [1] c_real_mean
+ * [2] c_fake_mean [3] gp (one lambda) [4] penalty (both lambdas) [5..7] 0.
+ * c_grads_flat is overwritten. */
+int dg_critic_step(dg_generator* g, dg_critic* c, const dg_hyper* hp,
+                   const float* coarse, const float* fine, const float* alpha, int batch,
+                   float* c_grads_flat, float* scalars_out, void* stream);
+/* _generator_train_iteration (wasserstein.py:65-80, excluding G_optimizer.step).
+ * scalars_out: [0] g_loss [1] c_fake_mean [2] l1 (unweighted) [3..7] 0. */
+int dg_generator_step(dg_generator* g, dg_critic* c, const dg_hyper* hp,
+                      const float* coarse, const float* fine, int batch,
+                      float* g_grads_flat, float* scalars_out, void* stream);
+
+/* ---- unit-testable conv primitives (NCHW fp32 in/out, OIHW fp32 weights)
+ * 3x3, padding 1, stride 1 or 2.  `precision` selects the kernel family.
+ * Replaces the cudnn_convolution / convolution_backward calls behind
+ * networks/generator.py:24 and networks/critic.py:21-86. */
+int dg_conv3x3_fwd(const float* x, const float* w, const float* bias, float* y,
+                   int batch, int ci, int co, int hin, int win, int stride, float lrelu_slope,
+                   int precision, void* stream);
+int dg_conv3x3_dgrad(const float* dy, const float* w, float* dx,
+                     int batch, int ci, int co, int hin, int win, int stride, int precision, void* stream);
+int dg_conv3x3_wgrad(const float* x, const float* dy, float* dw, float* dbias,
+                     int batch, int ci, int co, int hin, int win, int stride, int precision, void* stream);
+
+/* Number of kernel launches this library has enqueued since load (for bench.py's gpu_launches). */
+int64_t dg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOWNGAN_B200_H */

@@ -1,0 +1,110 @@
+"""CPU tests of the oracle itself: golden fixtures (generated from the real
+reference modules by oracle/make_golden.py) and the closed-form GP spec."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import networks as onet
+from oracle import trainer as otr
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    z = np.load(os.path.join(GOLD, "tiny.npz"))
+    t = {k: torch.from_numpy(z[k]) for k in z.files}
+    gspec = onet.GeneratorSpec(filters=8, channels=3, n_predictands=2, num_res_blocks=2, num_upsample=3)
+    cspec = onet.CriticSpec(coarse_dim=8, fine_dim=64, nc=2)
+    g_sd = {k[2:]: v for k, v in t.items() if k.startswith("G/")}
+    c_sd = {k[2:]: v for k, v in t.items() if k.startswith("C/")}
+    return t, gspec, cspec, g_sd, c_sd
+
+
+def test_state_dict_keys_follow_reference(tiny):
+    t, gspec, cspec, g_sd, c_sd = tiny
+    assert [k for k, _ in onet.generator_keys(gspec)] == list(g_sd.keys())
+    assert [k for k, _ in onet.critic_keys(cspec)] == list(c_sd.keys())
+    for k, shp in onet.generator_keys(gspec):
+        assert tuple(g_sd[k].shape) == shp
+    for k, shp in onet.critic_keys(cspec):
+        assert tuple(c_sd[k].shape) == shp
+
+
+def test_forward_matches_golden(tiny):
+    t, gspec, cspec, g_sd, c_sd = tiny
+    fake = onet.generator_forward(g_sd, gspec, t["coarse"])
+    assert torch.allclose(fake, t["fake"], rtol=0, atol=1e-6)
+    assert torch.allclose(onet.critic_forward(c_sd, cspec, t["fine"]), t["c_real"], rtol=0, atol=1e-6)
+    assert torch.allclose(onet.critic_forward(c_sd, cspec, t["fake"]), t["c_fake"], rtol=0, atol=1e-6)
+
+
+def test_steps_match_golden(tiny):
+    t, gspec, cspec, g_sd, c_sd = tiny
+    hp = otr.Hyper()
+    oc = otr.critic_loss_and_grads(g_sd, gspec, c_sd, cspec, t["coarse"], t["fine"], t["alpha"], hp)
+    assert torch.allclose(oc["loss"], t["critic_loss"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(oc["gp"], t["gp"], rtol=1e-5)
+    for k, v in oc["grads"].items():
+        ref = t["dC/" + k]
+        assert (v - ref).norm() <= 1e-4 * ref.norm() + 1e-7, k
+    og = otr.generator_loss_and_grads(g_sd, gspec, c_sd, cspec, t["coarse"], t["fine"], hp)
+    assert torch.allclose(og["loss"], t["gen_loss"], rtol=1e-5)
+    for k, v in og["grads"].items():
+        ref = t["dG/" + k]
+        assert (v - ref).norm() <= 1e-4 * ref.norm() + 1e-7, k
+
+
+def test_gp_closed_form_equals_autograd_fp64(tiny):
+    """The hand-written double backward (spec of the CUDA path) against create_graph autograd."""
+    t, gspec, cspec, g_sd, c_sd = tiny
+    hp = otr.Hyper()
+    torch.manual_seed(3)
+    # scale the critic so that ||grad|| straddles 1 (random init gives ~1e-4 and hides sign errors)
+    c64 = {k: v.double() * (1.9 if k.endswith("weight") and v.dim() == 4 else 1.0) for k, v in c_sd.items()}
+    real, fake, alpha = t["fine"].double(), t["fake"].double(), t["alpha"].double()
+    val, norms, gcf = otr.gp_param_grads_closed_form(c64, cspec, real, fake, alpha, hp)
+    cp = onet.as_leaf_params(c64)
+    gp, n2, _ = otr.gradient_penalty(cp, cspec, real, fake, alpha, hp)
+    ag = torch.autograd.grad(hp.gp_lambda * gp, list(cp.values()), allow_unused=True)
+    assert torch.allclose(val, hp.gp_lambda * gp, rtol=1e-12)
+    assert float(norms.min()) < 1.0 < float(norms.max()) or float(norms.mean()) > 1e-2
+    for (k, _p), a in zip(cp.items(), ag):
+        if a is None:
+            assert float(gcf[k].abs().max()) == 0.0, k
+        else:
+            assert (a - gcf[k]).norm() <= 1e-9 * (a.norm() + 1e-30), k
+
+
+def test_cfg1_summary_reproduces():
+    """BASELINE cfg-1 scalars recorded from the reference modules (make_golden.py)."""
+    with open(os.path.join(GOLD, "cfg1_summary.json")) as f:
+        s = json.load(f)
+    from downgan_b200.synthetic import synth_batch
+    gspec = onet.GeneratorSpec(filters=16, channels=2)
+    cspec = onet.CriticSpec(coarse_dim=16, fine_dim=128, nc=2)
+    torch.manual_seed(0)
+    c_sd = onet.init_critic_state(cspec)
+    g_sd = onet.init_generator_state(gspec)
+    coarse, fine, alpha = synth_batch(16, 2, 16)
+    with torch.no_grad():
+        fake = onet.generator_forward(g_sd, gspec, coarse[:2])
+    assert np.allclose(fake.flatten()[:8].numpy(), np.array(s["fake_sha_first8"]), atol=1e-6)
+
+
+def test_adam_matches_torch():
+    torch.manual_seed(0)
+    p = {"w": torch.randn(37)}
+    q = torch.nn.Parameter(p["w"].clone())
+    opt = torch.optim.Adam([q], 2.5e-4, betas=(0.9, 0.99))
+    st = otr.AdamState()
+    hp = otr.Hyper()
+    for i in range(5):
+        g = torch.randn(37)
+        q.grad = g.clone()
+        opt.step()
+        otr.adam_update(p, {"w": g}, st, hp)
+    assert torch.allclose(p["w"], q.detach(), atol=1e-7)
