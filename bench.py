@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — WGAN-GP train samples/s of the DoWnGAN iteration on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one batch of the reference's epoch loop (GAN/wasserstein.py:131-147):
+a critic iteration on a fresh batch, plus a generator iteration on the same batch
+when step % 5 == 0.  Workload = BASELINE.json configs[1]: 2-ch 16x16 -> 128x128,
+F=16, 16 RRDB, batch 64 per GPU, n_critic=5, synthetic ERA-shaped fields,
+random-init weights.  Data parallel is weak scaling: every rank trains on its own
+64-sample shard and the flat gradient buckets are all-reduced over NCCL.
+
+Prints ONE JSON line (rank 0).  `value` is timed with the batches resident in
+HBM; `e2e` is the same loop through the public trainer API with pinned HOST
+batches (H2D of every batch and D2H of the loss scalars inside the timed
+region).  `--impl reference` times the CPU oracle (the reference's PyTorch
+step restated in oracle/, pinned bit-exact against the reference modules) on
+the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "wgan_gp_train_samples_per_sec"
+CFG = dict(filters=16, channels=2, n_pred=2, rrdb=16, up=3, coarse=16, fine=128, batch=64, n_critic=5)
+# algorithmic conv+linear FLOPs per sample (necessary work only)
+F_G, F_C = 1.0347e9, 0.1998e9
+FLOPS_CRITIC_STEP = F_G + 10 * F_C
+FLOPS_GEN_STEP = 3 * F_G + 2 * F_C
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline leg and --impl reference)
+# ------------------------------------------------------------------------------------------
+def cpu_oracle_steps(n_steps: int, warmup: int, batch: int, seed: int = 0):
+    """Times `n_steps` steps of the schedule on the host with the oracle. Returns (seconds, samples)."""
+    from downgan_b200.synthetic import synth_batch
+    from oracle import networks as onet
+    from oracle import trainer as otr
+    torch.set_num_threads(os.cpu_count() or 1)
+    gspec = onet.GeneratorSpec(CFG["filters"], CFG["channels"], CFG["n_pred"], CFG["rrdb"], CFG["up"])
+    cspec = onet.CriticSpec(CFG["coarse"], CFG["fine"], CFG["n_pred"])
+    torch.manual_seed(seed)
+    c_sd = onet.init_critic_state(cspec)
+    g_sd = onet.init_generator_state(gspec)
+    tr = otr.OracleTrainer(g_sd, gspec, c_sd, cspec)
+    coarse, fine, alpha = synth_batch(batch, CFG["channels"], CFG["coarse"])
+    for _ in range(warmup):
+        tr.batch(coarse, fine, alpha)
+    tr.num_steps = 0
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        tr.batch(coarse, fine, alpha)
+    return time.perf_counter() - t0, n_steps * batch
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    sample_b = 16
+    secs, samples = cpu_oracle_steps(args.steps, args.warmup, sample_b)
+    val = samples / secs
+    cores = os.cpu_count() or 1
+    sample = (f"{args.steps} steps of the schedule (critic every step, generator every 5th) at batch {sample_b} "
+              f"(a quarter of each 64-sample batch), fp32, torch {torch.__version__} CPU, {cores} threads")
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, 1),
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def config_dict(args, world):
+    return {"workload": "cfg-2: DoWnGAN WGAN-GP, 2-ch (u10,v10) 16x16->128x128 (8x), F=16, 16 RRDB, batch 64 per GPU, "
+                        "n_critic=5 (critic every step, generator every 5th step)",
+            "global_batch": CFG["batch"] * world, "per_gpu_batch": CFG["batch"], "parallelism": f"dp{world}",
+            "precision": args.precision,
+            "l2_policy": "per-step working set (activations of a 192-sample critic batch, >1 GB) exceeds the 126 MB L2; "
+                         "8 distinct input batches are cycled"}
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("DOWNGAN_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch.distributed as dist
+    from downgan_b200 import _lib
+    from downgan_b200.GAN.wasserstein import WassersteinGAN
+    from downgan_b200.networks import Critic, Generator
+    from downgan_b200.synthetic import synth_batch
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    B = CFG["batch"]
+    torch.manual_seed(0)  # identical replicas on every rank
+    Cn = Critic(CFG["coarse"], CFG["fine"], CFG["n_pred"], precision=args.precision).to(dev)
+    Gn = Generator(CFG["filters"], CFG["fine"], CFG["channels"], CFG["n_pred"], CFG["rrdb"], CFG["up"],
+                   precision=args.precision).to(dev)
+    gopt = torch.optim.Adam(Gn.parameters(), 2.5e-4, betas=(0.9, 0.99))
+    copt = torch.optim.Adam(Cn.parameters(), 2.5e-4, betas=(0.9, 0.99))
+    tr = WassersteinGAN(Gn, Cn, gopt, copt)
+
+    NBATCH = 8
+    host = [synth_batch(B, CFG["channels"], CFG["coarse"], seed=1234 + 100 * rank + i, aseed=4321 + 100 * rank + i)
+            for i in range(NBATCH)]
+    host = [(c.pin_memory(), f.pin_memory(), a.pin_memory()) for c, f, a in host]
+    devb = [(c.to(dev), f.to(dev), a.to(dev)) for c, f, a in host]
+    h2d = sum(t.numel() * 4 for t in host[0])
+    d2h = 8 * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(steps, batches, read_scalars, step0=0):
+        for s in range(steps):
+            c, f, a = batches[(step0 + s) % NBATCH]
+            tr._critic_train_iteration(c, f, a)
+            if (step0 + s) % CFG["n_critic"] == 0:
+                tr._generator_train_iteration(c, f)
+            if read_scalars:
+                tr.last_critic.cpu()  # D2H of the step's loss scalars (synchronises, as a logging caller would)
+
+    def timed(steps, batches, read_scalars):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.dg_launch_count()
+        e0.record()
+        run(steps, batches, read_scalars)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), lib.dg_launch_count() - l0
+
+    # warm-up (also creates the native handles and workspaces)
+    run(args.warmup, devb, False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(args.steps, devb, False)
+    run(args.warmup, host, True)
+    ms_e2e, _ = timed(args.steps, host, True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel-class CUDA-event pass (same steps, events around every launch) ---------
+    prof = None
+    if not args.no_profile:
+        lib.dg_profile(1)
+        run(args.steps, devb, False)
+        buf = (C.c_double * (4 * len(_lib.PROFILE_CLASSES)))()
+        _lib.check(lib.dg_profile_report(buf, len(_lib.PROFILE_CLASSES)))
+        lib.dg_profile(0)
+        prof = {n: {"launches": int(buf[4 * i]), "ms": buf[4 * i + 1], "flops": buf[4 * i + 2], "bytes": buf[4 * i + 3]}
+                for i, n in enumerate(_lib.PROFILE_CLASSES) if buf[4 * i] > 0}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    samples = args.steps * B * world
+    value = samples / (ms * 1e-3)
+    e2e = samples / (ms_e2e * 1e-3)
+    hbm, tf_burst, tf_sus, which = peaks()
+    n_gen = (args.steps + CFG["n_critic"] - 1) // CFG["n_critic"]
+    alg_flops_per_rank = B * (args.steps * FLOPS_CRITIC_STEP + n_gen * FLOPS_GEN_STEP)
+
+    roofline = None
+    if prof:
+        conv = [k for k in prof if k in ("conv_direct", "wgrad_direct", "conv_tcgen05", "wgrad_tcgen05", "dense_block_tcgen05")]
+        dom = max(conv, key=lambda k: prof[k]["ms"])
+        d = prof[dom]
+        ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s",
+                    "frac": ach / tf_sus, "traffic": None, "peak_source": f"{which} (sustained cuBLAS bf16)",
+                    "launches": d["launches"], "avg_launch_us": 1e3 * d["ms"] / d["launches"],
+                    "share_of_profiled_time": d["ms"] / sum(v["ms"] for v in prof.values()),
+                    "whole_step_algorithmic_tflops": alg_flops_per_rank / (ms * 1e-3) / 1e12,
+                    "classes": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                                    "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 3) if v["flops"] else None,
+                                    "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)} for k, v in prof.items()},
+                    "hbm_peak_gbs": hbm}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        secs, smp = cpu_oracle_steps(5, 1, 16)
+        cores = os.cpu_count() or 1
+        cpu = {"value": smp / secs, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"5 steps of the schedule (5 critic + 1 generator iterations) at batch 16, fp32 oracle, {cores} threads"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": config_dict(args, world),
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "tcgen05": bool(lib.dg_has_tcgen05()),
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

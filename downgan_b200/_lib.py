@@ -43,6 +43,8 @@ _SIGNATURES = {
     "dg_abi_version": (C.c_int, []),
     "dg_has_tcgen05": (C.c_int, []),
     "dg_launch_count": (C.c_int64, []),
+    "dg_profile": (C.c_int, [C.c_int]),
+    "dg_profile_report": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
     "dg_generator_create": (C.c_int, [C.POINTER(GeneratorConfig), C.POINTER(_P)]),
     "dg_generator_destroy": (C.c_int, [_P]),
     "dg_critic_create": (C.c_int, [C.POINTER(CriticConfig), C.POINTER(_P)]),
@@ -70,6 +72,8 @@ _SIGNATURES = {
 }
 
 EXPORTS = tuple(_SIGNATURES.keys())
+PROFILE_CLASSES = ("conv_direct", "wgrad_direct", "conv_tcgen05", "wgrad_tcgen05", "dense_block_tcgen05", "linear",
+                   "l1_loss", "gp_norm", "adam", "interpolate", "layout")
 
 _lib: Optional[C.CDLL] = None
 

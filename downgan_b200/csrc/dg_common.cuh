@@ -54,6 +54,21 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
     }                                                                                    \
   } while (0)
 
+// ---- optional per-launch profiling (bench.py's roofline leg) ----------------
+// When enabled (dg_profile(1)) every wrapped launch is bracketed by CUDA events
+// on its own stream; dg_profile_report sums the durations per kernel class.
+enum ProfClass {
+  PC_CONV_DIRECT = 0, PC_WGRAD_DIRECT, PC_CONV_UMMA, PC_WGRAD_UMMA, PC_DENSE_UMMA, PC_FC,
+  PC_L1, PC_GP_NORMS, PC_ADAM, PC_INTERP, PC_LAYOUT, PC_COUNT
+};
+extern bool g_prof_on;
+struct Prof {
+  int idx = -1;
+  cudaStream_t st;
+  Prof(int cls, double flops, double bytes, cudaStream_t s);
+  ~Prof();
+};
+
 // ---- tensor views ---------------------------------------------------------
 // NHWC activation view: element (n,y,x,c) lives at p[((n*H + y)*W + x)*pitch + coff + c].
 // A dense-block concat buffer is ONE allocation with pitch = 5F; each conv
@@ -162,5 +177,9 @@ int gen_scalars(const float* scores, int B, const float* l1, float gamma, float 
 // tcgen05 path (dg_umma.cu)
 bool umma_supported(const ConvOp& op);
 int conv_umma(const ConvOp& op, cudaStream_t st);
+// bf16 re-pack of fp32 packed conv weights [tap][Ci][CoP] into the tcgen05 B-operand image
+// [(tap*Ci/8 + ci/8)][CoP][8]; element offsets are shared with the fp32 packed buffer.
+struct UmmaPackDesc { long long off; int Ci, CoP; };
+int pack_umma(const float* packed, void* dst_bf16, const UmmaPackDesc* table_dev, int n, int max_elems, cudaStream_t st);
 
 }  // namespace dg

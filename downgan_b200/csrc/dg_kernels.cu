@@ -20,6 +20,26 @@ void set_error(const char* fmt, ...) {
 const char* last_error() { return g_err; }
 
 // ---------------------------------------------------------------------------
+// profiling
+// ---------------------------------------------------------------------------
+bool g_prof_on = false;
+namespace {
+struct ProfRec { int cls; double flops, bytes; cudaEvent_t a, b; };
+std::vector<ProfRec> g_prof;
+}  // namespace
+Prof::Prof(int cls, double flops, double bytes, cudaStream_t s) : st(s) {
+  if (!g_prof_on) return;
+  ProfRec r; r.cls = cls; r.flops = flops; r.bytes = bytes;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  idx = (int)g_prof.size();
+  g_prof.push_back(r);
+}
+Prof::~Prof() {
+  if (idx >= 0) cudaEventRecord(g_prof[idx].b, st);
+}
+
+// ---------------------------------------------------------------------------
 // typed access through a TV
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float ldv(const void* p, int bf, size_t i) {
@@ -162,6 +182,9 @@ int conv_direct(const ConvOp& op, cudaStream_t st) {
   DG_CHECK(op.stride == 1 || op.stride == 2, "conv_direct: stride %d", op.stride);
   const long long total = (long long)op.B * op.Hout * op.Wout;
   dim3 grid((unsigned)((total + CONV_THREADS - 1) / CONV_THREADS), (unsigned)((op.Co + 15) / 16));
+  const double taps = op.transposed ? 2.25 : 9.0;
+  Prof prof(PC_CONV_DIRECT, 2.0 * total * op.Co * op.Ci * taps,
+            (double)total * op.Co * (op.y.bf ? 2 : 4) + (double)op.B * op.Hin * op.Win * op.Ci * (op.x.bf ? 2 : 4), st);
   conv_direct_kernel<<<grid, CONV_THREADS, 0, st>>>(op);
   DG_LAUNCH_CHECK();
   return 0;
@@ -235,15 +258,24 @@ int wgrad_direct(const WgradOp& op, cudaStream_t st) {
   if (ppb < 64) ppb = 64;
   if (ppb > 4096) ppb = 4096;
   dim3 grid((unsigned)((total + ppb - 1) / ppb), (unsigned)cic, (unsigned)coc);
+  Prof prof(PC_WGRAD_DIRECT, 2.0 * total * op.Co * op.Ci * 9.0,
+            (double)total * op.Co * (op.dy.bf ? 2 : 4) + (double)op.B * op.Hin * op.Win * op.Ci * (op.x.bf ? 2 : 4), st);
   wgrad_direct_kernel<<<grid, WG_THREADS, 0, st>>>(op, (int)ppb);
   DG_LAUNCH_CHECK();
   if (op.dbias) DG_TRY(colsum(op.dy, (size_t)total, op.Co, op.dbias, st));
   return 0;
 }
 
-// column sums over pixels (bias gradients); accumulates with atomics
+// column sums over pixels (bias gradients).  Block partials are combined in fp64 by the last
+// block to finish: critic bias gradients are sums of cancelling real/fake halves, and an fp32
+// atomic chain loses ~1e-3 of the result there.  out[c] += sum.
+constexpr int COLSUM_MAX_BLOCKS = 1024, COLSUM_MAX_C = 256;
+__device__ float g_colsum_part[COLSUM_MAX_BLOCKS * COLSUM_MAX_C];
+__device__ unsigned int g_colsum_done = 0;
+
 __global__ void colsum_kernel(TV dy, size_t pixels, int C, float* out, size_t pix_per_block) {
   __shared__ float sh[8][33];
+  __shared__ bool last;
   const size_t p0 = (size_t)blockIdx.x * pix_per_block;
   const size_t p1 = min(pixels, p0 + pix_per_block);
   for (int c0 = 0; c0 < C; c0 += 32) {
@@ -257,12 +289,24 @@ __global__ void colsum_kernel(TV dy, size_t pixels, int C, float* out, size_t pi
       float t = 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x];
-      atomicAdd(&out[c], t);
+      g_colsum_part[(size_t)blockIdx.x * C + c] = t;
     }
     __syncthreads();
   }
+  __threadfence();
+  if (threadIdx.x == 0 && threadIdx.y == 0) last = (atomicAdd(&g_colsum_done, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int c = threadIdx.y * 32 + threadIdx.x; c < C; c += 256) {
+    double t = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) t += (double)g_colsum_part[(size_t)b * C + c];
+    out[c] += (float)t;
+  }
+  if (threadIdx.x == 0 && threadIdx.y == 0) g_colsum_done = 0;
 }
 int colsum(TV dy, size_t pixels, int C, float* out, cudaStream_t st) {
+  DG_CHECK(C <= COLSUM_MAX_C, "colsum: %d channels > %d", C, COLSUM_MAX_C);
   size_t ppb = (pixels + 148 * 4 - 1) / (148 * 4);
   if (ppb < 64) ppb = 64;
   unsigned grid = (unsigned)((pixels + ppb - 1) / ppb);
@@ -410,6 +454,7 @@ __global__ void build_critic_input_kernel(const float* __restrict__ real, const 
 int build_critic_input(const float* real, const float* fake, int fake_is_nchw, const float* alpha, float* dst, int B,
                        int C, int H, int W, int mode, cudaStream_t st) {
   const size_t HW = (size_t)H * W;
+  Prof prof(PC_INTERP, 0.0, (double)HW * B * C * 4.0 * (mode == 0 ? 5.0 : 3.0), st);
   build_critic_input_kernel<<<ew_grid(HW * B), 256, 0, st>>>(real, fake, fake_is_nchw, alpha, dst, B, C, HW, mode);
   DG_LAUNCH_CHECK();
   return 0;
@@ -447,6 +492,7 @@ __global__ void fc_fwd_kernel(const void* __restrict__ x, int x_bf, const float*
 int fc_fwd(const void* x, int x_bf, const float* w, const float* bias, float* y, int NB, int K, int N, int act,
            float slope, const float* mask, cudaStream_t st) {
   const long long threads = (long long)NB * N * 32;
+  Prof prof(PC_FC, 2.0 * NB * N * K, (double)N * K * 4.0 + (double)NB * K * (x_bf ? 2 : 4), st);
   fc_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, x_bf, w, bias, y, NB, K, N, act, slope, mask);
   DG_LAUNCH_CHECK();
   return 0;
@@ -468,6 +514,7 @@ __global__ void fc_dgrad_kernel(const float* __restrict__ dz, const float* __res
 }
 int fc_dgrad(const float* dz, const float* w, void* dx, int dx_bf, int NB, int K, int N, const void* mask, int mask_bf,
              float slope, cudaStream_t st) {
+  Prof prof(PC_FC, 2.0 * NB * N * K, (double)N * K * 4.0 + (double)NB * K * (dx_bf ? 2 : 4), st);
   fc_dgrad_kernel<<<dim3((K + 255) / 256, NB), 256, N * sizeof(float), st>>>(dz, w, dx, dx_bf, K, N, mask, mask_bf, slope);
   DG_LAUNCH_CHECK();
   return 0;
@@ -484,6 +531,7 @@ __global__ void fc_wgrad_kernel(const float* __restrict__ dz, const void* __rest
   dw[(size_t)j * K + k] += s;
 }
 int fc_wgrad(const float* dz, const void* x, int x_bf, float* dw, int NB, int K, int N, cudaStream_t st) {
+  Prof prof(PC_FC, 2.0 * NB * N * K, (double)N * K * 8.0 + (double)NB * K * (x_bf ? 2 : 4), st);
   fc_wgrad_kernel<<<dim3((K + 255) / 256, N), 256, 0, st>>>(dz, x, x_bf, dw, NB, K, N);
   DG_LAUNCH_CHECK();
   return 0;
@@ -553,6 +601,7 @@ __global__ void gp_norms_kernel(const float* __restrict__ g, size_t per_sample, 
 }
 int gp_norms(const float* g, int B, size_t per_sample, float* sumsq, cudaStream_t st) {
   DG_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * B, st));
+  Prof prof(PC_GP_NORMS, 0.0, (double)per_sample * B * 4.0, st);
   unsigned bx = (unsigned)((per_sample / 4 + 1023) / 1024);
   if (bx < 1) bx = 1;
   if (bx > 32) bx = 32;
@@ -617,6 +666,7 @@ __global__ void l1_kernel(const float* __restrict__ a, const float* __restrict__
 int l1_loss(const float* a, const float* b, long long n, float scale, float* loss_out, float* d_a, const float* d_add,
             cudaStream_t st) {
   DG_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+  Prof prof(PC_L1, 0.0, (double)n * 4.0 * (2.0 + (d_a ? 1.0 : 0.0) + (d_add ? 1.0 : 0.0)), st);
   l1_kernel<<<ew_grid((size_t)n), 256, 0, st>>>(a, b, n, scale, loss_out, d_a, d_add);
   DG_LAUNCH_CHECK();
   return 0;
@@ -659,6 +709,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 int adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int step,
          float gscale, cudaStream_t st) {
+  Prof prof(PC_ADAM, 0.0, (double)n * 28.0, st);
   const double bc1 = 1.0 - pow((double)b1, (double)step);
   const double bc2 = 1.0 - pow((double)b2, (double)step);
   adam_kernel<<<ew_grid((size_t)n), 256, 0, st>>>(p, g, m, v, n, b1, b2, eps, (float)(lr / bc1),
@@ -670,4 +721,26 @@ int adam(float* p, const float* g, float* m, float* v, long long n, float lr, fl
 }  // namespace dg
 
 extern "C" const char* dg_last_error(void) { return dg::last_error(); }
+
+// Enable (1) / disable (0) per-launch event timing; enabling clears earlier records.
+extern "C" int dg_profile(int enable) {
+  if (enable) {
+    for (auto& r : dg::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    dg::g_prof.clear();
+  }
+  dg::g_prof_on = enable != 0;
+  return 0;
+}
+// out[cls*4 + {0,1,2,3}] = launches, total ms, algorithmic flops, algorithmic bytes. Synchronises the device.
+extern "C" int dg_profile_report(double* out, int n_classes) {
+  if (!out || n_classes < dg::PC_COUNT) { dg::set_error("dg_profile_report: need %d classes", (int)dg::PC_COUNT); return DG_ERR_INVALID; }
+  DG_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < n_classes * 4; ++i) out[i] = 0.0;
+  for (auto& r : dg::g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+    out[r.cls * 4 + 0] += 1.0; out[r.cls * 4 + 1] += ms; out[r.cls * 4 + 2] += r.flops; out[r.cls * 4 + 3] += r.bytes;
+  }
+  return 0;
+}
 extern "C" int64_t dg_launch_count(void) { return (int64_t)dg::g_launches.load(); }

@@ -72,6 +72,9 @@ struct dg_generator {
   long long pk_elems = 0, pkd_elems = 0;
   PackDesc *tab_fwd = nullptr, *tab_dgrad = nullptr;
   int n_fwd = 0, n_dgrad = 0, max_fwd = 0, max_dgrad = 0;
+  bf16 *pk_u = nullptr, *pkd_u = nullptr;  // tcgen05 B-operand images (bf16 mode)
+  UmmaPackDesc *utab_fwd = nullptr, *utab_dgrad = nullptr;
+  int n_ufwd = 0, n_udgrad = 0, max_ufwd = 1, max_udgrad = 1;
   std::vector<long long> db_dgrad_off;  // [(r*3+d)*5 + k] packed offset of Wt_k
   bool packed = false;
   // activations
@@ -139,6 +142,13 @@ static int upload_table(std::vector<void*>& pool, const std::vector<PackDesc>& t
   return 0;
 }
 
+static int upload_utable(std::vector<void*>& pool, const std::vector<UmmaPackDesc>& t, UmmaPackDesc** dev) {
+  DG_TRY(dev_alloc(pool, (void**)dev, sizeof(UmmaPackDesc) * std::max<size_t>(t.size(), 1)));
+  if (!t.empty()) DG_CUDA(cudaMemcpy(*dev, t.data(), sizeof(UmmaPackDesc) * t.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+static inline bool umma_ok(int ci, int co) { return ci % 16 == 0 && co % 16 == 0 && co <= 256; }
+
 extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator** out) {
   DG_CHECK(cfg && out, "dg_generator_create: null argument");
   DG_CHECK(cfg->filters >= 1 && cfg->channels >= 1 && cfg->n_predictands >= 1 && cfg->num_res_blocks >= 0 &&
@@ -202,13 +212,31 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
       }
   g->pkd_elems = pkd;
   g->n_fwd = (int)tf.size(); g->n_dgrad = (int)td.size(); g->max_fwd = maxf; g->max_dgrad = maxd;
+  std::vector<UmmaPackDesc> uf, ud;
+  if (g->bf) {
+    for (auto& l : g->layers)
+      if (umma_ok(l.Ci, l.Co)) { uf.push_back({l.pk_off, l.Ci, round_up(l.Co, 16)}); g->max_ufwd = std::max(g->max_ufwd, 9 * l.Ci * l.Co); }
+    for (auto& l : g->layers)
+      if (l.pkd_off >= 0 && umma_ok(l.Co, l.Ci)) { ud.push_back({l.pkd_off, l.Co, round_up(l.Ci, 16)}); g->max_udgrad = std::max(g->max_udgrad, 9 * l.Ci * l.Co); }
+    if (F % 16 == 0)
+      for (int i = 0; i < g->R * 3; ++i)
+        for (int k = 0; k < 5; ++k) {
+          ud.push_back({g->db_dgrad_off[(size_t)i * 5 + k], (5 - k) * F, round_up(F, 16)});
+          g->max_udgrad = std::max(g->max_udgrad, 9 * (5 - k) * F * F);
+        }
+  }
+  g->n_ufwd = (int)uf.size(); g->n_udgrad = (int)ud.size();
   int s = 0;
 #define GA(ptr, bytes) if ((s = dev_alloc(g->pool, (void**)&(ptr), (bytes))) != 0) { dg_generator_destroy(g); return s; }
   GA(g->pk, sizeof(float) * pk);
   GA(g->gpk, sizeof(float) * pk);
   GA(g->pkd, sizeof(float) * std::max<long long>(pkd, 1));
+  GA(g->pk_u, sizeof(bf16) * (pk + 64));
+  GA(g->pkd_u, sizeof(bf16) * (std::max<long long>(pkd, 1) + 64));
   if ((s = upload_table(g->pool, tf, &g->tab_fwd)) != 0) { dg_generator_destroy(g); return s; }
   if ((s = upload_table(g->pool, td, &g->tab_dgrad)) != 0) { dg_generator_destroy(g); return s; }
+  if ((s = upload_utable(g->pool, uf, &g->utab_fwd)) != 0) { dg_generator_destroy(g); return s; }
+  if ((s = upload_utable(g->pool, ud, &g->utab_dgrad)) != 0) { dg_generator_destroy(g); return s; }
   // ---- activations
   const size_t B = g->maxB, pc = (size_t)g->Hc * g->Hc, pf = (size_t)g->Hf * g->Hf;
   GA(g->x0, B * pc * g->Cin * g->esz);
@@ -249,6 +277,8 @@ extern "C" int dg_generator_pack(dg_generator* g, const float* params, void* str
   cudaStream_t st = (cudaStream_t)stream;
   DG_TRY(pack_weights(params, g->pk, g->tab_fwd, g->n_fwd, g->max_fwd, st));
   DG_TRY(pack_weights(params, g->pkd, g->tab_dgrad, g->n_dgrad, g->max_dgrad, st));
+  DG_TRY(pack_umma(g->pk, g->pk_u, g->utab_fwd, g->n_ufwd, g->max_ufwd, st));
+  DG_TRY(pack_umma(g->pkd, g->pkd_u, g->utab_dgrad, g->n_udgrad, g->max_udgrad, st));
   g->packed = true;
   return 0;
 }
@@ -263,6 +293,7 @@ static int gen_forward_internal(dg_generator* g, int B, cudaStream_t st) {
     op.x = x; op.Hin = H; op.Win = H; op.Ci = l.Ci;
     op.y = y; op.Hout = H; op.Wout = H; op.Co = l.Co;
     op.B = B; op.w = g->pk + l.pk_off; op.bias = g->pk + l.pkb_off;
+    if (g->bf) op.w_umma = g->pk_u + l.pk_off;
     return op;
   };
   void* first = g->R > 0 ? g->db[0] : g->trunk_out;
@@ -349,6 +380,7 @@ static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_co
     op.x = dy; op.Hin = H; op.Win = H; op.Ci = l.Co;
     op.y = dx; op.Hout = H; op.Wout = H; op.Co = l.Ci;
     op.B = B; op.w = g->pkd + l.pkd_off;
+    if (g->bf) op.w_umma = g->pkd_u + l.pkd_off;
     return op;
   };
   void* last_up = g->U > 0 ? g->up[g->U - 1] : g->t1;
@@ -405,6 +437,7 @@ static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_co
         op.x = g->act(g->D, 5 * F, 0); op.Hin = Hc; op.Win = Hc; op.Ci = (5 - k) * F;
         op.y = g->act(g->D, 5 * F, (5 - k) * F); op.Hout = Hc; op.Wout = Hc; op.Co = F;
         op.B = B; op.w = g->pkd + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + k];
+        if (g->bf) op.w_umma = g->pkd_u + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + k];
         op.act = ACT_MASK; op.slope = G_SLOPE; op.mask = g->act(buf, 5 * F, k * F);
         DG_TRY(run_conv(op, st));
       }
@@ -417,6 +450,7 @@ static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_co
       op.x = g->act(g->D, 5 * F, 0); op.Hin = Hc; op.Win = Hc; op.Ci = 5 * F;
       op.y = g->act(gout, F); op.Hout = Hc; op.Wout = Hc; op.Co = F;
       op.B = B; op.w = g->pkd + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + 0];
+      if (g->bf) op.w_umma = g->pkd_u + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + 0];
       op.r1 = g->act(gin, F); op.s1 = s_in;
       if (d == 0) { op.r2 = g->act(g->gR, F); op.s2 = 1.f; }
       DG_TRY(run_conv(op, st));
@@ -461,6 +495,9 @@ struct dg_critic {
   long long pk_elems = 0, pkd_elems = 0;
   PackDesc *tab_fwd = nullptr, *tab_dgrad = nullptr;
   int n_fwd = 0, n_dgrad = 0, max_fwd = 0, max_dgrad = 0;
+  bf16 *pk_u = nullptr, *pkd_u = nullptr;
+  UmmaPackDesc *utab_fwd = nullptr, *utab_dgrad = nullptr;
+  int n_ufwd = 0, n_udgrad = 0, max_ufwd = 1, max_udgrad = 1;
   bool packed = false;
   // activations for up to NBmax samples
   float* a0 = nullptr;       // NHWC fp32 input batch
@@ -563,13 +600,26 @@ extern "C" int dg_critic_create(const dg_critic_config* cfg, dg_critic** out) {
   add_copy(c->fc2b_off, c->pk_fc2b, 1);
   c->pk_elems = pk; c->pkd_elems = pkd;
   c->n_fwd = (int)tf.size(); c->n_dgrad = (int)td.size(); c->max_fwd = maxf; c->max_dgrad = maxd;
+  std::vector<UmmaPackDesc> uf, ud;
+  if (c->bf)
+    for (int i = 0; i < 8; ++i) {
+      const Layer& l = c->L[i];
+      if (l.stride != 1) continue;
+      if (umma_ok(l.Ci, l.Co)) { uf.push_back({l.pk_off, l.Ci, round_up(l.Co, 16)}); c->max_ufwd = std::max(c->max_ufwd, 9 * l.Ci * l.Co); }
+      if (umma_ok(l.Co, l.Ci)) { ud.push_back({l.pkd_off, l.Co, round_up(l.Ci, 16)}); c->max_udgrad = std::max(c->max_udgrad, 9 * l.Ci * l.Co); }
+    }
+  c->n_ufwd = (int)uf.size(); c->n_udgrad = (int)ud.size();
   int s = 0;
 #define CA(ptr, bytes) if ((s = dev_alloc(c->pool, (void**)&(ptr), (bytes))) != 0) { dg_critic_destroy(c); return s; }
   CA(c->pk, sizeof(float) * pk);
   CA(c->gpk, sizeof(float) * pk);
   CA(c->pkd, sizeof(float) * pkd);
+  CA(c->pk_u, sizeof(bf16) * (pk + 64));
+  CA(c->pkd_u, sizeof(bf16) * (pkd + 64));
   if ((s = upload_table(c->pool, tf, &c->tab_fwd)) != 0) { dg_critic_destroy(c); return s; }
   if ((s = upload_table(c->pool, td, &c->tab_dgrad)) != 0) { dg_critic_destroy(c); return s; }
+  if ((s = upload_utable(c->pool, uf, &c->utab_fwd)) != 0) { dg_critic_destroy(c); return s; }
+  if ((s = upload_utable(c->pool, ud, &c->utab_dgrad)) != 0) { dg_critic_destroy(c); return s; }
   const size_t NB = c->NBmax, B = c->maxB, pf = (size_t)c->Hf * c->Hf;
   CA(c->a0, NB * pf * c->nc * sizeof(float));
   size_t vmax = 0;
@@ -607,6 +657,8 @@ extern "C" int dg_critic_pack(dg_critic* c, const float* params, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DG_TRY(pack_weights(params, c->pk, c->tab_fwd, c->n_fwd, c->max_fwd, st));
   DG_TRY(pack_weights(params, c->pkd, c->tab_dgrad, c->n_dgrad, c->max_dgrad, st));
+  DG_TRY(pack_umma(c->pk, c->pk_u, c->utab_fwd, c->n_ufwd, c->max_ufwd, st));
+  DG_TRY(pack_umma(c->pkd, c->pkd_u, c->utab_dgrad, c->n_udgrad, c->max_udgrad, st));
   c->packed = true;
   return 0;
 }
@@ -620,6 +672,7 @@ static int critic_forward_internal(dg_critic* c, int NB, cudaStream_t st) {
     op.x = x; op.Hin = c->Hin[i]; op.Win = c->Hin[i]; op.Ci = l.Ci;
     op.y = c->act(c->a[i + 1], l.Co); op.Hout = c->Hout[i]; op.Wout = c->Hout[i]; op.Co = l.Co;
     op.B = NB; op.w = c->pk + l.pk_off; op.bias = (i == 0) ? c->pk + c->pk_b0 : nullptr;
+    if (c->bf && l.stride == 1) op.w_umma = c->pk_u + l.pk_off;
     op.stride = l.stride; op.act = ACT_LRELU; op.slope = C_SLOPE;
     DG_TRY(run_conv(op, st));
     x = op.y;
@@ -641,6 +694,7 @@ static int critic_backward_chain(dg_critic* c, int NB, int n0, int n1, float* g_
     op.x = c->act(c->dz[i + 1], l.Co); op.Hin = c->Hout[i]; op.Win = c->Hout[i]; op.Ci = l.Co;
     op.y = c->act(c->dz[i], l.Ci); op.Hout = c->Hin[i]; op.Wout = c->Hin[i]; op.Co = l.Ci;
     op.B = NB; op.w = c->pkd + l.pkd_off;
+    if (c->bf && l.stride == 1) op.w_umma = c->pkd_u + l.pkd_off;
     op.transposed = (l.stride == 2);
     op.act = ACT_MASK; op.slope = C_SLOPE; op.mask = c->act(c->a[i], l.Ci);
     DG_TRY(run_conv(op, st));
@@ -695,6 +749,7 @@ static int critic_gp_second_order(dg_critic* c, int n0, int B, cudaStream_t st) 
     op.x = v; op.Hin = c->Hin[i]; op.Win = c->Hin[i]; op.Ci = l.Ci;
     op.y = c->act(pp[i & 1], l.Co); op.Hout = c->Hout[i]; op.Wout = c->Hout[i]; op.Co = l.Co;
     op.B = B; op.w = c->pk + l.pk_off; op.bias = nullptr; op.stride = l.stride;
+    if (c->bf && l.stride == 1) op.w_umma = c->pk_u + l.pk_off;
     op.act = ACT_MASK; op.slope = C_SLOPE; op.mask = tv_batch(c->act(c->a[i + 1], l.Co), c->pix(i), n0);
     DG_TRY(run_conv(op, st));
     v = op.y;
@@ -856,8 +911,8 @@ struct Scratch {
 };
 }  // namespace
 
-static int prim_setup(Scratch& s, int precision, const float* w, int ci, int co, int mode, float** pk, cudaStream_t st) {
-  (void)precision;
+static int prim_setup(Scratch& s, int precision, const float* w, int ci, int co, int mode, float** pk, cudaStream_t st,
+                      bf16** pk_u = nullptr) {
   const bool dgrad = mode != 0;
   const size_t elems = dgrad ? packed_w_elems(co, ci) : packed_w_elems(ci, co);
   DG_TRY(dev_alloc(s.pool, (void**)pk, elems * sizeof(float)));
@@ -868,6 +923,18 @@ static int prim_setup(Scratch& s, int precision, const float* w, int ci, int co,
   DG_CUDA(cudaMemcpyAsync(dev, &d, sizeof(d), cudaMemcpyHostToDevice, st));
   DG_CUDA(cudaStreamSynchronize(st));
   DG_TRY(pack_weights(w, *pk, dev, 1, ci * co * 9, st));
+  if (pk_u) {
+    *pk_u = nullptr;
+    const int oci = dgrad ? co : ci, oco = dgrad ? ci : co;
+    if (precision == DG_BF16 && umma_ok(oci, oco) && mode != 2) {
+      DG_TRY(dev_alloc(s.pool, (void**)pk_u, (elems + 64) * sizeof(bf16)));
+      UmmaPackDesc u{0, oci, round_up(oco, 16)};
+      UmmaPackDesc* udev;
+      DG_TRY(dev_alloc(s.pool, (void**)&udev, sizeof(u)));
+      DG_CUDA(cudaMemcpy(udev, &u, sizeof(u), cudaMemcpyHostToDevice));
+      DG_TRY(pack_umma(*pk, *pk_u, udev, 1, (int)elems, st));
+    }
+  }
   return 0;
 }
 
@@ -879,15 +946,15 @@ extern "C" int dg_conv3x3_fwd(const float* x, const float* w, const float* bias,
   const int bf = precision == DG_BF16;
   const size_t esz = bf ? 2 : 4;
   const int ho = (hin - 1) / stride + 1, wo = (win - 1) / stride + 1;
-  float* pk; void *xi, *yo;
-  DG_TRY(prim_setup(s, precision, w, ci, co, 0, &pk, st));
+  float* pk; void *xi, *yo; bf16* pku;
+  DG_TRY(prim_setup(s, precision, w, ci, co, 0, &pk, st, &pku));
   DG_TRY(dev_alloc(s.pool, &xi, (size_t)batch * hin * win * ci * esz));
   DG_TRY(dev_alloc(s.pool, &yo, (size_t)batch * ho * wo * co * esz));
   DG_TRY(nchw_to_nhwc(x, tv(xi, bf, ci), batch, ci, hin, win, st));
   ConvOp op;
   op.x = tv(xi, bf, ci); op.Hin = hin; op.Win = win; op.Ci = ci;
   op.y = tv(yo, bf, co); op.Hout = ho; op.Wout = wo; op.Co = co;
-  op.B = batch; op.w = pk; op.bias = bias; op.stride = stride;
+  op.B = batch; op.w = pk; op.bias = bias; op.stride = stride; op.w_umma = pku;
   if (slope != 1.f) { op.act = ACT_LRELU; op.slope = slope; }
   DG_TRY(run_conv(op, st));
   DG_TRY(nhwc_to_nchw(tv(yo, bf, co), y, batch, co, ho, wo, st));
@@ -903,15 +970,15 @@ extern "C" int dg_conv3x3_dgrad(const float* dy, const float* w, float* dx, int 
   const int bf = precision == DG_BF16;
   const size_t esz = bf ? 2 : 4;
   const int ho = (hin - 1) / stride + 1, wo = (win - 1) / stride + 1;
-  float* pk; void *dyi, *dxo;
-  DG_TRY(prim_setup(s, precision, w, ci, co, stride == 2 ? 2 : 1, &pk, st));
+  float* pk; void *dyi, *dxo; bf16* pku;
+  DG_TRY(prim_setup(s, precision, w, ci, co, stride == 2 ? 2 : 1, &pk, st, &pku));
   DG_TRY(dev_alloc(s.pool, &dyi, (size_t)batch * ho * wo * co * esz));
   DG_TRY(dev_alloc(s.pool, &dxo, (size_t)batch * hin * win * ci * esz));
   DG_TRY(nchw_to_nhwc(dy, tv(dyi, bf, co), batch, co, ho, wo, st));
   ConvOp op;
   op.x = tv(dyi, bf, co); op.Hin = ho; op.Win = wo; op.Ci = co;
   op.y = tv(dxo, bf, ci); op.Hout = hin; op.Wout = win; op.Co = ci;
-  op.B = batch; op.w = pk; op.transposed = (stride == 2);
+  op.B = batch; op.w = pk; op.transposed = (stride == 2); op.w_umma = pku;
   DG_TRY(run_conv(op, st));
   DG_TRY(nhwc_to_nchw(tv(dxo, bf, ci), dx, batch, ci, hin, win, st));
   DG_CUDA(cudaStreamSynchronize(st));

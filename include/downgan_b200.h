@@ -167,6 +167,16 @@ int dg_conv3x3_wgrad(const float* x, const float* dy, float* dw, float* dbias,
 /* Number of kernel launches this library has enqueued since load (for bench.py's gpu_launches). */
 int64_t dg_launch_count(void);
 
+/* Per-launch CUDA-event timing for bench.py's roofline leg (no reference counterpart).
+ * dg_profile(1) clears and starts recording, dg_profile(0) stops.  dg_profile_report
+ * synchronises the device and writes, per kernel class c < DG_PROFILE_CLASSES,
+ * out[4c..4c+3] = {launches, total milliseconds, algorithmic FLOPs, algorithmic bytes}.
+ * Classes: 0 conv_direct 1 wgrad_direct 2 conv_tcgen05 3 wgrad_tcgen05 4 dense_block_tcgen05
+ * 5 linear 6 l1_loss 7 gp_norm 8 adam 9 interpolate 10 layout. */
+#define DG_PROFILE_CLASSES 11
+int dg_profile(int enable);
+int dg_profile_report(double* out, int n_classes);
+
 #ifdef __cplusplus
 }
 #endif

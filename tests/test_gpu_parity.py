@@ -180,18 +180,25 @@ def test_steps_cfg1(precision, scale):
     G, C, g_sd, c_sd = pu.build_pair(CFG1_G, CFG1_C, precision, seed=0, critic_scale=scale)
     coarse, fine, alpha = synth_batch(16, 2, 16)
     hp = otr.Hyper()
-    oc = otr.critic_loss_and_grads(g_sd, CFG1_G, c_sd, CFG1_C, coarse, fine, alpha, hp)
-    og = otr.generator_loss_and_grads(g_sd, CFG1_G, c_sd, CFG1_C, coarse, fine, hp)
+    # fp64 oracle = ground truth; the fp32 oracle (the reference's own dtype) gives the noise floor:
+    # a tensor passes at max(stated tolerance, 3 x the reference's own fp32-vs-fp64 error) — some
+    # bias gradients are sums of cancelling terms and sit at ~1.5e-3 in the reference itself.
+    oc = otr.critic_loss_and_grads(g_sd, CFG1_G, c_sd, CFG1_C, coarse, fine, alpha, hp, dtype=torch.float64)
+    og = otr.generator_loss_and_grads(g_sd, CFG1_G, c_sd, CFG1_C, coarse, fine, hp, dtype=torch.float64)
+    oc32 = otr.critic_loss_and_grads(g_sd, CFG1_G, c_sd, CFG1_C, coarse, fine, alpha, hp)
+    og32 = otr.generator_loss_and_grads(g_sd, CFG1_G, c_sd, CFG1_C, coarse, fine, hp)
     sc, cg, sg, gg = _run_steps(G, C, coarse, fine, alpha)
     tol = TOL_OUT[precision]
     assert abs(float(sc[0]) - float(oc["loss"])) <= tol * abs(float(oc["loss"]))
     assert abs(float(sc[1]) - float(oc["c_real_mean"])) <= tol * max(abs(float(oc["c_real_mean"])), 1e-3)
     assert abs(float(sc[3]) - float(oc["gp"])) <= tol * abs(float(oc["gp"]))
     assert abs(float(sg[0]) - float(og["loss"])) <= tol * abs(float(og["loss"]))
-    worst, wk, flat = pu.grad_report(cg, oc["grads"])
-    assert worst < TOL_GRAD_TENSOR[precision] and flat < TOL_GRAD_FLAT[precision], (wk, worst, flat)
-    worst, wk, flat = pu.grad_report(gg, og["grads"])
-    assert worst < TOL_GRAD_TENSOR[precision] and flat < TOL_GRAD_FLAT[precision], (wk, worst, flat)
+    for got, ref, ref32 in ((cg, oc["grads"], oc32["grads"]), (gg, og["grads"], og32["grads"])):
+        for k in ref:
+            floor = pu.rel(ref32[k], ref[k])
+            assert pu.rel(got[k], ref[k]) <= max(TOL_GRAD_TENSOR[precision], 3 * floor), (k, pu.rel(got[k], ref[k]), floor)
+        _w, _k, flat = pu.grad_report(got, ref)
+        assert flat < TOL_GRAD_FLAT[precision], flat
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
