@@ -180,6 +180,8 @@ int conv_umma(const ConvOp& op, cudaStream_t st);
 // bf16 re-pack of fp32 packed conv weights [tap][Ci][CoP] into the tcgen05 B-operand image
 // [(tap*Ci/8 + ci/8)][CoP][8]; element offsets are shared with the fp32 packed buffer.
 struct UmmaPackDesc { long long off; int Ci, CoP; };
+bool wgrad_umma_supported(const WgradOp& op);
+int wgrad_umma(const WgradOp& op, cudaStream_t st);
 int pack_umma(const float* packed, void* dst_bf16, const UmmaPackDesc* table_dev, int n, int max_elems, cudaStream_t st);
 
 }  // namespace dg

@@ -48,6 +48,11 @@ int dev_alloc(std::vector<void*>& pool, void** out, size_t bytes) {
   return 0;
 }
 
+int run_wgrad(const WgradOp& w, cudaStream_t st) {
+  if (wgrad_umma_supported(w)) return wgrad_umma(w, st);
+  return wgrad_direct(w, st);
+}
+
 int run_conv(const ConvOp& op, cudaStream_t st) {
   if (op.w_umma && umma_supported(op)) return conv_umma(op, st);
   return conv_direct(op, st);
@@ -372,7 +377,7 @@ static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_co
     WgradOp w;
     w.x = x; w.Hin = H; w.Win = H; w.Ci = l.Ci; w.dy = dy; w.Hout = H; w.Wout = H; w.Co = l.Co; w.B = B; w.stride = 1;
     w.dw = g->gpk + l.pk_off; w.dbias = g->gpk + l.pkb_off;
-    return wgrad_direct(w, st);
+    return run_wgrad(w, st);
   };
   auto dconv = [&](int li, TV dy, int H, TV dx) {  // data-gradient op of plain layer li: Ci_op = Co, Co_op = Ci
     const Layer& l = g->layers[li];
@@ -721,7 +726,7 @@ static int critic_wgrads_acts(dg_critic* c, int n0, int n, cudaStream_t st) {
     w.dy = tv_batch(c->act(c->dz[i + 1], l.Co), c->pix(i), n0); w.Hout = c->Hout[i]; w.Wout = c->Hout[i]; w.Co = l.Co;
     w.B = n; w.stride = l.stride;
     w.dw = c->gpk + l.pk_off; w.dbias = (i == 0) ? c->gpk + c->pk_b0 : nullptr;
-    DG_TRY(wgrad_direct(w, st));
+    DG_TRY(run_wgrad(w, st));
   }
   const size_t e8 = (size_t)c->fc_in;
   const void* a8 = c->bf ? (const void*)((bf16*)c->a[8] + (size_t)n0 * e8) : (const void*)((float*)c->a[8] + (size_t)n0 * e8);
@@ -744,7 +749,7 @@ static int critic_gp_second_order(dg_critic* c, int n0, int B, cudaStream_t st) 
     w.x = v; w.Hin = c->Hin[i]; w.Win = c->Hin[i]; w.Ci = l.Ci;
     w.dy = tv_batch(c->act(c->dz[i + 1], l.Co), c->pix(i), n0); w.Hout = c->Hout[i]; w.Wout = c->Hout[i]; w.Co = l.Co;
     w.B = B; w.stride = l.stride; w.dw = c->gpk + l.pk_off; w.dbias = nullptr;
-    DG_TRY(wgrad_direct(w, st));
+    DG_TRY(run_wgrad(w, st));
     ConvOp op;
     op.x = v; op.Hin = c->Hin[i]; op.Win = c->Hin[i]; op.Ci = l.Ci;
     op.y = c->act(pp[i & 1], l.Co); op.Hout = c->Hout[i]; op.Wout = c->Hout[i]; op.Co = l.Co;
@@ -1004,7 +1009,7 @@ extern "C" int dg_conv3x3_wgrad(const float* x, const float* dy, float* dw, floa
   w.x = tv(xi, bf, ci); w.Hin = hin; w.Win = win; w.Ci = ci;
   w.dy = tv(dyi, bf, co); w.Hout = ho; w.Wout = wo; w.Co = co; w.B = batch; w.stride = stride;
   w.dw = gpk; w.dbias = dbias ? gb : nullptr;
-  DG_TRY(wgrad_direct(w, st));
+  DG_TRY(run_wgrad(w, st));
   PackDesc d{}; d.src_off = 0; d.dst_off = 0; d.Ci = ci; d.Co = co; d.CoP = round_up(co, 16); d.mode = 0;
   PackDesc* dev;
   DG_TRY(dev_alloc(s.pool, (void**)&dev, sizeof(PackDesc)));

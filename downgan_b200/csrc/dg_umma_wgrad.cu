@@ -1,0 +1,230 @@
+// tcgen05 weight-gradient kernel for 3x3 convolutions (stride 1 and 2), sm_100a.
+//
+//   dW[tap][ci][co] = sum over output positions p of  x[p (+) tap][ci] * dy[p][co]
+//
+// is a GEMM whose contraction index is the pixel position.  Both operands are staged in shared
+// memory in the same "planar" layout the forward kernel uses,  [C/8 planes][positions][8 channels],
+// which is ALSO the tcgen05 canonical no-swizzle MN-major layout (8 channels contiguous, consecutive
+// K-steps = consecutive positions 16 B apart; LBO = 128 B between groups of 8 positions, SBO = plane
+// stride between groups of 8 channels).  So no transposition is needed: A = x^T (M = Ci, padded to
+// 128 lanes), B = dy (N = a chunk of Co), one descriptor start-address offset per tap, and the nine
+// per-tap accumulators (9 x NT columns) live in TMEM across all the tiles a CTA walks.  Stride-2
+// convolutions stage x as four parity sub-images so that every tap is again a constant offset.
+// Partial sums of different CTAs are combined with vectorised fp32 reductions (red.global.add.v4).
+#include "dg_umma.cuh"
+
+namespace dg {
+namespace {
+
+using namespace um;
+
+constexpr int WG_THREADS_U = 128;
+constexpr int WG_MAX_SMEM = 227 * 1024 - 2048;
+
+struct WgArgs {
+  WgradOp op;
+  int CoP;
+  int TH, PWt, npos16, PBx, PBd, nplx, npld, nsub;
+  int tiles_per_img, tiles_total, tiles_per_cta;
+  int NT, tmem_cols;
+  unsigned x_bytes, d_off, d_bytes;   // per-buffer x region size, offset of the dy buffers, per-buffer dy size
+};
+
+__global__ void __launch_bounds__(WG_THREADS_U) wgrad_umma_kernel(const WgArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ uint32_t tmem_slot;
+  const WgradOp& op = a.op;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int co0 = blockIdx.y * a.NT;
+  const int t_begin = blockIdx.x * a.tiles_per_cta;
+  const int t_end = min(a.tiles_total, t_begin + a.tiles_per_cta);
+  if (t_begin >= t_end) return;
+
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)a.tmem_cols);
+  if (tid == 32) { mbar_init(smem_u32(&mbar[0]), 1); mbar_init(smem_u32(&mbar[1]), 1); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t sbase = smem_u32(smem);
+  const int s = op.stride;
+  const bf16* xb = (const bf16*)op.x.p;
+  const bf16* db = (const bf16*)op.dy.p;
+  const uint32_t idesc = instr_desc(128, a.NT, 1, 1);
+  const int ksteps = a.npos16 >> 4;
+
+  int it = 0;
+  for (int t = t_begin; t < t_end; ++t, ++it) {
+    const int buf = it & 1;
+    if (it >= 2) mbar_wait(smem_u32(&mbar[buf]), ((it - 2) >> 1) & 1);  // MMAs that read this buffer are done
+    const int n = t / a.tiles_per_img;
+    const int y0 = (t - n * a.tiles_per_img) * a.TH;
+    const uint32_t sx = sbase + buf * a.x_bytes;
+    const uint32_t sd = sbase + a.d_off + buf * a.d_bytes;
+    // ---- x tile(s): every position of every real plane is written (zero fill outside the image)
+    const int xpos = a.PBx >> 4;
+    for (int sub = 0; sub < a.nsub; ++sub) {
+      const int py = sub >> 1, px = sub & 1;
+      const int total = xpos * a.nplx;
+      for (int i = tid; i < total; i += WG_THREADS_U) {
+        const int pos = i / a.nplx, pl = i - pos * a.nplx;
+        const int r = pos / a.PWt, c = pos - r * a.PWt;
+        int gy, gx;
+        bool ok;
+        if (s == 1) {
+          gy = y0 - 1 + r; gx = c - 1;
+          ok = r < a.TH + 2;
+        } else {
+          gy = 2 * (y0 - 1 + r) + py; gx = 2 * (c - 1) + px;
+          ok = r < a.TH + 1;
+        }
+        ok = ok && gy >= 0 && gy < op.Hin && gx >= 0 && gx < op.Win;
+        const bf16* src = ok ? xb + (((size_t)n * op.Hin + gy) * op.Win + gx) * op.x.pitch + op.x.coff + pl * 8 : xb;
+        cp_async16(sx + (sub * a.nplx + pl) * a.PBx + pos * 16, src, ok ? 16 : 0);
+      }
+    }
+    // ---- dy tile: pad columns and the rounding tail are zero
+    {
+      const int total = a.npos16 * a.npld;
+      for (int i = tid; i < total; i += WG_THREADS_U) {
+        const int pos = i / a.npld, pl = i - pos * a.npld;
+        const int r = pos / a.PWt, c = pos - r * a.PWt;
+        const int gy = y0 + r;
+        const bool ok = r < a.TH && gy < op.Hout && c < op.Wout;
+        const bf16* src = ok ? db + (((size_t)n * op.Hout + gy) * op.Wout + c) * op.dy.pitch + op.dy.coff + co0 + pl * 8 : db;
+        cp_async16(sd + pl * a.PBd + pos * 16, src, ok ? 16 : 0);
+      }
+    }
+    cp_async_wait_all();
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t bd = smem_desc(sd + ks * 256, 128, a.PBd);
+        const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap - 3 * ky;
+          int sub = 0, shift;
+          if (s == 1) {
+            shift = ky * a.PWt + kx;
+          } else {
+            sub = ((ky == 1) ? 0 : 2) + ((kx == 1) ? 0 : 1);
+            shift = ((ky == 0) ? 0 : 1) * a.PWt + ((kx == 0) ? 0 : 1);
+          }
+          const uint64_t ad = smem_desc(sx + sub * a.nplx * a.PBx + (shift + ks * 16) * 16, 128, a.PBx);
+          umma_f16(tmem + tap * a.NT, ad, bd, idesc, acc);
+        }
+      }
+      umma_commit(smem_u32(&mbar[buf]));
+    }
+    __syncwarp();
+  }
+  // ---- wait for the last MMAs of both buffers
+  {
+    const int last = it - 1;
+    mbar_wait(smem_u32(&mbar[last & 1]), (last >> 1) & 1);
+    if (it >= 2) mbar_wait(smem_u32(&mbar[(last - 1) & 1]), ((last - 1) >> 1) & 1);
+  }
+  tc_fence_after();
+  // ---- epilogue: lane = input channel ci, columns = [tap][co chunk]; fp32 reductions into dW
+  const int ci = tid;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  for (int tap = 0; tap < 9; ++tap) {
+    for (int nc = 0; nc < a.NT; nc += 16) {
+      float v[16];
+      tmem_ld16(tmem + lane_base + tap * a.NT + nc, v);
+      if (ci < op.Ci) {
+        float* dst = op.dw + ((size_t)tap * op.Ci + ci) * a.CoP + co0 + nc;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, (uint32_t)a.tmem_cols);
+}
+
+bool plan_wgrad(const WgradOp& op, WgArgs& a) {
+  if (!op.x.bf || !op.dy.bf) return false;
+  if (op.Ci % 16 || op.Co % 16 || op.Ci > 128 || op.Co > 256) return false;
+  if (op.x.pitch % 8 || op.x.coff % 8 || op.dy.pitch % 8 || op.dy.coff % 8) return false;
+  if (op.stride != 1 && op.stride != 2) return false;
+  if (op.stride == 2 && ((op.Hin & 1) || (op.Win & 1))) return false;
+  const int s = op.stride;
+  const int NT = (op.Co % 48 == 0) ? 48 : ((op.Co % 32 == 0) ? 32 : 16);
+  const int PWt = (s == 1) ? op.Wout + 2 : op.Wout + 1;
+  const int nplx = op.Ci / 8, npld = NT / 8, nsub = (s == 1) ? 1 : 4;
+  int bestTH = 0;
+  WgArgs b{};
+  for (int TH = 1; TH <= op.Hout; ++TH) {
+    const int npos16 = (TH * PWt + 15) & ~15;
+    if (TH > 1 && npos16 > 384) break;
+    const int xpos = (npos16 + 2 * PWt + 2 + 7) & ~7;
+    const unsigned PBx = xpos * 16, PBd = npos16 * 16;
+    const unsigned x_bytes = nsub * nplx * PBx, d_bytes = npld * PBd;
+    // the A descriptor always spans 16 planes (M = 128): the tail may alias later buffers but must stay inside smem
+    const unsigned span_end = x_bytes /*buffer 1 base*/ + (unsigned)((nsub - 1) * nplx + 16) * PBx;
+    unsigned total = 2 * x_bytes + 2 * d_bytes;
+    if (span_end > total) total = span_end;
+    if (total > (unsigned)WG_MAX_SMEM) break;
+    bestTH = TH;
+    b.TH = TH; b.PWt = PWt; b.npos16 = npos16; b.PBx = (int)PBx; b.PBd = (int)PBd;
+    b.x_bytes = x_bytes; b.d_off = 2 * x_bytes; b.d_bytes = d_bytes;
+  }
+  if (bestTH == 0) return false;
+  a = b;
+  a.op = op;
+  a.CoP = round_up(op.Co, 16);
+  a.nplx = nplx; a.npld = npld; a.nsub = nsub; a.NT = NT;
+  a.tiles_per_img = (op.Hout + a.TH - 1) / a.TH;
+  a.tiles_total = a.tiles_per_img * op.B;
+  int cols = 9 * NT, pc = 32;
+  while (pc < cols) pc <<= 1;
+  a.tmem_cols = pc;
+  return true;
+}
+
+unsigned smem_total(const WgArgs& a) {
+  const unsigned span_end = a.x_bytes + (unsigned)((a.nsub - 1) * a.nplx + 16) * a.PBx;
+  unsigned total = 2 * a.x_bytes + 2 * a.d_bytes;
+  return span_end > total ? span_end : total;
+}
+
+}  // namespace
+
+bool wgrad_umma_supported(const WgradOp& op) {
+  WgArgs a;
+  return plan_wgrad(op, a);
+}
+
+int wgrad_umma(const WgradOp& op, cudaStream_t st) {
+  WgArgs a;
+  if (!plan_wgrad(op, a)) { set_error("wgrad_umma: unsupported shape"); return DG_ERR_INVALID; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    DG_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_MAX_SMEM));
+    attr_set = true;
+  }
+  const int n_chunks = op.Co / a.NT;
+  // position split: enough CTAs to fill the chip, bounded so that the cross-CTA reductions stay small
+  long long S = (2 * 148 + n_chunks - 1) / n_chunks;
+  const long long cap = 3000000LL / (9LL * op.Ci * op.Co) + 1;
+  if (S > cap) S = cap;
+  if (S > a.tiles_total) S = a.tiles_total;
+  if (S < 1) S = 1;
+  a.tiles_per_cta = (int)((a.tiles_total + S - 1) / S);
+  S = (a.tiles_total + a.tiles_per_cta - 1) / a.tiles_per_cta;
+  const long long total = (long long)op.B * op.Hout * op.Wout;
+  Prof prof(PC_WGRAD_UMMA, 2.0 * total * op.Co * op.Ci * 9.0,
+            (double)total * op.Co * 2.0 + (double)op.B * op.Hin * op.Win * op.Ci * 2.0, st);
+  wgrad_umma_kernel<<<dim3((unsigned)S, (unsigned)n_chunks), WG_THREADS_U, smem_total(a), st>>>(a);
+  DG_LAUNCH_CHECK();
+  if (op.dbias) DG_TRY(colsum(op.dy, (size_t)total, op.Co, op.dbias, st));
+  return 0;
+}
+
+}  // namespace dg
