@@ -609,7 +609,6 @@ extern "C" int dg_critic_create(const dg_critic_config* cfg, dg_critic** out) {
   if (c->bf)
     for (int i = 0; i < 8; ++i) {
       const Layer& l = c->L[i];
-      if (l.stride != 1) continue;
       if (umma_ok(l.Ci, l.Co)) { uf.push_back({l.pk_off, l.Ci, round_up(l.Co, 16)}); c->max_ufwd = std::max(c->max_ufwd, 9 * l.Ci * l.Co); }
       if (umma_ok(l.Co, l.Ci)) { ud.push_back({l.pkd_off, l.Co, round_up(l.Ci, 16)}); c->max_udgrad = std::max(c->max_udgrad, 9 * l.Ci * l.Co); }
     }
@@ -677,7 +676,7 @@ static int critic_forward_internal(dg_critic* c, int NB, cudaStream_t st) {
     op.x = x; op.Hin = c->Hin[i]; op.Win = c->Hin[i]; op.Ci = l.Ci;
     op.y = c->act(c->a[i + 1], l.Co); op.Hout = c->Hout[i]; op.Wout = c->Hout[i]; op.Co = l.Co;
     op.B = NB; op.w = c->pk + l.pk_off; op.bias = (i == 0) ? c->pk + c->pk_b0 : nullptr;
-    if (c->bf && l.stride == 1) op.w_umma = c->pk_u + l.pk_off;
+    if (c->bf) op.w_umma = c->pk_u + l.pk_off;
     op.stride = l.stride; op.act = ACT_LRELU; op.slope = C_SLOPE;
     DG_TRY(run_conv(op, st));
     x = op.y;
@@ -699,7 +698,7 @@ static int critic_backward_chain(dg_critic* c, int NB, int n0, int n1, float* g_
     op.x = c->act(c->dz[i + 1], l.Co); op.Hin = c->Hout[i]; op.Win = c->Hout[i]; op.Ci = l.Co;
     op.y = c->act(c->dz[i], l.Ci); op.Hout = c->Hin[i]; op.Wout = c->Hin[i]; op.Co = l.Ci;
     op.B = NB; op.w = c->pkd + l.pkd_off;
-    if (c->bf && l.stride == 1) op.w_umma = c->pkd_u + l.pkd_off;
+    if (c->bf) op.w_umma = c->pkd_u + l.pkd_off;
     op.transposed = (l.stride == 2);
     op.act = ACT_MASK; op.slope = C_SLOPE; op.mask = c->act(c->a[i], l.Ci);
     DG_TRY(run_conv(op, st));
@@ -754,7 +753,7 @@ static int critic_gp_second_order(dg_critic* c, int n0, int B, cudaStream_t st) 
     op.x = v; op.Hin = c->Hin[i]; op.Win = c->Hin[i]; op.Ci = l.Ci;
     op.y = c->act(pp[i & 1], l.Co); op.Hout = c->Hout[i]; op.Wout = c->Hout[i]; op.Co = l.Co;
     op.B = B; op.w = c->pk + l.pk_off; op.bias = nullptr; op.stride = l.stride;
-    if (c->bf && l.stride == 1) op.w_umma = c->pk_u + l.pk_off;
+    if (c->bf) op.w_umma = c->pk_u + l.pk_off;
     op.act = ACT_MASK; op.slope = C_SLOPE; op.mask = tv_batch(c->act(c->a[i + 1], l.Co), c->pix(i), n0);
     DG_TRY(run_conv(op, st));
     v = op.y;
@@ -931,7 +930,7 @@ static int prim_setup(Scratch& s, int precision, const float* w, int ci, int co,
   if (pk_u) {
     *pk_u = nullptr;
     const int oci = dgrad ? co : ci, oco = dgrad ? ci : co;
-    if (precision == DG_BF16 && umma_ok(oci, oco) && mode != 2) {
+    if (precision == DG_BF16 && umma_ok(oci, oco)) {
       DG_TRY(dev_alloc(s.pool, (void**)pk_u, (elems + 64) * sizeof(bf16)));
       UmmaPackDesc u{0, oci, round_up(oco, 16)};
       UmmaPackDesc* udev;

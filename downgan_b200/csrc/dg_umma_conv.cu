@@ -1,0 +1,371 @@
+// tcgen05 / TMEM implicit-GEMM 3x3 convolution for sm_100a (bf16 operands, fp32 accumulate).
+//
+// Shared-memory layout ("planar"): the halo-padded input tile is stored as
+//     [Ci/8 planes][positions][8 channels]      (16 bytes per position per plane)
+// with positions = tile rows x padded width, row-major.  This is the tcgen05 canonical NO-SWIZZLE
+// K-major layout (core matrix = 8 consecutive positions x 16 B; SBO = 128 B; LBO = plane stride), so
+// the A operand of a tap is the SAME tile at a start-address offset of (dy*PW+dx)*16 bytes: the
+// tile is staged once and never re-gathered per tap.  MMA rows are consecutive padded positions;
+// the pad column(s) of each image row are computed and discarded in the epilogue.
+//
+// Three modes share the kernel:
+//   S1      stride-1 conv (also the data-gradient of a stride-1 conv, with flipped weights)
+//   S2_FWD  stride-2 conv: the input is staged as four parity sub-images so that every tap is again
+//           a constant position offset inside one sub-image
+//   S2_DGRAD data-gradient of a stride-2 conv: the tile is in dy resolution, the four output parity
+//           classes are four TMEM accumulators, each fed by its 1/2/2/4 contributing taps
+// Weights are pre-packed in global memory in the matching B layout [tap*Ci/8 planes][Co][8]; a CTA
+// stages the NT output channels of its blockIdx.y chunk.  The accumulator lives in TMEM (lane =
+// position, column = output channel) and is read back with tcgen05.ld for the fused epilogue (bias,
+// residual scale + skips, LeakyReLU / mask, bf16 pack, pixel-(un)shuffle addressing, channel-offset
+// store into the dense-block concat buffer).
+#include "dg_umma.cuh"
+
+namespace dg {
+namespace {
+
+using namespace um;
+
+constexpr int UMMA_THREADS = 128;
+constexpr int MAX_SMEM = 227 * 1024 - 2048;  // dynamic limit (static smem of the kernel comes on top)
+enum Mode { S1 = 0, S2_FWD = 1, S2_DGRAD = 2 };
+
+struct UmmaArgs {
+  ConvOp op;
+  int mode;
+  int TH, PW, n_mt, PB, tiles_per_img, NT, tmem_cols, nplanes, nsub, CoP;
+  int Ht, Wt;      // tile-space extent (S1/S2_FWD: output grid; S2_DGRAD: dy grid)
+  unsigned w_off;  // byte offset of the weight image in dynamic smem
+};
+
+// 16 consecutive channels of a view at element index i (16-byte aligned, checked on the host)
+__device__ __forceinline__ void load16(const TV& t, size_t i, float* v) {
+  if (t.bf) {
+    const uint4* p = reinterpret_cast<const uint4*>((const bf16*)t.p + i);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint4 q = p[h];
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[h * 8 + 2 * k] = __uint_as_float(w[k] << 16);
+        v[h * 8 + 2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+      }
+    }
+  } else {
+    const float4* p = reinterpret_cast<const float4*>((const float*)t.p + i);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float4 q = p[h];
+      v[4 * h] = q.x; v[4 * h + 1] = q.y; v[4 * h + 2] = q.z; v[4 * h + 3] = q.w;
+    }
+  }
+}
+__device__ __forceinline__ void store16(const TV& t, size_t i, const float* v) {
+  if (t.bf) {
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+      w[k] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    uint4* p = reinterpret_cast<uint4*>((bf16*)t.p + i);
+    p[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    p[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  } else {
+    float4* p = reinterpret_cast<float4*>((float*)t.p + i);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) p[h] = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+  }
+}
+__device__ __forceinline__ void st1(const TV& t, size_t i, float v) {
+  if (t.bf) ((bf16*)t.p)[i] = __float2bfloat16_rn(v);
+  else ((float*)t.p)[i] = v;
+}
+
+// fused epilogue for 16 channels [nc, nc+16) of output pixel (n, yo, xo)
+__device__ __forceinline__ void epilogue16(const ConvOp& op, float* v, int n, int yo, int xo, int nc) {
+  const size_t p = ((size_t)n * op.Hout + yo) * op.Wout + xo;
+  if (op.bias) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += op.bias[nc + j];
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] *= op.s_acc;
+  if (op.r1.p) {
+    float t[16];
+    load16(op.r1, p * op.r1.pitch + op.r1.coff + nc, t);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaf(op.s1, t[j], v[j]);
+  }
+  if (op.r2.p) {
+    float t[16];
+    load16(op.r2, p * op.r2.pitch + op.r2.coff + nc, t);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaf(op.s2, t[j], v[j]);
+  }
+  if (op.act == ACT_LRELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * op.slope;
+  } else if (op.act == ACT_MASK) {
+    float t[16];
+    load16(op.mask, p * op.mask.pitch + op.mask.coff + nc, t);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] *= (t[j] > 0.f ? 1.f : op.slope);
+  }
+  if (op.shuffle == SHUF_NONE) {
+    store16(op.y, p * op.y.pitch + op.y.coff + nc, v);
+  } else if (op.shuffle == SHUF_PIXEL) {  // nn.PixelShuffle(2) folded into the store addressing
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int co = nc + j, cc = co >> 2, ii = (co >> 1) & 1, jj = co & 1;
+      const size_t qq = ((size_t)n * (2 * op.Hout) + 2 * yo + ii) * (2 * op.Wout) + 2 * xo + jj;
+      st1(op.y, qq * op.y.pitch + op.y.coff + cc, v[j]);
+    }
+  } else {  // inverse shuffle: data-gradient w.r.t. the pre-shuffle activation
+    const size_t qq = ((size_t)n * (op.Hout >> 1) + (yo >> 1)) * (op.Wout >> 1) + (xo >> 1);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      st1(op.y, qq * op.y.pitch + op.y.coff + 4 * (nc + j) + 2 * (yo & 1) + (xo & 1), v[j]);
+  }
+}
+
+__global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const UmmaArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_slot;
+  const ConvOp& op = a.op;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n = blockIdx.x / a.tiles_per_img;
+  const int y0 = (blockIdx.x % a.tiles_per_img) * a.TH;
+  const int co0 = blockIdx.y * a.NT;
+  const int rows = min(a.TH, a.Ht - y0);
+  const int PW = a.PW, mode = a.mode;
+
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)a.tmem_cols);
+  if (tid == 32) mbar_init(smem_u32(&mbar), 1);
+
+  // ---- stage the input tile (zero fill = conv padding) and this CTA's slice of the weight image
+  const uint32_t sa = smem_u32(smem);
+  {
+    const int xpos = a.PB >> 4;
+    const bf16* xb = (const bf16*)op.x.p;
+    const int total = xpos * a.nplanes;
+    for (int sub = 0; sub < a.nsub; ++sub) {
+      const int py = sub >> 1, px = sub & 1;
+      for (int i = tid; i < total; i += UMMA_THREADS) {
+        const int pos = i / a.nplanes, pl = i - pos * a.nplanes;
+        const int r = pos / PW, c = pos - r * PW;
+        if (r >= a.TH + ((mode == S1) ? 2 : 1)) continue;  // beyond the tile: only read by discarded rows
+        int gy, gx;
+        if (mode == S1) { gy = y0 - 1 + r; gx = c - 1; }
+        else if (mode == S2_FWD) { gy = 2 * (y0 - 1 + r) + py; gx = 2 * (c - 1) + px; }
+        else { gy = y0 + r; gx = c; }
+        const bool ok = gy >= 0 && gy < op.Hin && gx >= 0 && gx < op.Win;
+        const bf16* src = ok ? xb + (((size_t)n * op.Hin + gy) * op.Win + gx) * op.x.pitch + op.x.coff + pl * 8 : xb;
+        cp_async16(sa + (sub * a.nplanes + pl) * a.PB + pos * 16, src, ok ? 16 : 0);
+      }
+    }
+    // weights: planes [tap*nplanes + pl], rows co0..co0+NT of CoP, 16 B per row
+    const int wrows = 9 * a.nplanes * a.NT;
+    const uint4* wsrc = reinterpret_cast<const uint4*>(op.w_umma);
+    const uint32_t sw = sa + a.w_off;
+    for (int i = tid; i < wrows; i += UMMA_THREADS) {
+      const int tp = i / a.NT, row = i - tp * a.NT;
+      cp_async16(sw + i * 16, wsrc + (size_t)tp * a.CoP + co0 + row, 16);
+    }
+  }
+  cp_async_wait_all();
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  // ---- one thread issues every MMA of the tile
+  if (tid == 0) {
+    const uint32_t idesc = instr_desc(128, a.NT);
+    const uint32_t sw = sa + a.w_off;
+    const int kcs = a.nplanes >> 1;
+    const uint32_t wplane = a.NT * 16;
+    if (mode != S2_DGRAD) {
+      for (int mt = 0; mt < a.n_mt; ++mt) {
+        uint32_t acc = 0;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap - 3 * ky;
+          int sub = 0, shift;
+          if (mode == S1) shift = ky * PW + kx;
+          else { sub = ((ky == 1) ? 0 : 2) + ((kx == 1) ? 0 : 1); shift = ((ky == 0) ? 0 : 1) * PW + ((kx == 0) ? 0 : 1); }
+          const uint32_t a0 = sa + sub * a.nplanes * a.PB + (mt * 128 + shift) * 16;
+          const uint32_t b0 = sw + tap * a.nplanes * wplane;
+          for (int kc = 0; kc < kcs; ++kc) {
+            umma_f16(tmem + mt * a.NT, smem_desc(a0 + 2 * kc * a.PB, a.PB, 128),
+                     smem_desc(b0 + 2 * kc * wplane, wplane, 128), idesc, acc);
+            acc = 1;
+          }
+        }
+      }
+    } else {
+      // output parity class (py,px): taps ky in {1} (py=0) or {0,2} (py=1); ky=0 reads dy one row below
+      for (int mt = 0; mt < a.n_mt; ++mt)
+        for (int cls = 0; cls < 4; ++cls) {
+          const int py = cls >> 1, px = cls & 1;
+          uint32_t acc = 0;
+          for (int ky = 0; ky < 3; ++ky) {
+            if ((py == 0) != (ky == 1)) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+              if ((px == 0) != (kx == 1)) continue;
+              const int shift = ((ky == 0) ? 1 : 0) * PW + ((kx == 0) ? 1 : 0);
+              const uint32_t a0 = sa + (mt * 128 + shift) * 16;
+              const uint32_t b0 = sw + (ky * 3 + kx) * a.nplanes * wplane;
+              for (int kc = 0; kc < kcs; ++kc) {
+                umma_f16(tmem + (mt * 4 + cls) * a.NT, smem_desc(a0 + 2 * kc * a.PB, a.PB, 128),
+                         smem_desc(b0 + 2 * kc * wplane, wplane, 128), idesc, acc);
+                acc = 1;
+              }
+            }
+          }
+        }
+    }
+    umma_commit(smem_u32(&mbar));
+  }
+  __syncwarp();
+  mbar_wait(smem_u32(&mbar), 0);
+  tc_fence_after();
+
+  // ---- epilogue: thread t owns accumulator row t of every M-tile
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const int ncls = (mode == S2_DGRAD) ? 4 : 1;
+  for (int mt = 0; mt < a.n_mt; ++mt) {
+    const int q = mt * 128 + tid;
+    const int r = q / PW, c = q - r * PW;
+    const bool valid = (r < rows) && (c < a.Wt);
+    for (int cls = 0; cls < ncls; ++cls) {
+      int yo = y0 + r, xo = c;
+      if (mode == S2_DGRAD) { yo = 2 * yo + (cls >> 1); xo = 2 * xo + (cls & 1); }
+      for (int nc = 0; nc < a.NT; nc += 16) {
+        float v[16];
+        tmem_ld16(tmem + lane_base + (mt * ncls + cls) * a.NT + nc, v);
+        if (valid) epilogue16(op, v, n, yo, xo, co0 + nc);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, (uint32_t)a.tmem_cols);
+}
+
+bool plan(const ConvOp& op, UmmaArgs& a) {
+  if (!op.w_umma || !op.x.bf) return false;
+  if (op.Ci % 16 || op.Co % 16 || op.Co > 256) return false;
+  if (op.x.pitch % 8 || op.x.coff % 8) return false;
+  int mode;
+  if (op.transposed) {
+    if (op.Hout != 2 * op.Hin || op.Wout != 2 * op.Win) return false;
+    mode = S2_DGRAD;
+  } else if (op.stride == 2) {
+    if (op.Hin != 2 * op.Hout || op.Win != 2 * op.Wout) return false;
+    mode = S2_FWD;
+  } else {
+    if (op.stride != 1 || op.Hin != op.Hout || op.Win != op.Wout) return false;
+    mode = S1;
+  }
+  auto aligned = [](const TV& t) {
+    if (!t.p) return true;
+    return t.bf ? (t.pitch % 8 == 0 && t.coff % 8 == 0) : (t.pitch % 4 == 0 && t.coff % 4 == 0);
+  };
+  if (!aligned(op.r1) || !aligned(op.r2) || !aligned(op.mask)) return false;
+  if (op.shuffle == SHUF_NONE && !aligned(op.y)) return false;
+  const int Ht = (mode == S2_DGRAD) ? op.Hin : op.Hout, Wt = (mode == S2_DGRAD) ? op.Win : op.Wout;
+  const int PW = (mode == S1) ? Wt + 2 : Wt + 1;
+  const int nplanes = op.Ci / 8, nsub = (mode == S2_FWD) ? 4 : 1, ncls = (mode == S2_DGRAD) ? 4 : 1;
+  const int halo = (mode == S1) ? 2 * PW + 2 : PW + 1;
+  // output-channel chunk per CTA: the largest divisor of Co whose weight image fits comfortably
+  int NT = 0;
+  for (int cand : {256, 128, 64, 32, 16}) {
+    if (cand > op.Co || op.Co % cand) continue;
+    if ((size_t)9 * op.Ci * cand * 2 > 112 * 1024) continue;
+    if (ncls * cand > 512) continue;
+    NT = cand;
+    break;
+  }
+  if (NT == 0) return false;
+  const size_t wbytes = (size_t)9 * op.Ci * NT * 2;
+  double best = -1.0;
+  int bestTH = 0, best_mt = 0;
+  for (int TH = 1; TH <= Ht; ++TH) {
+    const int span = TH * PW - (PW - Wt);
+    const int n_mt = (span + 127) / 128;
+    if (n_mt > 4 || n_mt * ncls * NT > 512) break;
+    const int pb_pos = ((n_mt * 128 + halo) + 7) & ~7;
+    const size_t smem = (size_t)nsub * nplanes * pb_pos * 16 + wbytes;
+    if (smem > (size_t)MAX_SMEM) break;
+    const int ntiles = (Ht + TH - 1) / TH;
+    const double eff = (double)(Ht * Wt) / ((double)ntiles * n_mt * 128);
+    if (eff > best + 1e-9) { best = eff; bestTH = TH; best_mt = n_mt; }
+  }
+  if (bestTH == 0) return false;
+  a.op = op;
+  a.mode = mode; a.Ht = Ht; a.Wt = Wt;
+  a.TH = bestTH; a.PW = PW; a.n_mt = best_mt; a.NT = NT; a.nplanes = nplanes; a.nsub = nsub;
+  a.CoP = round_up(op.Co, 16);
+  a.PB = (((best_mt * 128 + halo) + 7) & ~7) * 16;
+  a.tiles_per_img = (Ht + bestTH - 1) / bestTH;
+  int cols = best_mt * ncls * NT, pc = 32;
+  while (pc < cols) pc <<= 1;
+  a.tmem_cols = pc;
+  a.w_off = (unsigned)(nsub * nplanes * a.PB);
+  return true;
+}
+
+}  // namespace
+
+bool umma_supported(const ConvOp& op) {
+  UmmaArgs a;
+  return plan(op, a);
+}
+
+int conv_umma(const ConvOp& op, cudaStream_t st) {
+  UmmaArgs a;
+  if (!plan(op, a)) { set_error("conv_umma: unsupported shape"); return DG_ERR_INVALID; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    DG_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+    attr_set = true;
+  }
+  const size_t smem = (size_t)a.w_off + (size_t)9 * op.Ci * a.NT * 2;
+  const long long total = (long long)op.B * op.Hout * op.Wout;
+  const double taps = op.transposed ? 2.25 : 9.0;
+  Prof prof(PC_CONV_UMMA, 2.0 * total * op.Co * op.Ci * taps,
+            (double)total * op.Co * (op.y.bf ? 2 : 4) + (double)op.B * op.Hin * op.Win * op.Ci * 2.0, st);
+  conv_umma_kernel<<<dim3(op.B * a.tiles_per_img, op.Co / a.NT), UMMA_THREADS, smem, st>>>(a);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+// fp32 packed [tap][ci][CoP]  ->  bf16 planes [(tap*Ci/8 + ci/8)][CoP][8]   (same element offsets)
+__global__ void pack_umma_kernel(const float* __restrict__ src, bf16* __restrict__ dst, const UmmaPackDesc* __restrict__ tab) {
+  const UmmaPackDesc d = tab[blockIdx.y];
+  const long long n = 9LL * d.Ci * d.CoP;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(e % d.CoP);
+    const long long r = e / d.CoP;
+    const int ci = (int)(r % d.Ci), tap = (int)(r / d.Ci);
+    const long long o = (((long long)tap * (d.Ci >> 3) + (ci >> 3)) * d.CoP + co) * 8 + (ci & 7);
+    dst[d.off + o] = __float2bfloat16_rn(src[d.off + e]);
+  }
+}
+
+int pack_umma(const float* packed, void* dst_bf16, const UmmaPackDesc* table_dev, int n, int max_elems, cudaStream_t st) {
+  if (n == 0) return 0;
+  int bx = (max_elems + 255) / 256;
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  pack_umma_kernel<<<dim3(bx, n), 256, 0, st>>>(packed, (bf16*)dst_bf16, table_dev);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dg
+
+extern "C" int dg_has_tcgen05(void) { return 1; }

@@ -215,7 +215,8 @@ def test_gp_standalone(precision):
     gp, grads = tr._gp(fine, fake, C, alpha=alpha, want_grads=True)
     torch.cuda.synchronize()
     assert abs(float(gp) * hp.gp_lambda - float(val)) <= TOL_OUT[precision] * abs(float(val))
-    assert pu.rel(tr.last_gp_norms, norms) < TOL_OUT[precision]
+    # per-sample ||grad|| through 8 masked layers of a 2.5x-scaled critic: bf16 operands move single samples by a few %
+    assert pu.rel(tr.last_gp_norms, norms) < (1e-3 if precision == "fp32" else 5e-2)
     worst, wk, flat = pu.grad_report(pu.flat_to_dict(C, grads), gcf)
     assert worst < TOL_GRAD_TENSOR[precision] and flat < TOL_GRAD_FLAT[precision], (wk, worst, flat)
 
@@ -252,25 +253,42 @@ def test_loss_curves_200_steps(precision):
     gopt = torch.optim.Adam(G.parameters(), 2.5e-4, betas=(0.9, 0.99))
     copt = torch.optim.Adam(C.parameters(), 2.5e-4, betas=(0.9, 0.99))
     tr = pu.WassersteinGAN(G, C, gopt, copt)
-    ref = otr.OracleTrainer(g_sd, TINY_G, c_sd, TINY_C)
-    closs, gloss, rc, rg = [], [], [], []
+    # Ground truth = fp64 oracle.  GAN dynamics amplify rounding differences once the critic has
+    # learnt ||grad|| ~ 1 (the critic loss falls from ~100 to O(1) and changes sign), so the
+    # reference's own fp32 run drifts from fp64 late in the curve; that measured drift is the
+    # yardstick:  (a) the first 40 steps must agree pointwise to 1e-3 relative,  (b) over all 200
+    # steps the deviation must stay within 3x the fp32-oracle-vs-fp64-oracle deviation plus 1e-3 of
+    # the curve's range.
+    ref = otr.OracleTrainer(g_sd, TINY_G, c_sd, TINY_C, dtype=torch.float64)
+    ref32 = otr.OracleTrainer(g_sd, TINY_G, c_sd, TINY_C)
+    closs, gloss, rc, rg, rc32, rg32 = [], [], [], [], [], []
     for step in range(200):
         coarse, fine, alpha = synth_batch(4, 3, 8, seed=1000 + step % 7, aseed=step)
         oc, og = ref.batch(coarse, fine, alpha)
+        oc32, og32 = ref32.batch(coarse, fine, alpha)
         tr._critic_train_iteration(coarse, fine, alpha)
         closs.append(tr.last_critic.clone())
         if tr.num_steps % 5 == 0:
             tr._generator_train_iteration(coarse, fine)
             gloss.append(tr.last_generator.clone())
             rg.append(float(og["loss"]))
+            rg32.append(float(og32["loss"]))
         tr.num_steps += 1
         rc.append(float(oc["loss"]))
+        rc32.append(float(oc32["loss"]))
     torch.cuda.synchronize()
     closs = torch.stack(closs).cpu()[:, 0].double()
     gloss = torch.stack(gloss).cpu()[:, 0].double()
     rc, rg = torch.tensor(rc).double(), torch.tensor(rg).double()
+    rc32, rg32 = torch.tensor(rc32).double(), torch.tensor(rg32).double()
     assert len(gloss) == 40
-    assert float(((closs - rc).abs() / rc.abs().clamp_min(1e-3)).max()) < 2e-2
-    assert float(((gloss - rg).abs() / rg.abs().clamp_min(1e-3)).max()) < 2e-2
+    assert float(((closs - rc).abs() / rc.abs())[:40].max()) < 1e-3
+    assert float(((gloss - rg).abs() / rg.abs())[:8].max()) < 1e-3
+    for ours, r64, r32 in ((closs, rc, rc32), (gloss, rg, rg32)):
+        drift = float((r32 - r64).abs().max())
+        span = float(r64.max() - r64.min())
+        dev = float((ours - r64).abs().max())
+        print(f"loss curve: max|cuda-fp64| {dev:.4f}  max|fp32 oracle-fp64| {drift:.4f}  range {span:.2f}")
+        assert dev <= 3 * drift + 1e-3 * span, (dev, drift, span)
     tr.sync_optimizer_state()
     assert len(copt.state_dict()["state"]) == 13
