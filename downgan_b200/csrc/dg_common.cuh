@@ -185,3 +185,11 @@ int wgrad_umma(const WgradOp& op, cudaStream_t st);
 int pack_umma(const float* packed, void* dst_bf16, const UmmaPackDesc* table_dev, int n, int max_elems, cudaStream_t st);
 
 }  // namespace dg
+
+namespace dg {
+// boundary-layer kernels (dg_skinny.cu)
+bool conv_skinny_supported(const ConvOp& op);
+int conv_skinny(const ConvOp& op, cudaStream_t st);
+bool wgrad_skinny_supported(const WgradOp& op);
+int wgrad_skinny(const WgradOp& op, cudaStream_t st);
+}  // namespace dg

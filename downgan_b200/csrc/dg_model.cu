@@ -49,11 +49,13 @@ int dev_alloc(std::vector<void*>& pool, void** out, size_t bytes) {
 }
 
 int run_wgrad(const WgradOp& w, cudaStream_t st) {
+  if (wgrad_skinny_supported(w)) return wgrad_skinny(w, st);
   if (wgrad_umma_supported(w)) return wgrad_umma(w, st);
   return wgrad_direct(w, st);
 }
 
 int run_conv(const ConvOp& op, cudaStream_t st) {
+  if (conv_skinny_supported(op)) return conv_skinny(op, st);
   if (op.w_umma && umma_supported(op)) return conv_umma(op, st);
   return conv_direct(op, st);
 }
