@@ -24,9 +24,8 @@ from __future__ import annotations
 from typing import Optional
 
 import torch
-import torch.distributed as dist
 
-from .. import _lib
+from .. import _lib, dp
 from ..config import hyperparams as hp
 from ..networks.critic import Critic
 from ..networks.generator import Generator
@@ -120,17 +119,9 @@ class WassersteinGAN:
         self.C.ensure_packed(c)
         return g, c
 
-    @staticmethod
-    def _world() -> int:
-        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-
     def _allreduce(self, grads: torch.Tensor) -> float:
         """Sum-all-reduce the flat gradient bucket over NCCL; returns the 1/world scale for Adam."""
-        w = self._world()
-        if w > 1:
-            dist.all_reduce(grads, op=dist.ReduceOp.SUM)
-            return 1.0 / w
-        return 1.0
+        return dp.allreduce_sum_(grads)
 
     # ---- iterations ------------------------------------------------------------
     def _critic_train_iteration(self, coarse, fine, alpha: Optional[torch.Tensor] = None):
