@@ -193,3 +193,10 @@ int conv_skinny(const ConvOp& op, cudaStream_t st);
 bool wgrad_skinny_supported(const WgradOp& op);
 int wgrad_skinny(const WgradOp& op, cudaStream_t st);
 }  // namespace dg
+
+namespace dg {
+// persistent fused RRDB trunk, forward (dg_umma_trunk.cu)
+bool trunk_fused_supported(int F, int Hc, int R, int bf);
+int trunk_fwd_fused(const void* x_in, int in_pitch, int in_coff, void* y_out, int out_pitch, void* const* db_bufs_dev,
+                    const void* w_umma, const float* bias, int R, int B, cudaStream_t st);
+}  // namespace dg

@@ -3,6 +3,7 @@
 // linear layers, weight packing, gradient-penalty / loss reductions and Adam.
 // Everything accumulates in fp32.  sm_100a only.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "dg_common.cuh"
 
@@ -736,9 +737,13 @@ extern "C" int dg_profile_report(double* out, int n_classes) {
   if (!out || n_classes < dg::PC_COUNT) { dg::set_error("dg_profile_report: need %d classes", (int)dg::PC_COUNT); return DG_ERR_INVALID; }
   DG_CUDA(cudaDeviceSynchronize());
   for (int i = 0; i < n_classes * 4; ++i) out[i] = 0.0;
+  const char* dump = getenv("DG_PROFILE_DUMP");  // optional per-launch CSV: class,flops,bytes,ms
+  FILE* f = dump ? fopen(dump, "a") : nullptr;
+  struct Closer { FILE* f; ~Closer() { if (f) fclose(f); } } closer{f};
   for (auto& r : dg::g_prof) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+    if (f) fprintf(f, "%d,%.0f,%.0f,%.6f\n", r.cls, r.flops, r.bytes, ms);
     out[r.cls * 4 + 0] += 1.0; out[r.cls * 4 + 1] += ms; out[r.cls * 4 + 2] += r.flops; out[r.cls * 4 + 3] += r.bytes;
   }
   return 0;

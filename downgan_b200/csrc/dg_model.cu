@@ -87,6 +87,7 @@ struct dg_generator {
   // activations
   void* x0 = nullptr;
   std::vector<void*> db;  // R*3 concat buffers (B,Hc,Hc,5F)
+  void** db_ptrs_dev = nullptr;  // device copy of db[] for the fused trunk kernel
   void *trunk_out = nullptr, *t1 = nullptr, *c30 = nullptr;
   std::vector<void*> up;  // U post-shuffle activations
   float* fake = nullptr;  // (B,Hf,Hf,Cout) NHWC fp32
@@ -250,6 +251,10 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
   const int ndb = std::max(1, g->R * 3);
   g->db.assign(ndb, nullptr);
   for (int i = 0; i < ndb; ++i) GA(g->db[i], B * pc * 5 * F * g->esz);
+  GA(g->db_ptrs_dev, sizeof(void*) * ndb);
+  if (cudaMemcpy(g->db_ptrs_dev, g->db.data(), sizeof(void*) * ndb, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("cudaMemcpy(db_ptrs) failed"); dg_generator_destroy(g); return DG_ERR_CUDA;
+  }
   GA(g->trunk_out, B * pc * F * g->esz);
   GA(g->t1, B * pc * F * g->esz);
   g->up.assign(g->U, nullptr);
@@ -292,7 +297,7 @@ extern "C" int dg_generator_pack(dg_generator* g, const float* params, void* str
 
 // Generator.forward, networks/generator.py:83-90 (dense block :36-41, RRDB :52-53).
 // Input already in g->x0 (NHWC); output in g->fake (NHWC fp32).
-static int gen_forward_internal(dg_generator* g, int B, cudaStream_t st) {
+static int gen_forward_internal(dg_generator* g, int B, bool save, cudaStream_t st) {
   const int F = g->F, Hc = g->Hc;
   auto conv = [&](int li, TV x, int H, TV y) {
     const Layer& l = g->layers[li];
@@ -309,7 +314,14 @@ static int gen_forward_internal(dg_generator* g, int B, cudaStream_t st) {
     ConvOp op = conv(g->idx_conv1(), g->act(g->x0, g->Cin), Hc, g->act(first, first_pitch));
     DG_TRY(run_conv(op, st));
   }
-  for (int r = 0; r < g->R; ++r)
+  const bool fused_trunk = trunk_fused_supported(F, Hc, g->R, g->bf);
+  if (fused_trunk) {
+    // persistent tcgen05 kernel: the whole RRDB trunk with the concat buffer resident in shared memory
+    const Layer& l0 = g->layers[g->idx_db(0, 0, 1)];
+    DG_TRY(trunk_fwd_fused(g->db[0], 5 * F, 0, g->trunk_out, F, save ? (void* const*)g->db_ptrs_dev : nullptr,
+                           g->pk_u + l0.pk_off, g->pk + l0.pkb_off, g->R, B, st));
+  }
+  for (int r = 0; r < (fused_trunk ? 0 : g->R); ++r)
     for (int d = 0; d < 3; ++d) {
       void* buf = g->db[r * 3 + d];
       for (int k = 1; k <= 4; ++k) {
@@ -353,18 +365,17 @@ static int gen_forward_internal(dg_generator* g, int B, cudaStream_t st) {
     ConvOp op = conv(g->idx_c32(), g->act(g->c30, F), H, tv(g->fake, 0, g->Cout));
     DG_TRY(run_conv(op, st));
   }
-  g->saved_batch = B;
+  g->saved_batch = save ? B : 0;
   return 0;
 }
 
 extern "C" int dg_generator_fwd(dg_generator* g, const float* coarse, int batch, float* fake, int save, void* stream) {
-  (void)save;
   DG_CHECK(g && coarse, "dg_generator_fwd: null argument");
   DG_CHECK(batch >= 1 && batch <= g->maxB, "dg_generator_fwd: batch %d outside [1,%d]", batch, g->maxB);
   if (!g->packed) { set_error("dg_generator_fwd: dg_generator_pack has not been called"); return DG_ERR_STATE; }
   cudaStream_t st = (cudaStream_t)stream;
   DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), batch, g->Cin, g->Hc, g->Hc, st));
-  DG_TRY(gen_forward_internal(g, batch, st));
+  DG_TRY(gen_forward_internal(g, batch, save != 0, st));
   if (fake) DG_TRY(nhwc_to_nchw(tv(g->fake, 0, g->Cout), fake, batch, g->Cout, g->Hf, g->Hf, st));
   return 0;
 }
@@ -848,7 +859,7 @@ extern "C" int dg_critic_step(dg_generator* g, dg_critic* c, const dg_hyper* hp,
   DG_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(float), st));
   // fake = G(coarse): the reference keeps the graph (:35) but discards the generator gradients (:65)
   DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), B, g->Cin, g->Hc, g->Hc, st));
-  DG_TRY(gen_forward_internal(g, B, st));
+  DG_TRY(gen_forward_internal(g, B, false, st));
   g->saved_batch = 0;
   // one 3B critic batch: [real ; fake ; alpha*real + (1-alpha)*fake]   (:37-38, :91-97)
   DG_TRY(build_critic_input(fine, g->fake, 0, alpha, c->a0, B, c->nc, c->Hf, c->Hf, 0, st));
@@ -878,7 +889,7 @@ extern "C" int dg_generator_step(dg_generator* g, dg_critic* c, const dg_hyper* 
   const long long n = (long long)B * g->Hf * g->Hf * g->Cout;
   DG_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(float), st));
   DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), B, g->Cin, g->Hc, g->Hc, st));
-  DG_TRY(gen_forward_internal(g, B, st));
+  DG_TRY(gen_forward_internal(g, B, true, st));
   // c_fake = C(fake); adversarial seed d(-gamma*mean)/dscore = -gamma/B
   DG_CUDA(cudaMemcpyAsync(c->a0, g->fake, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
   DG_TRY(critic_forward_internal(c, B, st));

@@ -1,0 +1,227 @@
+// Persistent fused RRDB trunk (forward) on tcgen05, sm_100a.
+//
+// One CTA owns one 16x16 coarse image for the WHOLE trunk (R residual-in-residual blocks = 3R dense
+// blocks = 15R convolutions, networks/generator.py:36-41,52-53 of the reference).  The dense-block
+// concat buffer (x, o1..o4 = 80 channels) never leaves shared memory: it is the planar tile
+// [10 planes][18x18 padded positions][8 ch] that the tcgen05 A descriptors read directly (tap =
+// start-address offset), and every epilogue writes its 16 output channels (bias + LeakyReLU, or
+// 0.2*o5 + x [+ RRDB skip]) straight into the next two planes / back into planes 0-1.  Only the
+// per-layer weight images stream in from L2 (double-buffered cp.async, prefetched during the MMAs
+// of the previous layer).  Three warps issue the MMAs of the three M-tiles in parallel; the
+// accumulators (3 x 16 TMEM columns) are read back by all four warps.  With `db_bufs` set, every
+// slice is also stored to the per-block global concat buffers for the backward pass.
+#include "dg_umma.cuh"
+
+namespace dg {
+namespace {
+
+using namespace um;
+
+constexpr int TF = 16;            // filters
+constexpr int TW = 16;            // coarse grid edge
+constexpr int TPW = TW + 2;       // padded width
+constexpr int TNMT = 3;           // M-tiles: 3*128 >= 16*18-2
+constexpr int TPBPOS = 424;       // positions per plane incl. over-read slack (3*128 + 2*18 + 2 -> 424)
+constexpr int TPB = TPBPOS * 16;  // plane stride in bytes
+constexpr int T_X_BYTES = 10 * TPB;
+constexpr int T_W_BYTES = 9 * 80 * TF * 2;
+constexpr int T_SMEM = T_X_BYTES + 2 * T_W_BYTES;
+constexpr float G_SLOPE = 0.01f, RES = 0.2f;
+
+struct TrunkArgs {
+  const bf16* x_in; int in_pitch, in_coff;  // (B,16,16,pitch): conv1 output
+  bf16* y_out; int out_pitch;               // (B,16,16,pitch): trunk output
+  bf16* const* db_bufs;                     // [3R] concat buffers (pitch 80) or nullptr
+  const bf16* w;                            // B-operand images of the 15R dense convs, consecutive
+  const float* bias;                        // 16 floats per dense conv, consecutive
+  int R, B;
+};
+
+__device__ __forceinline__ void st_shared16(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared16(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack8(uint4 q, float* v) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[2 * k] = __uint_as_float(w[k] << 16);
+    v[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+  }
+}
+
+__global__ void __launch_bounds__(128) trunk_fwd_kernel(const TrunkArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.x;
+  const uint32_t sX = smem_u32(smem);
+  const uint32_t sW = sX + T_X_BYTES;
+
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 64);
+  if (tid == 32) mbar_init(smem_u32(&mbar), TNMT);
+  // zero the whole concat tile: halo ring and pad columns are the convolution's zero padding
+  for (int i = tid; i < T_X_BYTES / 16; i += 128) st_shared16(sX + i * 16, make_uint4(0, 0, 0, 0));
+  __syncthreads();
+  // image -> planes 0,1 (interior positions), weights of layer 0 -> buffer 0
+  for (int i = tid; i < 256 * 2; i += 128) {
+    const int pix = i >> 1, pl = i & 1;
+    const int y = pix >> 4, x = pix & 15;
+    cp_async16(sX + pl * TPB + ((y + 1) * TPW + x + 1) * 16,
+               a.x_in + ((size_t)n * 256 + pix) * a.in_pitch + a.in_coff + pl * 8, 16);
+  }
+  for (int i = tid; i < 288; i += 128) cp_async16(sW + i * 16, reinterpret_cast<const uint4*>(a.w) + i, 16);
+  cp_async_wait_all();
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc = instr_desc(128, TF);
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+
+  // this thread's three output positions (one per M-tile)
+  int pos[TNMT], pix[TNMT];
+  bool valid[TNMT];
+#pragma unroll
+  for (int mt = 0; mt < TNMT; ++mt) {
+    const int q = mt * 128 + tid;
+    const int y = q / TPW, x = q - y * TPW;
+    valid[mt] = (x < TW) && (y < TW);
+    pos[mt] = q + TPW + 1;
+    pix[mt] = y * TW + x;
+  }
+  uint4 xr[TNMT][2];  // RRDB input at this thread's positions (bf16 x 16)
+  const int total = a.R * 15;
+  size_t w_elem = 0;  // element offset of the current layer's weight image
+  for (int L = 0; L < total; ++L) {
+    const int db = L / 5, k = L - db * 5 + 1, d = db % 3;
+    const uint32_t wb = sW + (L & 1) * T_W_BYTES;
+    if (k == 1 && d == 0) {
+#pragma unroll
+      for (int mt = 0; mt < TNMT; ++mt) {
+        xr[mt][0] = ld_shared16(sX + pos[mt] * 16);
+        xr[mt][1] = ld_shared16(sX + TPB + pos[mt] * 16);
+      }
+    }
+    // ---- MMAs of this layer: warp w issues M-tile w (9 taps x k K-steps)
+    if (warp < TNMT && lane == 0) {
+      uint32_t acc = 0;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3, dx = tap - 3 * dy;
+        const uint32_t a0 = sX + (warp * 128 + dy * TPW + dx) * 16;
+        const uint32_t b0 = wb + tap * (2 * k) * 256;
+        for (int kc = 0; kc < k; ++kc) {
+          umma_f16(tmem + warp * TF, smem_desc(a0 + 2 * kc * TPB, TPB, 128), smem_desc(b0 + 2 * kc * 256, 256, 128),
+                   idesc, acc);
+          acc = 1;
+        }
+      }
+      umma_commit(smem_u32(&mbar));
+    }
+    __syncwarp();
+    // ---- prefetch the next layer's weights into the other buffer while the tensor pipe runs
+    const size_t w_next = w_elem + (size_t)9 * k * TF * TF;
+    if (L + 1 < total) {
+      const int kn = (k == 5) ? 1 : k + 1;
+      const uint4* src = reinterpret_cast<const uint4*>(a.w + w_next);
+      const uint32_t dst = sW + ((L + 1) & 1) * T_W_BYTES;
+      for (int i = tid; i < 288 * kn; i += 128) cp_async16(dst + i * 16, src + i, 16);
+    }
+    float bias[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) bias[j] = __ldg(a.bias + (size_t)L * 16 + j);
+    mbar_wait(smem_u32(&mbar), L & 1);
+    tc_fence_after();
+    // ---- epilogue
+    bf16* save_cur = a.db_bufs ? a.db_bufs[db] : nullptr;
+    bf16* save_next = (a.db_bufs && db + 1 < a.R * 3) ? a.db_bufs[db + 1] : nullptr;
+#pragma unroll
+    for (int mt = 0; mt < TNMT; ++mt) {
+      float v[16];
+      tmem_ld16(tmem + lane_base + mt * TF, v);
+      if (!valid[mt]) continue;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += bias[j];
+      if (k < 5) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * G_SLOPE;
+        const uint4 lo = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+        const uint4 hi = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+        st_shared16(sX + (2 * k) * TPB + pos[mt] * 16, lo);
+        st_shared16(sX + (2 * k + 1) * TPB + pos[mt] * 16, hi);
+        if (save_cur) {
+          uint4* g = reinterpret_cast<uint4*>(save_cur + ((size_t)n * 256 + pix[mt]) * 80 + 16 * k);
+          g[0] = lo; g[1] = hi;
+        }
+      } else {
+        float xo[16];
+        unpack8(ld_shared16(sX + pos[mt] * 16), xo);
+        unpack8(ld_shared16(sX + TPB + pos[mt] * 16), xo + 8);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(RES, v[j], xo[j]);
+        if (d == 2) {
+          float xq[16];
+          unpack8(xr[mt][0], xq);
+          unpack8(xr[mt][1], xq + 8);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(RES, v[j], xq[j]);
+        }
+        const uint4 lo = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+        const uint4 hi = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+        st_shared16(sX + pos[mt] * 16, lo);
+        st_shared16(sX + TPB + pos[mt] * 16, hi);
+        if (L + 1 == total) {
+          uint4* g = reinterpret_cast<uint4*>(a.y_out + ((size_t)n * 256 + pix[mt]) * a.out_pitch);
+          g[0] = lo; g[1] = hi;
+        } else if (save_next) {
+          uint4* g = reinterpret_cast<uint4*>(save_next + ((size_t)n * 256 + pix[mt]) * 80);
+          g[0] = lo; g[1] = hi;
+        }
+      }
+    }
+    w_elem = w_next;
+    cp_async_wait_all();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
+}  // namespace
+
+bool trunk_fused_supported(int F, int Hc, int R, int bf) { return bf && F == TF && Hc == TW && R >= 1; }
+
+// x_in: conv1 output view; y_out: trunk output (pitch out_pitch); db_bufs_dev: device array of 3R
+// concat-buffer pointers (pitch 80) or nullptr when the activations need not be kept.
+int trunk_fwd_fused(const void* x_in, int in_pitch, int in_coff, void* y_out, int out_pitch, void* const* db_bufs_dev,
+                    const void* w_umma, const float* bias, int R, int B, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DG_CUDA(cudaFuncSetAttribute(trunk_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
+    attr_set = true;
+  }
+  TrunkArgs a;
+  a.x_in = (const bf16*)x_in; a.in_pitch = in_pitch; a.in_coff = in_coff;
+  a.y_out = (bf16*)y_out; a.out_pitch = out_pitch;
+  a.db_bufs = (bf16* const*)db_bufs_dev;
+  a.w = (const bf16*)w_umma; a.bias = bias; a.R = R; a.B = B;
+  const double px = (double)B * 256;
+  Prof prof(PC_DENSE_UMMA, 2.0 * px * 16.0 * 9.0 * 16.0 * 15.0 * 3.0 * R, px * 16.0 * 2.0 * 2.0, st);
+  trunk_fwd_kernel<<<B, 128, T_SMEM, st>>>(a);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dg
