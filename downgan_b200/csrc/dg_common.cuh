@@ -200,3 +200,10 @@ bool trunk_fused_supported(int F, int Hc, int R, int bf);
 int trunk_fwd_fused(const void* x_in, int in_pitch, int in_coff, void* y_out, int out_pitch, void* const* db_bufs_dev,
                     const void* w_umma, const float* bias, int R, int B, cudaStream_t st);
 }  // namespace dg
+
+namespace dg {
+// batched tcgen05 weight gradients: one launch for many layers (dg_umma_wgrad.cu)
+size_t wgrad_umma_args_size();
+int wgrad_umma_batched(const WgradOp* ops, int n, void* table_dev, std::vector<unsigned char>& shadow, int S_per_op,
+                       cudaStream_t st);
+}  // namespace dg

@@ -92,6 +92,9 @@ struct dg_generator {
   std::vector<void*> up;  // U post-shuffle activations
   float* fake = nullptr;  // (B,Hf,Hf,Cout) NHWC fp32
   // backward workspaces
+  std::vector<void*> Dall;        // per-dense-block dz buffers (bf16 mode: weight gradients are batched after the dgrad chain)
+  void* wg_table_dev = nullptr;   // device table of the batched weight-gradient launch
+  std::vector<unsigned char> wg_shadow;
   void *D = nullptr, *gR = nullptr, *gx0 = nullptr, *gx1 = nullptr, *gT1 = nullptr, *gA = nullptr, *gB = nullptr;
   float* dfake = nullptr;  // NHWC fp32
   float* fine_nhwc = nullptr;
@@ -266,6 +269,12 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
   GA(g->l1, 64);
   // backward
   GA(g->D, B * pc * 5 * F * g->esz);
+  if (g->bf && F % 16 == 0 && g->R > 0) {
+    g->Dall.assign((size_t)g->R * 3, nullptr);
+    g->Dall[0] = g->D;
+    for (int i = 1; i < g->R * 3; ++i) GA(g->Dall[i], B * pc * 5 * F * g->esz);
+    GA(g->wg_table_dev, wgrad_umma_args_size() * (size_t)g->R * 15);
+  }
   GA(g->gR, B * pc * F * g->esz);
   GA(g->gx0, B * pc * F * g->esz);
   GA(g->gx1, B * pc * F * g->esz);
@@ -442,12 +451,17 @@ static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_co
   const size_t pix = (size_t)B * Hc * Hc;
   // trunk, RRDB by RRDB
   void* gxs[2] = {g->gx0, g->gx1};
+  const bool batched_wgrad = !g->Dall.empty();
+  std::vector<WgradOp> wops;
+  if (batched_wgrad) wops.reserve((size_t)g->R * 15);
+  void* const D0 = g->D;
   for (int r = g->R - 1; r >= 0; --r) {
     // g->gR holds dL/d(RRDB_r output)
     void* gin = g->gR;
     float s_in = RES_SCALE;
     for (int d = 2; d >= 0; --d) {
       void* buf = g->db[r * 3 + d];
+      if (batched_wgrad) g->D = g->Dall[(size_t)r * 3 + d];
       // dz5 = 0.2 * s_in * gin
       DG_TRY(scale_add(g->act(g->D, 5 * F, 0), g->act(gin, F), RES_SCALE * s_in, TV(), 0.f, pix, F, st));
       for (int k = 4; k >= 1; --k) {
@@ -460,8 +474,19 @@ static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_co
         DG_TRY(run_conv(op, st));
       }
       // weight gradients of b1..b5: x = buf[0:kF], dy = dz_k
-      for (int k = 1; k <= 5; ++k)
-        DG_TRY(wgrad(g->idx_db(r, d, k), g->act(buf, 5 * F, 0), Hc, g->act(g->D, 5 * F, (5 - k) * F)));
+      for (int k = 1; k <= 5; ++k) {
+        if (!batched_wgrad) {
+          DG_TRY(wgrad(g->idx_db(r, d, k), g->act(buf, 5 * F, 0), Hc, g->act(g->D, 5 * F, (5 - k) * F)));
+          continue;
+        }
+        const Layer& l = g->layers[g->idx_db(r, d, k)];
+        WgradOp w;
+        memset(&w, 0, sizeof(w));
+        w.x = g->act(buf, 5 * F, 0); w.Hin = Hc; w.Win = Hc; w.Ci = l.Ci;
+        w.dy = g->act(g->D, 5 * F, (5 - k) * F); w.Hout = Hc; w.Wout = Hc; w.Co = l.Co; w.B = B; w.stride = 1;
+        w.dw = g->gpk + l.pk_off; w.dbias = g->gpk + l.pkb_off;
+        wops.push_back(w);
+      }
       // gx = conv(D, Wt_0) + s_in*gin (+ gR when this is the RRDB's first block)
       void* gout = (d == 0) ? g->gR : gxs[d & 1];
       ConvOp op;
@@ -476,6 +501,9 @@ static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_co
       s_in = 1.f;
     }
   }
+  g->D = D0;
+  if (batched_wgrad && !wops.empty())  // all 15R dense-conv weight + bias gradients in one tcgen05 launch
+    DG_TRY(wgrad_umma_batched(wops.data(), (int)wops.size(), g->wg_table_dev, g->wg_shadow, 2, st));
   // dL/d(out1) = gR (through the trunk / conv2) + gT1 (long skip)
   DG_TRY(scale_add(g->act(g->gx0, F), g->act(g->gR, F), 1.f, g->act(g->gT1, F), 1.f, pix, F, st));
   DG_TRY(wgrad(g->idx_conv1(), g->act(g->x0, g->Cin), Hc, g->act(g->gx0, F)));

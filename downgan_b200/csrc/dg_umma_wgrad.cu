@@ -11,6 +11,8 @@
 // per-tap accumulators (9 x NT columns) live in TMEM across all the tiles a CTA walks.  Stride-2
 // convolutions stage x as four parity sub-images so that every tap is again a constant offset.
 // Partial sums of different CTAs are combined with vectorised fp32 reductions (red.global.add.v4).
+#include <algorithm>
+
 #include "dg_umma.cuh"
 
 namespace dg {
@@ -30,16 +32,19 @@ struct WgArgs {
   unsigned x_bytes, d_off, d_bytes;   // per-buffer x region size, offset of the dy buffers, per-buffer dy size
 };
 
-__global__ void __launch_bounds__(WG_THREADS_U) wgrad_umma_kernel(const WgArgs a) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t mbar[2];
-  __shared__ uint32_t tmem_slot;
+__device__ __forceinline__ void wgrad_body(const WgArgs& a, uint8_t* smem, uint64_t* mbar, uint32_t* tmem_slot_p) {
+  uint32_t& tmem_slot = *tmem_slot_p;
   const WgradOp& op = a.op;
   const int tid = threadIdx.x, warp = tid >> 5;
+  if ((int)blockIdx.y * a.NT >= op.Co) return;
   const int co0 = blockIdx.y * a.NT;
   const int t_begin = blockIdx.x * a.tiles_per_cta;
   const int t_end = min(a.tiles_total, t_begin + a.tiles_per_cta);
   if (t_begin >= t_end) return;
+  // bias gradient: thread t sums channel (t % NT) over positions t / NT, t / NT + 128 / NT, ...
+  const int bc = tid % a.NT, bslice = tid / a.NT, bstep = WG_THREADS_U / a.NT;
+  const bool bias_on = op.dbias != nullptr && bslice < bstep;
+  float bsum = 0.f;
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)a.tmem_cols);
   if (tid == 32) { mbar_init(smem_u32(&mbar[0]), 1); mbar_init(smem_u32(&mbar[1]), 1); }
@@ -99,6 +104,11 @@ __global__ void __launch_bounds__(WG_THREADS_U) wgrad_umma_kernel(const WgArgs a
     cp_async_wait_all();
     fence_proxy_async();
     __syncthreads();
+    if (bias_on) {  // column sums of the staged dy tile (zero outside the image)
+      const uint8_t* dz = smem + a.d_off + buf * a.d_bytes + (bc >> 3) * a.PBd + (bc & 7) * 2;
+      for (int pos = bslice; pos < a.npos16; pos += bstep)
+        bsum += __bfloat162float(*reinterpret_cast<const bf16*>(dz + pos * 16));
+    }
     if (tid == 0) {
       tc_fence_after();
       for (int ks = 0; ks < ksteps; ++ks) {
@@ -143,9 +153,32 @@ __global__ void __launch_bounds__(WG_THREADS_U) wgrad_umma_kernel(const WgArgs a
       }
     }
   }
+  if (bias_on) atomicAdd(op.dbias + co0 + bc, bsum);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, (uint32_t)a.tmem_cols);
+}
+
+__global__ void __launch_bounds__(WG_THREADS_U) wgrad_umma_kernel(const WgArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ uint32_t tmem_slot;
+  wgrad_body(a, smem, mbar, &tmem_slot);
+}
+
+// one launch for many layers: blockIdx.z selects the op (all ops share the launch geometry limits)
+__global__ void __launch_bounds__(WG_THREADS_U) wgrad_umma_batched_kernel(const WgArgs* __restrict__ table) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ WgArgs sa;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(table + blockIdx.z);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sa);
+    for (int i = threadIdx.x; i < (int)(sizeof(WgArgs) / 4); i += WG_THREADS_U) dst[i] = src[i];
+  }
+  __syncthreads();
+  wgrad_body(sa, smem, mbar, &tmem_slot);
 }
 
 bool plan_wgrad(const WgradOp& op, WgArgs& a) {
@@ -223,7 +256,48 @@ int wgrad_umma(const WgradOp& op, cudaStream_t st) {
             (double)total * op.Co * 2.0 + (double)op.B * op.Hin * op.Win * op.Ci * 2.0, st);
   wgrad_umma_kernel<<<dim3((unsigned)S, (unsigned)n_chunks), WG_THREADS_U, smem_total(a), st>>>(a);
   DG_LAUNCH_CHECK();
-  if (op.dbias) DG_TRY(colsum(op.dy, (size_t)total, op.Co, op.dbias, st));
+  return 0;  // the bias gradient (op.dbias) is accumulated inside the kernel
+}
+
+size_t wgrad_umma_args_size() { return sizeof(WgArgs); }
+
+// Many weight gradients in ONE launch (blockIdx.z = op).  `table_dev` holds n * wgrad_umma_args_size()
+// bytes; `shadow` is the host copy of what was last uploaded (re-uploaded only when the plan changes,
+// e.g. another batch size).  S_per_op = position split per op.
+int wgrad_umma_batched(const WgradOp* ops, int n, void* table_dev, std::vector<unsigned char>& shadow, int S_per_op,
+                       cudaStream_t st) {
+  if (n <= 0) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DG_CUDA(cudaFuncSetAttribute(wgrad_umma_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_MAX_SMEM));
+    attr_set = true;
+  }
+  std::vector<WgArgs> tab((size_t)n);
+  unsigned smem = 0, gx = 1, gy = 1;
+  double flops = 0, bytes = 0;
+  for (int i = 0; i < n; ++i) {
+    WgArgs& a = tab[(size_t)i];
+    if (!plan_wgrad(ops[i], a)) { set_error("wgrad_umma_batched: op %d unsupported", i); return DG_ERR_INVALID; }
+    long long S = S_per_op;
+    if (S > a.tiles_total) S = a.tiles_total;
+    if (S < 1) S = 1;
+    a.tiles_per_cta = (int)((a.tiles_total + S - 1) / S);
+    S = (a.tiles_total + a.tiles_per_cta - 1) / a.tiles_per_cta;
+    gx = std::max(gx, (unsigned)S);
+    gy = std::max(gy, (unsigned)(ops[i].Co / a.NT));
+    smem = std::max(smem, smem_total(a));
+    const double total = (double)ops[i].B * ops[i].Hout * ops[i].Wout;
+    flops += 2.0 * total * ops[i].Co * ops[i].Ci * 9.0;
+    bytes += total * ops[i].Co * 2.0 + (double)ops[i].B * ops[i].Hin * ops[i].Win * ops[i].Ci * 2.0;
+  }
+  const size_t nbytes = sizeof(WgArgs) * (size_t)n;
+  if (shadow.size() != nbytes || memcmp(shadow.data(), tab.data(), nbytes) != 0) {
+    shadow.assign((const unsigned char*)tab.data(), (const unsigned char*)tab.data() + nbytes);
+    DG_CUDA(cudaMemcpyAsync(table_dev, shadow.data(), nbytes, cudaMemcpyHostToDevice, st));
+  }
+  Prof prof(PC_WGRAD_UMMA, flops, bytes, st);
+  wgrad_umma_batched_kernel<<<dim3(gx, gy, (unsigned)n), WG_THREADS_U, smem, st>>>((const WgArgs*)table_dev);
+  DG_LAUNCH_CHECK();
   return 0;
 }
 
