@@ -179,53 +179,96 @@ __global__ void __launch_bounds__(128) conv_co2_kernel(ConvOp op) {
 
 // ---------------------------------------------------------------------------------------------
 // weight gradient with one 2-channel side and one 16-channel side (288 outputs), stride 1.
-// lane = (c16 = lane & 15, c2 = lane >> 4) owns the nine taps of one (ci, co) pair.
+// lane = (tap = lane % 9, sub = lane / 9): a warp walks three pixels per iteration, each lane owns
+// the 2 x 16 outputs of its tap, so one 8-byte and one 32/64-byte load feed 32 FMAs.
 //   x2 == 1 : x has 2 channels (critic features.0), dy has 16
 //   x2 == 0 : x has 16 channels, dy has 2 (generator conv3.2)
 // ---------------------------------------------------------------------------------------------
 constexpr int WS_WARPS = 8;
+
+__device__ __forceinline__ void ld16(const TV& t, size_t i, bool ok, float* v) {
+  if (!ok) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    return;
+  }
+  if (t.bf) {
+    const uint4* p = reinterpret_cast<const uint4*>((const bf16*)t.p + i);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint4 q = p[h];
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[h * 8 + 2 * k] = __uint_as_float(w[k] << 16);
+        v[h * 8 + 2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+      }
+    }
+  } else {
+    const float4* p = reinterpret_cast<const float4*>((const float*)t.p + i);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float4 q = p[h];
+      v[4 * h] = q.x; v[4 * h + 1] = q.y; v[4 * h + 2] = q.z; v[4 * h + 3] = q.w;
+    }
+  }
+}
+__device__ __forceinline__ void ld2(const TV& t, size_t i, bool ok, float* v) {
+  v[0] = ok ? ldv(t.p, t.bf, i) : 0.f;
+  v[1] = ok ? ldv(t.p, t.bf, i + 1) : 0.f;
+}
+
 __global__ void __launch_bounds__(WS_WARPS * 32) wgrad_skinny_kernel(WgradOp op, int x2, long long pix_per_warp) {
-  __shared__ float red[WS_WARPS][9][32];
+  __shared__ float red[WS_WARPS][27][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c16 = lane & 15, c2 = lane >> 4;
+  const int tap = lane % 9, sub = lane / 9;
+  const bool active = lane < 27;
+  const int ky = tap / 3, kx = tap - 3 * ky;
   const int H = op.Hin, W = op.Win;
   const long long total = (long long)op.B * H * W;
   const long long gw = (long long)blockIdx.x * WS_WARPS + warp;
   const long long p0 = gw * pix_per_warp, p1 = min(total, p0 + pix_per_warp);
-  const int cx = x2 ? c2 : c16, cd = x2 ? c16 : c2;
-  float acc[9];
+  float acc[2][16];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) acc[k] = 0.f;
-  for (long long p = p0; p < p1; ++p) {
-    const int x = (int)(p % W);
-    const long long t = p / W;
-    const int y = (int)(t % H);
-    const long long nrow = t - y;  // n*H
-    const float d = ldv(op.dy.p, op.dy.bf, (size_t)p * op.dy.pitch + op.dy.coff + cd);
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int gy = y + ky - 1;
-      if (gy < 0 || gy >= H) continue;
+    for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+  if (active) {
+    for (long long p = p0 + sub; p < p1; p += 3) {
+      const int x = (int)(p % W);
+      const long long t = p / W;
+      const int y = (int)(t % H);
+      const long long nrow = t - y;  // n*H
+      const int gy = y + ky - 1, gx = x + kx - 1;
+      const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+      const size_t xi = (((size_t)nrow + gy) * W + gx) * op.x.pitch + op.x.coff;
+      const size_t di = (size_t)p * op.dy.pitch + op.dy.coff;
+      float a2[2], a16[16];
+      if (x2) { ld2(op.x, xi, ok, a2); ld16(op.dy, di, true, a16); }
+      else { ld16(op.x, xi, ok, a16); ld2(op.dy, di, true, a2); }
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int gx = x + kx - 1;
-        if (gx < 0 || gx >= W) continue;
-        const float xv = ldv(op.x.p, op.x.bf, (((size_t)nrow + gy) * W + gx) * op.x.pitch + op.x.coff + cx);
-        acc[ky * 3 + kx] = fmaf(xv, d, acc[ky * 3 + kx]);
+      for (int j = 0; j < 16; ++j) {
+        acc[0][j] = fmaf(a2[0], a16[j], acc[0][j]);
+        acc[1][j] = fmaf(a2[1], a16[j], acc[1][j]);
       }
     }
   }
+  // block reduction: rows = lane (tap, sub), 32 values each
+  if (active) {
 #pragma unroll
-  for (int k = 0; k < 9; ++k) red[warp][k][lane] = acc[k];
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) red[warp][lane][i * 16 + j] = acc[i][j];
+  }
   __syncthreads();
   const int CoP = (op.Co + 15) & ~15;
   for (int i = threadIdx.x; i < 288; i += WS_WARPS * 32) {
-    const int k = i / 32, l = i % 32;
+    const int k = i / 32, e = i % 32;   // k = tap, e = c2*16 + c16
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < WS_WARPS; ++w) s += red[w][k][l];
-    const int l16 = l & 15, l2 = l >> 4;
-    const int ci = x2 ? l2 : l16, co = x2 ? l16 : l2;
+    for (int w = 0; w < WS_WARPS; ++w) s += red[w][k][e] + red[w][k + 9][e] + red[w][k + 18][e];
+    const int c2 = e >> 4, c16 = e & 15;
+    const int ci = x2 ? c2 : c16, co = x2 ? c16 : c2;
     atomicAdd(&op.dw[((size_t)k * op.Ci + ci) * CoP + co], s);
   }
 }
@@ -258,7 +301,9 @@ int conv_skinny(const ConvOp& op, cudaStream_t st) {
 
 bool wgrad_skinny_supported(const WgradOp& op) {
   if (op.stride != 1 || op.Hin != op.Hout || op.Win != op.Wout) return false;
-  return (op.Ci == 2 && op.Co == 16) || (op.Ci == 16 && op.Co == 2);
+  if (op.Ci == 2 && op.Co == 16) return aligned16(op.dy);
+  if (op.Ci == 16 && op.Co == 2) return aligned16(op.x);
+  return false;
 }
 
 int wgrad_skinny(const WgradOp& op, cudaStream_t st) {
