@@ -207,3 +207,7 @@ size_t wgrad_umma_args_size();
 int wgrad_umma_batched(const WgradOp* ops, int n, void* table_dev, std::vector<unsigned char>& shadow, int S_per_op,
                        cudaStream_t st);
 }  // namespace dg
+
+namespace dg {
+int pack_trunk_slices(const float* pk_first_dense, void* dst_bf16, int n_db, cudaStream_t st);
+}  // namespace dg

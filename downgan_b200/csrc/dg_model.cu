@@ -80,6 +80,7 @@ struct dg_generator {
   PackDesc *tab_fwd = nullptr, *tab_dgrad = nullptr;
   int n_fwd = 0, n_dgrad = 0, max_fwd = 0, max_dgrad = 0;
   bf16 *pk_u = nullptr, *pkd_u = nullptr;  // tcgen05 B-operand images (bf16 mode)
+  bf16* pk_trunk = nullptr;                // slice-major images of the dense convs for the fused trunk kernel
   UmmaPackDesc *utab_fwd = nullptr, *utab_dgrad = nullptr;
   int n_ufwd = 0, n_udgrad = 0, max_ufwd = 1, max_udgrad = 1;
   std::vector<long long> db_dgrad_off;  // [(r*3+d)*5 + k] packed offset of Wt_k
@@ -244,6 +245,7 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
   GA(g->pkd, sizeof(float) * std::max<long long>(pkd, 1));
   GA(g->pk_u, sizeof(bf16) * (pk + 64));
   GA(g->pkd_u, sizeof(bf16) * (std::max<long long>(pkd, 1) + 64));
+  GA(g->pk_trunk, sizeof(bf16) * ((size_t)std::max(1, g->R * 3) * 9 * F * F * 15 + 64));
   if ((s = upload_table(g->pool, tf, &g->tab_fwd)) != 0) { dg_generator_destroy(g); return s; }
   if ((s = upload_table(g->pool, td, &g->tab_dgrad)) != 0) { dg_generator_destroy(g); return s; }
   if ((s = upload_utable(g->pool, uf, &g->utab_fwd)) != 0) { dg_generator_destroy(g); return s; }
@@ -300,6 +302,8 @@ extern "C" int dg_generator_pack(dg_generator* g, const float* params, void* str
   DG_TRY(pack_weights(params, g->pkd, g->tab_dgrad, g->n_dgrad, g->max_dgrad, st));
   DG_TRY(pack_umma(g->pk, g->pk_u, g->utab_fwd, g->n_ufwd, g->max_ufwd, st));
   DG_TRY(pack_umma(g->pkd, g->pkd_u, g->utab_dgrad, g->n_udgrad, g->max_udgrad, st));
+  if (trunk_fused_supported(g->F, g->Hc, g->R, g->bf))
+    DG_TRY(pack_trunk_slices(g->pk + g->layers[g->idx_db(0, 0, 1)].pk_off, g->pk_trunk, g->R * 3, st));
   g->packed = true;
   return 0;
 }
@@ -328,7 +332,7 @@ static int gen_forward_internal(dg_generator* g, int B, bool save, cudaStream_t 
     // persistent tcgen05 kernel: the whole RRDB trunk with the concat buffer resident in shared memory
     const Layer& l0 = g->layers[g->idx_db(0, 0, 1)];
     DG_TRY(trunk_fwd_fused(g->db[0], 5 * F, 0, g->trunk_out, F, save ? (void* const*)g->db_ptrs_dev : nullptr,
-                           g->pk_u + l0.pk_off, g->pk + l0.pkb_off, g->R, B, st));
+                           g->pk_trunk, g->pk + l0.pkb_off, g->R, B, st));
   }
   for (int r = 0; r < (fused_trunk ? 0 : g->R); ++r)
     for (int d = 0; d < 3; ++d) {

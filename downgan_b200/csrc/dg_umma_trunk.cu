@@ -21,6 +21,8 @@ constexpr int TF = 16;            // filters
 constexpr int TW = 16;            // coarse grid edge
 constexpr int TPW = TW + 2;       // padded width
 constexpr int TNMT = 3;           // M-tiles: 3*128 >= 16*18-2
+constexpr int T_COLS_MT = 5 * TF; // TMEM columns per M-tile: one 16-column accumulator per layer of the block
+constexpr int T_TMEM_COLS = 256;  // 3 * 80 = 240 -> power of two
 constexpr int TPBPOS = 424;       // positions per plane incl. over-read slack (3*128 + 2*18 + 2 -> 424)
 constexpr int TPB = TPBPOS * 16;  // plane stride in bytes
 constexpr int T_X_BYTES = 10 * TPB;
@@ -32,7 +34,7 @@ struct TrunkArgs {
   const bf16* x_in; int in_pitch, in_coff;  // (B,16,16,pitch): conv1 output
   bf16* y_out; int out_pitch;               // (B,16,16,pitch): trunk output
   bf16* const* db_bufs;                     // [3R] concat buffers (pitch 80) or nullptr
-  const bf16* w;                            // B-operand images of the 15R dense convs, consecutive
+  const bf16* w;                            // slice-major B-operand images, 5 per dense block (pack_trunk_slices)
   const float* bias;                        // 16 floats per dense conv, consecutive
   int R, B;
 };
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(128) trunk_fwd_kernel(const TrunkArgs a) {
   const uint32_t sX = smem_u32(smem);
   const uint32_t sW = sX + T_X_BYTES;
 
-  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 64);
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), T_TMEM_COLS);
   if (tid == 32) mbar_init(smem_u32(&mbar), TNMT);
   // zero the whole concat tile: halo ring and pad columns are the convolution's zero padding
   for (int i = tid; i < T_X_BYTES / 16; i += 128) st_shared16(sX + i * 16, make_uint4(0, 0, 0, 0));
@@ -79,14 +81,13 @@ __global__ void __launch_bounds__(128) trunk_fwd_kernel(const TrunkArgs a) {
     cp_async16(sX + pl * TPB + ((y + 1) * TPW + x + 1) * 16,
                a.x_in + ((size_t)n * 256 + pix) * a.in_pitch + a.in_coff + pl * 8, 16);
   }
-  for (int i = tid; i < 288; i += 128) cp_async16(sW + i * 16, reinterpret_cast<const uint4*>(a.w) + i, 16);
+  for (int i = tid; i < 18 * 5 * TF; i += 128) cp_async16(sW + i * 16, reinterpret_cast<const uint4*>(a.w) + i, 16);
   cp_async_wait_all();
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t idesc = instr_desc(128, TF);
   const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
 
   // this thread's three output positions (one per M-tile)
@@ -102,9 +103,15 @@ __global__ void __launch_bounds__(128) trunk_fwd_kernel(const TrunkArgs a) {
   }
   uint4 xr[TNMT][2];  // RRDB input at this thread's positions (bf16 x 16)
   const int total = a.R * 15;
-  size_t w_elem = 0;  // element offset of the current layer's weight image
+  size_t w_elem = 0;  // element offset of the current slice's weight image
+  // Input-stationary schedule: as soon as slice j of the concat buffer (x, o1..o4) exists, ONE round
+  // of MMAs adds its contribution to ALL later layers j+1..5 (N = 16*(5-j) output channels, weight
+  // image = slice j of W_{j+1..5} side by side).  Every A block is then read from shared memory once
+  // per dense block instead of once per consuming layer (3x less operand traffic, the actual bound
+  // of an N=16 MMA), and layer j+1's accumulator is complete after round j.
   for (int L = 0; L < total; ++L) {
-    const int db = L / 5, k = L - db * 5 + 1, d = db % 3;
+    const int db = L / 5, k = L - db * 5 + 1, d = db % 3, j = k - 1;
+    const int Nj = TF * (5 - j);
     const uint32_t wb = sW + (L & 1) * T_W_BYTES;
     if (k == 1 && d == 0) {
 #pragma unroll
@@ -113,29 +120,27 @@ __global__ void __launch_bounds__(128) trunk_fwd_kernel(const TrunkArgs a) {
         xr[mt][1] = ld_shared16(sX + TPB + pos[mt] * 16);
       }
     }
-    // ---- MMAs of this layer: warp w issues M-tile w (9 taps x k K-steps)
+    // ---- MMA round of slice j: warp w issues M-tile w (9 taps, K = 16 channels, N = Nj)
     if (warp < TNMT && lane == 0) {
-      uint32_t acc = 0;
+      const uint32_t idj = instr_desc(128, Nj);
+      const uint32_t wplane = Nj * 16;
       for (int tap = 0; tap < 9; ++tap) {
         const int dy = tap / 3, dx = tap - 3 * dy;
-        const uint32_t a0 = sX + (warp * 128 + dy * TPW + dx) * 16;
-        const uint32_t b0 = wb + tap * (2 * k) * 256;
-        for (int kc = 0; kc < k; ++kc) {
-          umma_f16(tmem + warp * TF, smem_desc(a0 + 2 * kc * TPB, TPB, 128), smem_desc(b0 + 2 * kc * 256, 256, 128),
-                   idesc, acc);
-          acc = 1;
-        }
+        const uint32_t a0 = sX + 2 * j * TPB + (warp * 128 + dy * TPW + dx) * 16;
+        const uint32_t b0 = wb + tap * 2 * wplane;
+        umma_f16(tmem + warp * T_COLS_MT + j * TF, smem_desc(a0, TPB, 128), smem_desc(b0, wplane, 128), idj,
+                 (j > 0 || tap > 0) ? 1u : 0u);
       }
       umma_commit(smem_u32(&mbar));
     }
     __syncwarp();
-    // ---- prefetch the next layer's weights into the other buffer while the tensor pipe runs
-    const size_t w_next = w_elem + (size_t)9 * k * TF * TF;
+    // ---- prefetch the next slice's weights into the other buffer while the tensor pipe runs
+    const size_t w_next = w_elem + (size_t)9 * TF * Nj;
     if (L + 1 < total) {
-      const int kn = (k == 5) ? 1 : k + 1;
+      const int Nn = (k == 5) ? 5 * TF : Nj - TF;
       const uint4* src = reinterpret_cast<const uint4*>(a.w + w_next);
       const uint32_t dst = sW + ((L + 1) & 1) * T_W_BYTES;
-      for (int i = tid; i < 288 * kn; i += 128) cp_async16(dst + i * 16, src + i, 16);
+      for (int i = tid; i < 18 * Nn; i += 128) cp_async16(dst + i * 16, src + i, 16);
     }
     float bias[16];
 #pragma unroll
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(128) trunk_fwd_kernel(const TrunkArgs a) {
 #pragma unroll
     for (int mt = 0; mt < TNMT; ++mt) {
       float v[16];
-      tmem_ld16(tmem + lane_base + mt * TF, v);
+      tmem_ld16(tmem + lane_base + mt * T_COLS_MT + j * TF, v);
       if (!valid[mt]) continue;
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] += bias[j];
@@ -196,10 +201,40 @@ __global__ void __launch_bounds__(128) trunk_fwd_kernel(const TrunkArgs a) {
     __syncthreads();
     tc_fence_after();
   }
-  if (warp == 0) tmem_dealloc(tmem, 64);
+  if (warp == 0) tmem_dealloc(tmem, T_TMEM_COLS);
+}
+
+// fp32 packed per-layer weights [tap][16k][16] of one dense block  ->  slice-major bf16 images:
+// slice j: [tap][2 planes][N_j = 16*(5-j) rows = layers j+1..5 side by side][8 channels of slice j]
+constexpr int T_DB_ELEMS = 9 * TF * TF * 15;
+__global__ void pack_trunk_kernel(const float* __restrict__ pk_db0, bf16* __restrict__ dst, int n_db) {
+  const int db = blockIdx.y;
+  if (db >= n_db) return;
+  const float* src = pk_db0 + (size_t)db * T_DB_ELEMS;
+  bf16* out = dst + (size_t)db * T_DB_ELEMS;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < T_DB_ELEMS; e += gridDim.x * blockDim.x) {
+    int j = 0, base = 0;
+    while (j < 4 && e >= base + 9 * TF * TF * (5 - j)) { base += 9 * TF * TF * (5 - j); ++j; }
+    const int Nj = TF * (5 - j);
+    int r = e - base;
+    const int c8 = r & 7; r >>= 3;
+    const int row = r % Nj; r /= Nj;
+    const int pl = r & 1, tap = r >> 1;
+    const int k = j + 1 + row / TF, co = row % TF;        // consuming layer (1-based) and its output channel
+    const int ci = TF * j + pl * 8 + c8;                   // input channel inside the concat buffer
+    const size_t layer_off = (size_t)9 * TF * TF * (k - 1) * k / 2;  // layers 1..k-1 of this block
+    out[e] = __float2bfloat16_rn(src[layer_off + ((size_t)tap * (TF * k) + ci) * TF + co]);
+  }
 }
 
 }  // namespace
+
+int pack_trunk_slices(const float* pk_first_dense, void* dst_bf16, int n_db, cudaStream_t st) {
+  if (n_db <= 0) return 0;
+  pack_trunk_kernel<<<dim3(32, n_db), 256, 0, st>>>(pk_first_dense, (bf16*)dst_bf16, n_db);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
 
 bool trunk_fused_supported(int F, int Hc, int R, int bf) { return bf && F == TF && Hc == TW && R >= 1; }
 
