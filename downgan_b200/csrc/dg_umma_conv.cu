@@ -35,6 +35,7 @@ struct UmmaArgs {
   int mode;
   int TH, PW, n_mt, PB, tiles_per_img, NT, tmem_cols, nplanes, nsub, CoP;
   int Ht, Wt;      // tile-space extent (S1/S2_FWD: output grid; S2_DGRAD: dy grid)
+  unsigned magic_np, magic_pw;  // ceil(2^32 / nplanes), ceil(2^32 / PW)
   unsigned w_off;  // byte offset of the weight image in dynamic smem
 };
 
@@ -148,15 +149,15 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const UmmaArgs 
   // ---- stage the input tile (zero fill = conv padding) and this CTA's slice of the weight image
   const uint32_t sa = smem_u32(smem);
   {
-    const int xpos = a.PB >> 4;
     const bf16* xb = (const bf16*)op.x.p;
-    const int total = xpos * a.nplanes;
+    // only the (TH + halo) rows of the tile are staged; positions beyond feed discarded rows only.
+    // index decomposition by multiply-high with precomputed reciprocals (exact for i < 2^16)
+    const int total = (a.TH + ((mode == S1) ? 2 : 1)) * PW * a.nplanes;
     for (int sub = 0; sub < a.nsub; ++sub) {
       const int py = sub >> 1, px = sub & 1;
       for (int i = tid; i < total; i += UMMA_THREADS) {
-        const int pos = i / a.nplanes, pl = i - pos * a.nplanes;
-        const int r = pos / PW, c = pos - r * PW;
-        if (r >= a.TH + ((mode == S1) ? 2 : 1)) continue;  // beyond the tile: only read by discarded rows
+        const int pos = (int)__umulhi((unsigned)i, a.magic_np), pl = i - pos * a.nplanes;
+        const int r = (int)__umulhi((unsigned)pos, a.magic_pw), c = pos - r * PW;
         int gy, gx;
         if (mode == S1) { gy = y0 - 1 + r; gx = c - 1; }
         else if (mode == S2_FWD) { gy = 2 * (y0 - 1 + r) + py; gx = 2 * (c - 1) + px; }
@@ -300,6 +301,7 @@ bool plan(const ConvOp& op, UmmaArgs& a) {
     const int pb_pos = ((n_mt * 128 + halo) + 7) & ~7;
     const size_t smem = (size_t)nsub * nplanes * pb_pos * 16 + wbytes;
     if (smem > (size_t)MAX_SMEM) break;
+    if ((TH + 2) * PW * nplanes >= 65536) break;  // loader index arithmetic is exact below 2^16
     const int ntiles = (Ht + TH - 1) / TH;
     const double eff = (double)(Ht * Wt) / ((double)ntiles * n_mt * 128);
     if (eff > best + 1e-9) { best = eff; bestTH = TH; best_mt = n_mt; }
@@ -315,6 +317,8 @@ bool plan(const ConvOp& op, UmmaArgs& a) {
   while (pc < cols) pc <<= 1;
   a.tmem_cols = pc;
   a.w_off = (unsigned)(nsub * nplanes * a.PB);
+  a.magic_np = (unsigned)((0x100000000ULL + nplanes - 1) / nplanes);
+  a.magic_pw = (unsigned)((0x100000000ULL + PW - 1) / PW);
   return true;
 }
 

@@ -30,6 +30,7 @@ struct WgArgs {
   int tiles_per_img, tiles_total, tiles_per_cta;
   int NT, tmem_cols;
   unsigned x_bytes, d_off, d_bytes;   // per-buffer x region size, offset of the dy buffers, per-buffer dy size
+  unsigned magic_nx, magic_nd, magic_pw;  // ceil(2^32 / nplx), ceil(2^32 / npld), ceil(2^32 / PWt)
 };
 
 __device__ __forceinline__ void wgrad_body(const WgArgs& a, uint8_t* smem, uint64_t* mbar, uint32_t* tmem_slot_p) {
@@ -73,8 +74,8 @@ __device__ __forceinline__ void wgrad_body(const WgArgs& a, uint8_t* smem, uint6
       const int py = sub >> 1, px = sub & 1;
       const int total = xpos * a.nplx;
       for (int i = tid; i < total; i += WG_THREADS_U) {
-        const int pos = i / a.nplx, pl = i - pos * a.nplx;
-        const int r = pos / a.PWt, c = pos - r * a.PWt;
+        const int pos = (int)__umulhi((unsigned)i, a.magic_nx), pl = i - pos * a.nplx;
+        const int r = (int)__umulhi((unsigned)pos, a.magic_pw), c = pos - r * a.PWt;
         int gy, gx;
         bool ok;
         if (s == 1) {
@@ -93,8 +94,8 @@ __device__ __forceinline__ void wgrad_body(const WgArgs& a, uint8_t* smem, uint6
     {
       const int total = a.npos16 * a.npld;
       for (int i = tid; i < total; i += WG_THREADS_U) {
-        const int pos = i / a.npld, pl = i - pos * a.npld;
-        const int r = pos / a.PWt, c = pos - r * a.PWt;
+        const int pos = (int)__umulhi((unsigned)i, a.magic_nd), pl = i - pos * a.npld;
+        const int r = (int)__umulhi((unsigned)pos, a.magic_pw), c = pos - r * a.PWt;
         const int gy = y0 + r;
         const bool ok = r < a.TH && gy < op.Hout && c < op.Wout;
         const bf16* src = ok ? db + (((size_t)n * op.Hout + gy) * op.Wout + c) * op.dy.pitch + op.dy.coff + co0 + pl * 8 : db;
@@ -204,6 +205,7 @@ bool plan_wgrad(const WgradOp& op, WgArgs& a) {
     unsigned total = 2 * x_bytes + 2 * d_bytes;
     if (span_end > total) total = span_end;
     if (total > (unsigned)WG_MAX_SMEM) break;
+    if ((long long)xpos * nplx >= 65536 || (long long)npos16 * npld >= 65536) break;  // exact index arithmetic
     bestTH = TH;
     b.TH = TH; b.PWt = PWt; b.npos16 = npos16; b.PBx = (int)PBx; b.PBd = (int)PBd;
     b.x_bytes = x_bytes; b.d_off = 2 * x_bytes; b.d_bytes = d_bytes;
@@ -213,6 +215,9 @@ bool plan_wgrad(const WgradOp& op, WgArgs& a) {
   a.op = op;
   a.CoP = round_up(op.Co, 16);
   a.nplx = nplx; a.npld = npld; a.nsub = nsub; a.NT = NT;
+  a.magic_nx = (unsigned)((0x100000000ULL + nplx - 1) / nplx);
+  a.magic_nd = (unsigned)((0x100000000ULL + npld - 1) / npld);
+  a.magic_pw = (unsigned)((0x100000000ULL + PWt - 1) / PWt);
   a.tiles_per_img = (op.Hout + a.TH - 1) / a.TH;
   a.tiles_total = a.tiles_per_img * op.B;
   int cols = 9 * NT, pc = 32;
