@@ -19,6 +19,8 @@
 // position, column = output channel) and is read back with tcgen05.ld for the fused epilogue (bias,
 // residual scale + skips, LeakyReLU / mask, bf16 pack, pixel-(un)shuffle addressing, channel-offset
 // store into the dense-block concat buffer).
+#include <algorithm>
+
 #include "dg_umma.cuh"
 
 namespace dg {
@@ -36,7 +38,9 @@ struct UmmaArgs {
   int TH, PW, n_mt, PB, tiles_per_img, NT, tmem_cols, nplanes, nsub, CoP;
   int Ht, Wt;      // tile-space extent (S1/S2_FWD: output grid; S2_DGRAD: dy grid)
   unsigned magic_np, magic_pw;  // ceil(2^32 / nplanes), ceil(2^32 / PW)
-  unsigned w_off;  // byte offset of the weight image in dynamic smem
+  unsigned w_off;  // byte offset of the weight image in dynamic smem (after the two input-tile buffers)
+  unsigned a_bytes;  // bytes of one input-tile buffer
+  int tiles_total, nbuf;
 };
 
 // 16 consecutive channels of a view at element index i (16-byte aligned, checked on the host)
@@ -131,128 +135,155 @@ __device__ __forceinline__ void epilogue16(const ConvOp& op, float* v, int n, in
   }
 }
 
+// Persistent over tiles: a CTA stages its weight slice ONCE, then walks tiles blockIdx.x,
+// blockIdx.x + gridDim.x, ...; the cp.async staging of tile i+1 (other buffer) is issued right
+// after the MMAs of tile i, so it overlaps the tensor pipe and the epilogue of tile i.
 __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const UmmaArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_slot;
   const ConvOp& op = a.op;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int n = blockIdx.x / a.tiles_per_img;
-  const int y0 = (blockIdx.x % a.tiles_per_img) * a.TH;
   const int co0 = blockIdx.y * a.NT;
-  const int rows = min(a.TH, a.Ht - y0);
   const int PW = a.PW, mode = a.mode;
+  if ((int)blockIdx.x >= a.tiles_total) return;
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)a.tmem_cols);
   if (tid == 32) mbar_init(smem_u32(&mbar), 1);
 
-  // ---- stage the input tile (zero fill = conv padding) and this CTA's slice of the weight image
-  const uint32_t sa = smem_u32(smem);
-  {
-    const bf16* xb = (const bf16*)op.x.p;
-    // only the (TH + halo) rows of the tile are staged; positions beyond feed discarded rows only.
-    // index decomposition by multiply-high with precomputed reciprocals (exact for i < 2^16)
-    const int total = (a.TH + ((mode == S1) ? 2 : 1)) * PW * a.nplanes;
-    for (int sub = 0; sub < a.nsub; ++sub) {
-      const int py = sub >> 1, px = sub & 1;
-      for (int i = tid; i < total; i += UMMA_THREADS) {
-        const int pos = (int)__umulhi((unsigned)i, a.magic_np), pl = i - pos * a.nplanes;
-        const int r = (int)__umulhi((unsigned)pos, a.magic_pw), c = pos - r * PW;
+  const uint32_t sa0 = smem_u32(smem);
+  const uint32_t sw = sa0 + a.w_off;
+  const bf16* xb = (const bf16*)op.x.p;
+  const int trows = a.TH + ((mode == S1) ? 2 : 1);
+
+  // stage one input tile (zero fill = conv padding); only the (TH + halo) rows are written, positions
+  // beyond feed discarded rows only.  A thread owns (column c, plane pl) pairs and walks the rows, so
+  // the per-chunk work is an add and a compare (no index decomposition in the inner loop).
+  const int row_elems = PW * a.nplanes;
+  auto load_tile = [&](int tile, uint32_t sa) {
+    const int n = tile / a.tiles_per_img;
+    const int y0 = (tile - n * a.tiles_per_img) * a.TH;
+    const int ystep = (mode == S2_FWD) ? 2 : 1;
+    for (int e = tid; e < row_elems; e += UMMA_THREADS) {
+      const int c = (int)__umulhi((unsigned)e, a.magic_np), pl = e - c * a.nplanes;
+      for (int sub = 0; sub < a.nsub; ++sub) {
+        const int py = sub >> 1, px = sub & 1;
         int gy, gx;
-        if (mode == S1) { gy = y0 - 1 + r; gx = c - 1; }
-        else if (mode == S2_FWD) { gy = 2 * (y0 - 1 + r) + py; gx = 2 * (c - 1) + px; }
-        else { gy = y0 + r; gx = c; }
-        const bool ok = gy >= 0 && gy < op.Hin && gx >= 0 && gx < op.Win;
-        const bf16* src = ok ? xb + (((size_t)n * op.Hin + gy) * op.Win + gx) * op.x.pitch + op.x.coff + pl * 8 : xb;
-        cp_async16(sa + (sub * a.nplanes + pl) * a.PB + pos * 16, src, ok ? 16 : 0);
+        if (mode == S1) { gy = y0 - 1; gx = c - 1; }
+        else if (mode == S2_FWD) { gy = 2 * (y0 - 1) + py; gx = 2 * (c - 1) + px; }
+        else { gy = y0; gx = c; }
+        const bool okx = gx >= 0 && gx < op.Win;
+        const bf16* src = xb + (((size_t)n * op.Hin + gy) * op.Win + (okx ? gx : 0)) * op.x.pitch + op.x.coff + pl * 8;
+        const size_t sstep = (size_t)ystep * op.Win * op.x.pitch;
+        uint32_t dst = sa + (sub * a.nplanes + pl) * a.PB + c * 16;
+        for (int r = 0; r < trows; ++r, gy += ystep, src += sstep, dst += PW * 16) {
+          const bool ok = okx && gy >= 0 && gy < op.Hin;
+          cp_async16(dst, ok ? src : xb, ok ? 16 : 0);
+        }
       }
     }
+  };
+  {
     // weights: planes [tap*nplanes + pl], rows co0..co0+NT of CoP, 16 B per row
     const int wrows = 9 * a.nplanes * a.NT;
     const uint4* wsrc = reinterpret_cast<const uint4*>(op.w_umma);
-    const uint32_t sw = sa + a.w_off;
     for (int i = tid; i < wrows; i += UMMA_THREADS) {
       const int tp = i / a.NT, row = i - tp * a.NT;
       cp_async16(sw + i * 16, wsrc + (size_t)tp * a.CoP + co0 + row, 16);
     }
   }
+  load_tile(blockIdx.x, sa0);
   cp_async_wait_all();
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const int ncls = (mode == S2_DGRAD) ? 4 : 1;
+  const uint32_t idesc = instr_desc(128, a.NT);
+  const int kcs = a.nplanes >> 1;
+  const uint32_t wplane = a.NT * 16;
 
-  // ---- one thread issues every MMA of the tile
-  if (tid == 0) {
-    const uint32_t idesc = instr_desc(128, a.NT);
-    const uint32_t sw = sa + a.w_off;
-    const int kcs = a.nplanes >> 1;
-    const uint32_t wplane = a.NT * 16;
-    if (mode != S2_DGRAD) {
-      for (int mt = 0; mt < a.n_mt; ++mt) {
-        uint32_t acc = 0;
-        for (int tap = 0; tap < 9; ++tap) {
-          const int ky = tap / 3, kx = tap - 3 * ky;
-          int sub = 0, shift;
-          if (mode == S1) shift = ky * PW + kx;
-          else { sub = ((ky == 1) ? 0 : 2) + ((kx == 1) ? 0 : 1); shift = ((ky == 0) ? 0 : 1) * PW + ((kx == 0) ? 0 : 1); }
-          const uint32_t a0 = sa + sub * a.nplanes * a.PB + (mt * 128 + shift) * 16;
-          const uint32_t b0 = sw + tap * a.nplanes * wplane;
-          for (int kc = 0; kc < kcs; ++kc) {
-            umma_f16(tmem + mt * a.NT, smem_desc(a0 + 2 * kc * a.PB, a.PB, 128),
-                     smem_desc(b0 + 2 * kc * wplane, wplane, 128), idesc, acc);
-            acc = 1;
-          }
-        }
-      }
-    } else {
-      // output parity class (py,px): taps ky in {1} (py=0) or {0,2} (py=1); ky=0 reads dy one row below
-      for (int mt = 0; mt < a.n_mt; ++mt)
-        for (int cls = 0; cls < 4; ++cls) {
-          const int py = cls >> 1, px = cls & 1;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x, ++it) {
+    const uint32_t sa = sa0 + ((a.nbuf == 2) ? (it & 1) * a.a_bytes : 0u);
+    // ---- one thread issues every MMA of the tile
+    if (tid == 0) {
+      if (mode != S2_DGRAD) {
+        for (int mt = 0; mt < a.n_mt; ++mt) {
           uint32_t acc = 0;
-          for (int ky = 0; ky < 3; ++ky) {
-            if ((py == 0) != (ky == 1)) continue;
-            for (int kx = 0; kx < 3; ++kx) {
-              if ((px == 0) != (kx == 1)) continue;
-              const int shift = ((ky == 0) ? 1 : 0) * PW + ((kx == 0) ? 1 : 0);
-              const uint32_t a0 = sa + (mt * 128 + shift) * 16;
-              const uint32_t b0 = sw + (ky * 3 + kx) * a.nplanes * wplane;
-              for (int kc = 0; kc < kcs; ++kc) {
-                umma_f16(tmem + (mt * 4 + cls) * a.NT, smem_desc(a0 + 2 * kc * a.PB, a.PB, 128),
-                         smem_desc(b0 + 2 * kc * wplane, wplane, 128), idesc, acc);
-                acc = 1;
-              }
+          for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap - 3 * ky;
+            int sub = 0, shift;
+            if (mode == S1) shift = ky * PW + kx;
+            else { sub = ((ky == 1) ? 0 : 2) + ((kx == 1) ? 0 : 1); shift = ((ky == 0) ? 0 : 1) * PW + ((kx == 0) ? 0 : 1); }
+            const uint32_t a0 = sa + sub * a.nplanes * a.PB + (mt * 128 + shift) * 16;
+            const uint32_t b0 = sw + tap * a.nplanes * wplane;
+            for (int kc = 0; kc < kcs; ++kc) {
+              umma_f16(tmem + mt * a.NT, smem_desc(a0 + 2 * kc * a.PB, a.PB, 128),
+                       smem_desc(b0 + 2 * kc * wplane, wplane, 128), idesc, acc);
+              acc = 1;
             }
           }
         }
+      } else {
+        // output parity class (py,px): taps ky in {1} (py=0) or {0,2} (py=1); ky=0 reads dy one row below
+        for (int mt = 0; mt < a.n_mt; ++mt)
+          for (int cls = 0; cls < 4; ++cls) {
+            const int py = cls >> 1, px = cls & 1;
+            uint32_t acc = 0;
+            for (int ky = 0; ky < 3; ++ky) {
+              if ((py == 0) != (ky == 1)) continue;
+              for (int kx = 0; kx < 3; ++kx) {
+                if ((px == 0) != (kx == 1)) continue;
+                const int shift = ((ky == 0) ? 1 : 0) * PW + ((kx == 0) ? 1 : 0);
+                const uint32_t a0 = sa + (mt * 128 + shift) * 16;
+                const uint32_t b0 = sw + (ky * 3 + kx) * a.nplanes * wplane;
+                for (int kc = 0; kc < kcs; ++kc) {
+                  umma_f16(tmem + (mt * 4 + cls) * a.NT, smem_desc(a0 + 2 * kc * a.PB, a.PB, 128),
+                           smem_desc(b0 + 2 * kc * wplane, wplane, 128), idesc, acc);
+                  acc = 1;
+                }
+              }
+            }
+          }
+      }
+      umma_commit(smem_u32(&mbar));
     }
-    umma_commit(smem_u32(&mbar));
-  }
-  __syncwarp();
-  mbar_wait(smem_u32(&mbar), 0);
-  tc_fence_after();
+    __syncwarp();
+    // ---- stage the next tile: into the other buffer while the MMAs run (nbuf == 2), or into the
+    //      same buffer once they are done (nbuf == 1); either way it overlaps the epilogue
+    const int next = tile + gridDim.x;
+    if (a.nbuf == 2 && next < a.tiles_total) load_tile(next, sa0 + ((it + 1) & 1) * a.a_bytes);
+    mbar_wait(smem_u32(&mbar), it & 1);
+    tc_fence_after();
+    if (a.nbuf == 1 && next < a.tiles_total) load_tile(next, sa0);
 
-  // ---- epilogue: thread t owns accumulator row t of every M-tile
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-  const int ncls = (mode == S2_DGRAD) ? 4 : 1;
-  for (int mt = 0; mt < a.n_mt; ++mt) {
-    const int q = mt * 128 + tid;
-    const int r = q / PW, c = q - r * PW;
-    const bool valid = (r < rows) && (c < a.Wt);
-    for (int cls = 0; cls < ncls; ++cls) {
-      int yo = y0 + r, xo = c;
-      if (mode == S2_DGRAD) { yo = 2 * yo + (cls >> 1); xo = 2 * xo + (cls & 1); }
-      for (int nc = 0; nc < a.NT; nc += 16) {
-        float v[16];
-        tmem_ld16(tmem + lane_base + (mt * ncls + cls) * a.NT + nc, v);
-        if (valid) epilogue16(op, v, n, yo, xo, co0 + nc);
+    // ---- epilogue: thread t owns accumulator row t of every M-tile
+    const int n = tile / a.tiles_per_img;
+    const int y0 = (tile - n * a.tiles_per_img) * a.TH;
+    const int rows = min(a.TH, a.Ht - y0);
+    for (int mt = 0; mt < a.n_mt; ++mt) {
+      const int q = mt * 128 + tid;
+      const int r = (int)__umulhi((unsigned)q, a.magic_pw), c = q - r * PW;
+      const bool valid = (r < rows) && (c < a.Wt);
+      for (int cls = 0; cls < ncls; ++cls) {
+        int yo = y0 + r, xo = c;
+        if (mode == S2_DGRAD) { yo = 2 * yo + (cls >> 1); xo = 2 * xo + (cls & 1); }
+        for (int nc = 0; nc < a.NT; nc += 16) {
+          float v[16];
+          tmem_ld16(tmem + lane_base + (mt * ncls + cls) * a.NT + nc, v);
+          if (valid) epilogue16(op, v, n, yo, xo, co0 + nc);
+        }
       }
     }
+    cp_async_wait_all();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
   }
-  tc_fence_before();
-  __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, (uint32_t)a.tmem_cols);
 }
 
@@ -316,7 +347,11 @@ bool plan(const ConvOp& op, UmmaArgs& a) {
   int cols = best_mt * ncls * NT, pc = 32;
   while (pc < cols) pc <<= 1;
   a.tmem_cols = pc;
-  a.w_off = (unsigned)(nsub * nplanes * a.PB);
+  a.a_bytes = (unsigned)(nsub * nplanes * a.PB);
+  // a second input buffer only when it is cheap: occupancy (co-resident CTAs) hides more latency
+  a.nbuf = (2 * (size_t)a.a_bytes + wbytes <= 56 * 1024) ? 2 : 1;
+  a.w_off = a.nbuf * a.a_bytes;
+  a.tiles_total = a.tiles_per_img * op.B;
   a.magic_np = (unsigned)((0x100000000ULL + nplanes - 1) / nplanes);
   a.magic_pw = (unsigned)((0x100000000ULL + PW - 1) / PW);
   return true;
@@ -342,7 +377,12 @@ int conv_umma(const ConvOp& op, cudaStream_t st) {
   const double taps = op.transposed ? 2.25 : 9.0;
   Prof prof(PC_CONV_UMMA, 2.0 * total * op.Co * op.Ci * taps,
             (double)total * op.Co * (op.y.bf ? 2 : 4) + (double)op.B * op.Hin * op.Win * op.Ci * 2.0, st);
-  conv_umma_kernel<<<dim3(op.B * a.tiles_per_img, op.Co / a.NT), UMMA_THREADS, smem, st>>>(a);
+  const int n_chunks = op.Co / a.NT;
+  int per_sm = (int)((size_t)(MAX_SMEM + 2048) / (smem + 1024));  // co-resident CTAs by shared memory
+  per_sm = std::max(1, std::min(per_sm, std::min(4, 512 / a.tmem_cols)));
+  int gx = (148 * per_sm + n_chunks - 1) / n_chunks;
+  gx = std::max(1, std::min(gx, a.tiles_total));
+  conv_umma_kernel<<<dim3(gx, n_chunks), UMMA_THREADS, smem, st>>>(a);
   DG_LAUNCH_CHECK();
   return 0;
 }
