@@ -811,12 +811,55 @@ static int critic_gp_second_order(dg_critic* c, int n0, int B, cudaStream_t st) 
 }
 
 static int critic_gp_first_order(dg_critic* c, const dg_hyper* hp, int n0, int B, float* scalars, int write_loss,
-                                 float* norms_out, cudaStream_t st) {
+                                 float* norms_out, cudaStream_t st, float* u_out = nullptr) {
   const size_t per = (size_t)c->Hf * c->Hf * c->nc;
   DG_TRY(gp_norms(c->g, B, per, c->sumsq, st));
   DG_TRY(gp_finish(c->sumsq, B, hp->gp_lambda, norms_out ? norms_out : c->norms, c->coef, scalars, write_loss, st));
-  DG_TRY(gp_scale(c->g, c->coef, c->u, B, per, st));
+  DG_TRY(gp_scale(c->g, c->coef, u_out ? u_out : c->u, B, per, st));
   (void)n0;
+  return 0;
+}
+
+// Fused-step variant of the two functions above.  The interpolates occupy samples [2B, 3B) of every
+// saved activation; once the input-gradient chain is done their activations are only needed as
+// LeakyReLU masks, so the JVP chain v_l = m_l * conv_l(v_{l-1}) is written IN PLACE over them (each
+// epilogue thread reads the mask element and overwrites the same element).  Afterwards
+// a[l] = [real acts ; fake acts ; v_l] and dz[l+1] = [dz real ; dz fake ; dz interpolates], so ONE
+// weight-gradient launch per layer over all 3B samples yields  d(E[C(fake)] - E[C(real)])/dW + dGP/dW.
+static int critic_second_order_and_wgrads(dg_critic* c, int B, cudaStream_t st) {
+  const int n0 = 2 * B;
+  TV v = tv_batch(tv(c->a0, 0, c->nc), (size_t)c->Hf * c->Hf, n0);  // u was written here by gp_scale
+  for (int i = 0; i < 8; ++i) {
+    const Layer& l = c->L[i];
+    ConvOp op;
+    op.x = v; op.Hin = c->Hin[i]; op.Win = c->Hin[i]; op.Ci = l.Ci;
+    op.y = tv_batch(c->act(c->a[i + 1], l.Co), c->pix(i), n0); op.Hout = c->Hout[i]; op.Wout = c->Hout[i]; op.Co = l.Co;
+    op.B = B; op.w = c->pk + l.pk_off; op.bias = nullptr; op.stride = l.stride;
+    if (c->bf) op.w_umma = c->pk_u + l.pk_off;
+    op.act = ACT_MASK; op.slope = C_SLOPE; op.mask = op.y;
+    DG_TRY(run_conv(op, st));
+    v = op.y;
+  }
+  // classifier: dW_fc1 over all 3B rows at once; v_fc and dW_fc2 as in critic_gp_second_order
+  DG_TRY(fc_wgrad(c->dz9, c->a[8], c->bf, c->gpk + c->pk_fc1w, 3 * B, c->fc_in, FC_HIDDEN, st));
+  DG_TRY(colsum(tv(c->dz9, 0, FC_HIDDEN), (size_t)n0, FC_HIDDEN, c->gpk + c->pk_fc1b, st));
+  DG_TRY(fc_wgrad(c->seed, c->a9, 0, c->gpk + c->pk_fc2w, n0, FC_HIDDEN, 1, st));
+  DG_TRY(colsum(tv(c->seed, 0, 1), (size_t)n0, 1, c->gpk + c->pk_fc2b, st));
+  DG_TRY(fc_fwd(v.p, c->bf, c->pk + c->pk_fc1w, nullptr, c->vfc, B, c->fc_in, FC_HIDDEN, ACT_MASK, C_SLOPE,
+                c->a9 + (size_t)n0 * FC_HIDDEN, st));
+  DG_TRY(colsum(tv(c->vfc, 0, FC_HIDDEN), (size_t)B, FC_HIDDEN, c->gpk + c->pk_fc2w, st));
+  for (int i = 0; i < 8; ++i) {
+    const Layer& l = c->L[i];
+    WgradOp w;
+    w.x = (i == 0) ? tv(c->a0, 0, c->nc) : c->act(c->a[i], l.Ci);
+    w.Hin = c->Hin[i]; w.Win = c->Hin[i]; w.Ci = l.Ci;
+    w.dy = c->act(c->dz[i + 1], l.Co); w.Hout = c->Hout[i]; w.Wout = c->Hout[i]; w.Co = l.Co;
+    w.B = 3 * B; w.stride = l.stride;
+    w.dw = c->gpk + l.pk_off; w.dbias = nullptr;
+    DG_TRY(run_wgrad(w, st));
+  }
+  // features.0.bias: real + fake samples only (the gradient penalty contributes exactly zero to biases)
+  DG_TRY(colsum(c->act(c->dz[1], c->L[0].Co), (size_t)n0 * c->pix(0), c->L[0].Co, c->gpk + c->pk_b0, st));
   return 0;
 }
 
@@ -900,10 +943,10 @@ extern "C" int dg_critic_step(dg_generator* g, dg_critic* c, const dg_hyper* hp,
   critic_seed_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(c->seed, B);
   DG_LAUNCH_CHECK();
   DG_TRY(critic_backward_chain(c, 3 * B, 2 * B, B, c->g, st));
-  DG_TRY(critic_gp_first_order(c, hp, 2 * B, B, scalars, 1, nullptr, st));
+  DG_TRY(critic_gp_first_order(c, hp, 2 * B, B, scalars, 1, nullptr, st,
+                               c->a0 + (size_t)2 * B * c->Hf * c->Hf * c->nc));  // u overwrites the interpolates
   DG_CUDA(cudaMemsetAsync(c->gpk, 0, sizeof(float) * c->pk_elems, st));
-  DG_TRY(critic_wgrads_acts(c, 0, 2 * B, st));
-  DG_TRY(critic_gp_second_order(c, 2 * B, B, st));
+  DG_TRY(critic_second_order_and_wgrads(c, B, st));
   DG_TRY(unpack_wgrads(c->gpk, c_grads_flat, c->tab_fwd, c->n_fwd, c->max_fwd, st));
   c->saved_batch = 0;
   return 0;
