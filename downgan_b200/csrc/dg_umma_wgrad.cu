@@ -60,6 +60,19 @@ __device__ __forceinline__ void wgrad_body(const WgArgs& a, uint8_t* smem, uint6
   const uint32_t idesc = instr_desc(128, a.NT, 1, 1);
   const int ksteps = a.npos16 >> 4;
 
+  // The MMAs contract over every staged position, so everything they can read must be finite:
+  // zero both x regions and both dy regions once; afterwards a tile only rewrites its own rows
+  // (stale x rows of earlier tiles only ever meet dy == 0).
+  {
+    const uint32_t zbytes = a.d_off + 2 * a.d_bytes;
+    for (uint32_t i = tid * 16; i < zbytes; i += WG_THREADS_U * 16)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sbase + i), "r"(0u) : "memory");
+    __syncthreads();
+  }
+  const int xrows = a.TH + ((s == 1) ? 2 : 1);
+  const int xrow_elems = a.PWt * a.nplx, drow_elems = a.PWt * a.npld;
+  const int ystep = (s == 1) ? 1 : 2;
+
   int it = 0;
   for (int t = t_begin; t < t_end; ++t, ++it) {
     const int buf = it & 1;
@@ -68,38 +81,34 @@ __device__ __forceinline__ void wgrad_body(const WgArgs& a, uint8_t* smem, uint6
     const int y0 = (t - n * a.tiles_per_img) * a.TH;
     const uint32_t sx = sbase + buf * a.x_bytes;
     const uint32_t sd = sbase + a.d_off + buf * a.d_bytes;
-    // ---- x tile(s): every position of every real plane is written (zero fill outside the image)
-    const int xpos = a.PBx >> 4;
-    for (int sub = 0; sub < a.nsub; ++sub) {
-      const int py = sub >> 1, px = sub & 1;
-      const int total = xpos * a.nplx;
-      for (int i = tid; i < total; i += WG_THREADS_U) {
-        const int pos = (int)__umulhi((unsigned)i, a.magic_nx), pl = i - pos * a.nplx;
-        const int r = (int)__umulhi((unsigned)pos, a.magic_pw), c = pos - r * a.PWt;
+    // ---- x tile(s): a thread owns (column, plane) pairs and walks the rows (zero fill = padding)
+    for (int e = tid; e < xrow_elems; e += WG_THREADS_U) {
+      const int c = (int)__umulhi((unsigned)e, a.magic_nx), pl = e - c * a.nplx;
+      for (int sub = 0; sub < a.nsub; ++sub) {
         int gy, gx;
-        bool ok;
-        if (s == 1) {
-          gy = y0 - 1 + r; gx = c - 1;
-          ok = r < a.TH + 2;
-        } else {
-          gy = 2 * (y0 - 1 + r) + py; gx = 2 * (c - 1) + px;
-          ok = r < a.TH + 1;
+        if (s == 1) { gy = y0 - 1; gx = c - 1; }
+        else { gy = 2 * (y0 - 1) + (sub >> 1); gx = 2 * (c - 1) + (sub & 1); }
+        const bool okx = gx >= 0 && gx < op.Win;
+        const bf16* src = xb + (((size_t)n * op.Hin + gy) * op.Win + (okx ? gx : 0)) * op.x.pitch + op.x.coff + pl * 8;
+        const size_t sstep = (size_t)ystep * op.Win * op.x.pitch;
+        uint32_t dst = sx + (sub * a.nplx + pl) * a.PBx + c * 16;
+        for (int r = 0; r < xrows; ++r, gy += ystep, src += sstep, dst += a.PWt * 16) {
+          const bool ok = okx && gy >= 0 && gy < op.Hin;
+          cp_async16(dst, ok ? src : xb, ok ? 16 : 0);
         }
-        ok = ok && gy >= 0 && gy < op.Hin && gx >= 0 && gx < op.Win;
-        const bf16* src = ok ? xb + (((size_t)n * op.Hin + gy) * op.Win + gx) * op.x.pitch + op.x.coff + pl * 8 : xb;
-        cp_async16(sx + (sub * a.nplx + pl) * a.PBx + pos * 16, src, ok ? 16 : 0);
       }
     }
-    // ---- dy tile: pad columns and the rounding tail are zero
-    {
-      const int total = a.npos16 * a.npld;
-      for (int i = tid; i < total; i += WG_THREADS_U) {
-        const int pos = (int)__umulhi((unsigned)i, a.magic_nd), pl = i - pos * a.npld;
-        const int r = (int)__umulhi((unsigned)pos, a.magic_pw), c = pos - r * a.PWt;
-        const int gy = y0 + r;
-        const bool ok = r < a.TH && gy < op.Hout && c < op.Wout;
-        const bf16* src = ok ? db + (((size_t)n * op.Hout + gy) * op.Wout + c) * op.dy.pitch + op.dy.coff + co0 + pl * 8 : db;
-        cp_async16(sd + pl * a.PBd + pos * 16, src, ok ? 16 : 0);
+    // ---- dy tile rows (pad column and rows outside the image are zero-filled)
+    for (int e = tid; e < drow_elems; e += WG_THREADS_U) {
+      const int c = (int)__umulhi((unsigned)e, a.magic_nd), pl = e - c * a.npld;
+      const bool okx = c < op.Wout;
+      const bf16* src = db + (((size_t)n * op.Hout + y0) * op.Wout + (okx ? c : 0)) * op.dy.pitch + op.dy.coff + co0 + pl * 8;
+      const size_t sstep = (size_t)op.Wout * op.dy.pitch;
+      uint32_t dst = sd + pl * a.PBd + c * 16;
+      int gy = y0;
+      for (int r = 0; r < a.TH; ++r, ++gy, src += sstep, dst += a.PWt * 16) {
+        const bool ok = okx && gy < op.Hout;
+        cp_async16(dst, ok ? src : db, ok ? 16 : 0);
       }
     }
     cp_async_wait_all();
@@ -112,22 +121,25 @@ __device__ __forceinline__ void wgrad_body(const WgArgs& a, uint8_t* smem, uint6
     }
     if (tid == 0) {
       tc_fence_after();
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint64_t bd = smem_desc(sd + ks * 256, 128, a.PBd);
-        const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+      uint64_t ad0[9];
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const int ky = tap / 3, kx = tap - 3 * ky;
-          int sub = 0, shift;
-          if (s == 1) {
-            shift = ky * a.PWt + kx;
-          } else {
-            sub = ((ky == 1) ? 0 : 2) + ((kx == 1) ? 0 : 1);
-            shift = ((ky == 0) ? 0 : 1) * a.PWt + ((kx == 0) ? 0 : 1);
-          }
-          const uint64_t ad = smem_desc(sx + sub * a.nplx * a.PBx + (shift + ks * 16) * 16, 128, a.PBx);
-          umma_f16(tmem + tap * a.NT, ad, bd, idesc, acc);
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap - 3 * ky;
+        int sub = 0, shift;
+        if (s == 1) {
+          shift = ky * a.PWt + kx;
+        } else {
+          sub = ((ky == 1) ? 0 : 2) + ((kx == 1) ? 0 : 1);
+          shift = ((ky == 0) ? 0 : 1) * a.PWt + ((kx == 0) ? 0 : 1);
         }
+        ad0[tap] = smem_desc(sx + sub * a.nplx * a.PBx + shift * 16, 128, a.PBx);
+      }
+      const uint64_t bd0 = smem_desc(sd, 128, a.PBd);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+        const uint64_t kadv = (uint64_t)(ks * 16);  // 16 positions x 16 B, in 16-byte descriptor units
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) umma_f16(tmem + tap * a.NT, ad0[tap] + kadv, bd0 + kadv, idesc, acc);
       }
       umma_commit(smem_u32(&mbar[buf]));
     }
