@@ -182,12 +182,52 @@ class WassersteinGAN:
 
     # ---- epoch loop (wasserstein.py:120-189, logging/plotting out of scope) ----
     def _train_epoch(self, dataloader, testdataloader=None, epoch: int = 0):
-        for data in dataloader:
-            coarse, fine = data[0], data[1]
-            self._critic_train_iteration(coarse, fine)
-            if self.num_steps % hp.critic_iterations == 0:
-                self._generator_train_iteration(coarse, fine)
-            self.num_steps += 1
+        """One pass over `dataloader` with the reference schedule (wasserstein.py:131-147): a critic
+        iteration per batch, a generator iteration on the same batch when num_steps % n_critic == 0.
+        Batches may live on the host: batch i+1 is copied to the device on a side stream while batch
+        i trains, and the loss scalars of every step are copied back asynchronously into pinned
+        memory (no per-step device synchronisation).  Returns a (steps, 8) CPU tensor of the critic
+        scalars (CRITIC_SCALARS order) — the reference logs the same quantities through mlflow."""
+        dev = self.device
+        with torch.cuda.device(dev):
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            main = torch.cuda.current_stream()
+
+            def stage(data):
+                if data is None:
+                    return None
+                with torch.cuda.stream(self._copy_stream):
+                    ts = [t.to(device=dev, dtype=torch.float32, non_blocking=True) for t in data[:3]]
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_stream)
+                return ts, ev
+
+            it = iter(dataloader)
+            nxt = stage(next(it, None))
+            logs = []
+            while nxt is not None:
+                (ts, ev), nxt = nxt, stage(next(it, None))
+                main.wait_event(ev)
+                for t in ts:
+                    t.record_stream(main)
+                coarse, fine = ts[0], ts[1]
+                alpha = ts[2] if len(ts) > 2 else None
+                self._critic_train_iteration(coarse, fine, alpha)
+                if self.num_steps % hp.critic_iterations == 0:
+                    self._generator_train_iteration(coarse, fine)
+                self.num_steps += 1
+                k = len(logs)
+                if getattr(self, "_log_host", None) is None or k >= self._log_host.shape[0]:
+                    main.synchronize()  # growing the pinned ring: rare (every 1024 steps)
+                    grown = torch.empty(max(1024, 2 * (k + 1)), 8, dtype=torch.float32, pin_memory=True)
+                    if getattr(self, "_log_host", None) is not None:
+                        grown[:k].copy_(self._log_host[:k])
+                    self._log_host = grown
+                self._log_host[k].copy_(self.last_critic, non_blocking=True)
+                logs.append(k)
+            main.synchronize()
+        return self._log_host[:len(logs)].clone() if logs else torch.zeros(0, 8)
 
     def train(self, dataloader, testdataloader=None):
         self.num_steps = 0

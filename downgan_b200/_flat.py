@@ -27,10 +27,19 @@ class FlatParamsMixin:
 
     def flat_params(self) -> torch.Tensor:
         """Ensure every parameter is a view into one flat CUDA fp32 buffer and return it."""
-        params = self._param_list()
+        params = self._param_cache if getattr(self, "_param_cache", None) is not None else self._param_list()
+        self._param_cache = params
         dev = params[0].device
         if dev.type != "cuda":
             raise RuntimeError("downgan_b200 modules run on CUDA only (no CPU fallback): call .to('cuda') first")
+        flat = self._flat
+        if flat is not None and self._offsets is not None and flat.device == dev:
+            # fast path: `.to()` / `load_state_dict(assign=True)` re-point every parameter, so checking the
+            # first and the last one is enough to know the views are still in place
+            base = flat.data_ptr()
+            p0, p1 = params[0], params[-1]
+            if p0.data_ptr() == base and p1.data_ptr() == base + 4 * self._offsets[-1] and p1.dtype == torch.float32:
+                return flat
         offs, n = [], 0
         for p in params:
             offs.append(n)
@@ -73,7 +82,8 @@ class FlatParamsMixin:
         self._dirty = True
 
     def _params_version(self) -> int:
-        return sum(p._version for p in self._param_list())
+        ps = self._param_cache if getattr(self, "_param_cache", None) is not None else self._param_list()
+        return sum(p._version for p in ps)
 
     def _needs_pack(self) -> bool:
         v = self._params_version()

@@ -81,6 +81,8 @@ struct dg_generator {
   int n_fwd = 0, n_dgrad = 0, max_fwd = 0, max_dgrad = 0;
   bf16 *pk_u = nullptr, *pkd_u = nullptr;  // tcgen05 B-operand images (bf16 mode)
   bf16* pk_trunk = nullptr;                // slice-major images of the dense convs for the fused trunk kernel
+  bf16* pkd_trunk = nullptr;               // same for the dense data-gradient matrices (fused trunk backward)
+  void** d_ptrs_dev = nullptr;             // device copy of Dall[]
   UmmaPackDesc *utab_fwd = nullptr, *utab_dgrad = nullptr;
   int n_ufwd = 0, n_udgrad = 0, max_ufwd = 1, max_udgrad = 1;
   std::vector<long long> db_dgrad_off;  // [(r*3+d)*5 + k] packed offset of Wt_k
@@ -246,6 +248,7 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
   GA(g->pk_u, sizeof(bf16) * (pk + 64));
   GA(g->pkd_u, sizeof(bf16) * (std::max<long long>(pkd, 1) + 64));
   GA(g->pk_trunk, sizeof(bf16) * ((size_t)std::max(1, g->R * 3) * 9 * F * F * 15 + 64));
+  GA(g->pkd_trunk, sizeof(bf16) * ((size_t)std::max(1, g->R * 3) * 9 * F * F * 15 + 64));
   if ((s = upload_table(g->pool, tf, &g->tab_fwd)) != 0) { dg_generator_destroy(g); return s; }
   if ((s = upload_table(g->pool, td, &g->tab_dgrad)) != 0) { dg_generator_destroy(g); return s; }
   if ((s = upload_utable(g->pool, uf, &g->utab_fwd)) != 0) { dg_generator_destroy(g); return s; }
@@ -276,6 +279,10 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
     g->Dall[0] = g->D;
     for (int i = 1; i < g->R * 3; ++i) GA(g->Dall[i], B * pc * 5 * F * g->esz);
     GA(g->wg_table_dev, wgrad_umma_args_size() * (size_t)g->R * 15);
+    GA(g->d_ptrs_dev, sizeof(void*) * g->Dall.size());
+    if (cudaMemcpy(g->d_ptrs_dev, g->Dall.data(), sizeof(void*) * g->Dall.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("cudaMemcpy(d_ptrs) failed"); dg_generator_destroy(g); return DG_ERR_CUDA;
+    }
   }
   GA(g->gR, B * pc * F * g->esz);
   GA(g->gx0, B * pc * F * g->esz);
@@ -303,7 +310,10 @@ extern "C" int dg_generator_pack(dg_generator* g, const float* params, void* str
   DG_TRY(pack_umma(g->pk, g->pk_u, g->utab_fwd, g->n_ufwd, g->max_ufwd, st));
   DG_TRY(pack_umma(g->pkd, g->pkd_u, g->utab_dgrad, g->n_udgrad, g->max_udgrad, st));
   if (trunk_fused_supported(g->F, g->Hc, g->R, g->bf))
-    DG_TRY(pack_trunk_slices(g->pk + g->layers[g->idx_db(0, 0, 1)].pk_off, g->pk_trunk, g->R * 3, st));
+  {
+    DG_TRY(pack_trunk_slices(g->pk + g->layers[g->idx_db(0, 0, 1)].pk_off, g->pk_trunk, g->R * 3, 0, st));
+    DG_TRY(pack_trunk_slices(g->pkd + g->db_dgrad_off[0], g->pkd_trunk, g->R * 3, 1, st));
+  }
   g->packed = true;
   return 0;
 }
@@ -459,7 +469,23 @@ static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_co
   std::vector<WgradOp> wops;
   if (batched_wgrad) wops.reserve((size_t)g->R * 15);
   void* const D0 = g->D;
-  for (int r = g->R - 1; r >= 0; --r) {
+  const bool fused_bwd = batched_wgrad && trunk_fused_supported(F, Hc, g->R, g->bf);
+  if (fused_bwd) {
+    // persistent tcgen05 kernel: the whole data-gradient chain of the trunk, dz slices saved per block
+    DG_TRY(trunk_bwd_fused(g->gR, g->gR, (void* const*)g->db_ptrs_dev, (void* const*)g->d_ptrs_dev, g->pkd_trunk, g->R, B, st));
+    for (int r = g->R - 1; r >= 0; --r)
+      for (int d = 2; d >= 0; --d)
+        for (int k = 1; k <= 5; ++k) {
+          const Layer& l = g->layers[g->idx_db(r, d, k)];
+          WgradOp w;
+          memset(&w, 0, sizeof(w));
+          w.x = g->act(g->db[r * 3 + d], 5 * F, 0); w.Hin = Hc; w.Win = Hc; w.Ci = l.Ci;
+          w.dy = g->act(g->Dall[(size_t)r * 3 + d], 5 * F, (5 - k) * F); w.Hout = Hc; w.Wout = Hc; w.Co = l.Co;
+          w.B = B; w.stride = 1; w.dw = g->gpk + l.pk_off; w.dbias = g->gpk + l.pkb_off;
+          wops.push_back(w);
+        }
+  }
+  for (int r = fused_bwd ? -1 : g->R - 1; r >= 0; --r) {
     // g->gR holds dL/d(RRDB_r output)
     void* gin = g->gR;
     float s_in = RES_SCALE;

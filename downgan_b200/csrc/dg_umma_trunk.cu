@@ -29,6 +29,7 @@ constexpr int T_X_BYTES = 10 * TPB;
 constexpr int T_W_BYTES = 9 * 80 * TF * 2;
 constexpr int T_SMEM = T_X_BYTES + 2 * T_W_BYTES;
 constexpr float G_SLOPE = 0.01f, RES = 0.2f;
+constexpr int T_DB_ELEMS_ = 9 * TF * TF * 15;  // weight elements of one dense block
 
 struct TrunkArgs {
   const bf16* x_in; int in_pitch, in_coff;  // (B,16,16,pitch): conv1 output
@@ -204,10 +205,190 @@ __global__ void __launch_bounds__(128) trunk_fwd_kernel(const TrunkArgs a) {
   if (warp == 0) tmem_dealloc(tmem, T_TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward (data-gradient chain) of the whole trunk, same structure as the forward kernel.
+// With D = [dz5, dz4, dz3, dz2, dz1] the gradient w.r.t. slice k of a dense block's concat buffer
+// is one conv over D[0:(5-k)], so the backward of a dense block is again a dense
+// block: slice i of D feeds every later output in one N = 16*(5-i) MMA round.  The epilogue
+// multiplies by the LeakyReLU mask taken from the saved forward buffer, the last round adds the
+// block / RRDB skips.  Every D slice is also stored to global memory for the batched
+// weight-gradient launch that follows.
+// ---------------------------------------------------------------------------------------------
+struct TrunkBwdArgs {
+  const bf16* g_in;            // (B,16,16,16): dL/d(trunk output)
+  bf16* g_out;                 // (B,16,16,16): dL/d(trunk input)
+  const bf16* const* fwd_bufs; // [3R] saved concat buffers (pitch 80): masks
+  bf16* const* d_bufs;         // [3R] dz buffers (pitch 80), written here
+  const bf16* w;               // slice-major images of the dense data-gradient matrices, 5 per block
+  int R, B;
+};
+
+__global__ void __launch_bounds__(128) trunk_bwd_kernel(const TrunkBwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.x;
+  const uint32_t sX = smem_u32(smem);
+  const uint32_t sW = sX + T_X_BYTES;
+  const int n_db = a.R * 3;
+
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), T_TMEM_COLS);
+  if (tid == 32) mbar_init(smem_u32(&mbar), TNMT);
+  for (int i = tid; i < T_X_BYTES / 16; i += 128) st_shared16(sX + i * 16, make_uint4(0, 0, 0, 0));
+  // weights of the LAST block's slice 0 -> buffer 0
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.w + (size_t)(n_db - 1) * T_DB_ELEMS_);
+    for (int i = tid; i < 18 * 5 * TF; i += 128) cp_async16(sW + i * 16, src + i, 16);
+  }
+  int pos[TNMT], pix[TNMT];
+  bool valid[TNMT];
+#pragma unroll
+  for (int mt = 0; mt < TNMT; ++mt) {
+    const int q = mt * 128 + tid;
+    const int y = q / TPW, x = q - y * TPW;
+    valid[mt] = (x < TW) && (y < TW);
+    pos[mt] = q + TPW + 1;
+    pix[mt] = valid[mt] ? y * TW + x : 0;
+  }
+  // incoming gradient at this thread's positions (bf16 x 16 per position)
+  uint4 gin[TNMT][2], gr[TNMT][2];
+#pragma unroll
+  for (int mt = 0; mt < TNMT; ++mt) {
+    const uint4* g = reinterpret_cast<const uint4*>(a.g_in + ((size_t)n * 256 + pix[mt]) * TF);
+    gin[mt][0] = valid[mt] ? g[0] : make_uint4(0, 0, 0, 0);
+    gin[mt][1] = valid[mt] ? g[1] : make_uint4(0, 0, 0, 0);
+    gr[mt][0] = gr[mt][1] = make_uint4(0, 0, 0, 0);
+  }
+  cp_async_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+
+  int L = 0;
+  for (int db = n_db - 1; db >= 0; --db) {
+    const int d = db % 3;
+    const float s_in = (d == 2) ? RES : 1.f;
+    const bf16* fbuf = a.fwd_bufs[db];
+    bf16* dbuf = a.d_bufs[db];
+    if (d == 2) {
+#pragma unroll
+      for (int mt = 0; mt < TNMT; ++mt) { gr[mt][0] = gin[mt][0]; gr[mt][1] = gin[mt][1]; }
+    }
+    // slice 0 of D: dz5 = 0.2 * s_in * g
+#pragma unroll
+    for (int mt = 0; mt < TNMT; ++mt) {
+      if (!valid[mt]) continue;
+      float g[16];
+      unpack8(gin[mt][0], g);
+      unpack8(gin[mt][1], g + 8);
+      const float sc = RES * s_in;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) g[j] *= sc;
+      const uint4 lo = make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7]));
+      const uint4 hi = make_uint4(pack2(g[8], g[9]), pack2(g[10], g[11]), pack2(g[12], g[13]), pack2(g[14], g[15]));
+      st_shared16(sX + pos[mt] * 16, lo);
+      st_shared16(sX + TPB + pos[mt] * 16, hi);
+      uint4* gd = reinterpret_cast<uint4*>(dbuf + ((size_t)n * 256 + pix[mt]) * 80);
+      gd[0] = lo; gd[1] = hi;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    size_t w_elem = (size_t)db * T_DB_ELEMS_;
+    for (int j = 0; j < 5; ++j, ++L) {
+      const int t = j + 1;  // output of this round: dz_{5-t} (t < 5) or the block-input gradient (t == 5)
+      const int Nj = TF * (5 - j);
+      const uint32_t wb = sW + (L & 1) * T_W_BYTES;
+      if (warp < TNMT && lane == 0) {
+        const uint32_t idj = instr_desc(128, Nj);
+        const uint32_t wplane = Nj * 16;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = tap / 3, dx = tap - 3 * dy;
+          const uint32_t a0 = sX + 2 * j * TPB + (warp * 128 + dy * TPW + dx) * 16;
+          const uint32_t b0 = wb + tap * 2 * wplane;
+          umma_f16(tmem + warp * T_COLS_MT + j * TF, smem_desc(a0, TPB, 128), smem_desc(b0, wplane, 128), idj,
+                   (j > 0 || tap > 0) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&mbar));
+      }
+      __syncwarp();
+      // prefetch the next slice's weights (next slice of this block, or slice 0 of the previous block)
+      const size_t w_next = (j < 4) ? w_elem + (size_t)9 * TF * Nj : (size_t)(db - 1) * T_DB_ELEMS_;
+      if (j < 4 || db > 0) {
+        const int Nn = (j == 4) ? 5 * TF : Nj - TF;
+        const uint4* src = reinterpret_cast<const uint4*>(a.w + w_next);
+        const uint32_t dst = sW + ((L + 1) & 1) * T_W_BYTES;
+        for (int i = tid; i < 18 * Nn; i += 128) cp_async16(dst + i * 16, src + i, 16);
+      }
+      // mask source for this round (issued before the wait so the latency hides behind the MMAs)
+      uint4 mk[TNMT][2];
+      if (t < 5) {
+#pragma unroll
+        for (int mt = 0; mt < TNMT; ++mt) {
+          const uint4* m = reinterpret_cast<const uint4*>(fbuf + ((size_t)n * 256 + pix[mt]) * 80 + TF * (5 - t));
+          mk[mt][0] = m[0]; mk[mt][1] = m[1];
+        }
+      }
+      mbar_wait(smem_u32(&mbar), L & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int mt = 0; mt < TNMT; ++mt) {
+        float v[16];
+        tmem_ld16(tmem + lane_base + mt * T_COLS_MT + j * TF, v);
+        if (!valid[mt]) continue;
+        if (t < 5) {
+          float m[16];
+          unpack8(mk[mt][0], m);
+          unpack8(mk[mt][1], m + 8);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] *= (m[q] > 0.f ? 1.f : G_SLOPE);
+          const uint4 lo = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+          const uint4 hi = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+          st_shared16(sX + (2 * t) * TPB + pos[mt] * 16, lo);
+          st_shared16(sX + (2 * t + 1) * TPB + pos[mt] * 16, hi);
+          uint4* gd = reinterpret_cast<uint4*>(dbuf + ((size_t)n * 256 + pix[mt]) * 80 + TF * t);
+          gd[0] = lo; gd[1] = hi;
+        } else {
+          float g[16];
+          unpack8(gin[mt][0], g);
+          unpack8(gin[mt][1], g + 8);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = fmaf(s_in, g[q], v[q]);
+          if (d == 0) {
+            unpack8(gr[mt][0], g);
+            unpack8(gr[mt][1], g + 8);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] += g[q];
+          }
+          gin[mt][0] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+          gin[mt][1] = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+        }
+      }
+      w_elem = w_next;
+      cp_async_wait_all();
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < TNMT; ++mt) {
+    if (!valid[mt]) continue;
+    uint4* g = reinterpret_cast<uint4*>(a.g_out + ((size_t)n * 256 + pix[mt]) * TF);
+    g[0] = gin[mt][0]; g[1] = gin[mt][1];
+  }
+  if (warp == 0) tmem_dealloc(tmem, T_TMEM_COLS);
+}
+
 // fp32 packed per-layer weights [tap][16k][16] of one dense block  ->  slice-major bf16 images:
 // slice j: [tap][2 planes][N_j = 16*(5-j) rows = layers j+1..5 side by side][8 channels of slice j]
 constexpr int T_DB_ELEMS = 9 * TF * TF * 15;
-__global__ void pack_trunk_kernel(const float* __restrict__ pk_db0, bf16* __restrict__ dst, int n_db) {
+__global__ void pack_trunk_kernel(const float* __restrict__ pk_db0, bf16* __restrict__ dst, int n_db, int bwd) {
   const int db = blockIdx.y;
   if (db >= n_db) return;
   const float* src = pk_db0 + (size_t)db * T_DB_ELEMS;
@@ -222,16 +403,36 @@ __global__ void pack_trunk_kernel(const float* __restrict__ pk_db0, bf16* __rest
     const int pl = r & 1, tap = r >> 1;
     const int k = j + 1 + row / TF, co = row % TF;        // consuming layer (1-based) and its output channel
     const int ci = TF * j + pl * 8 + c8;                   // input channel inside the concat buffer
-    const size_t layer_off = (size_t)9 * TF * TF * (k - 1) * k / 2;  // layers 1..k-1 of this block
+    // forward: layers 1..k-1 of this block precede layer k.  backward: "layer" t = k consumes the 16t
+    // rows [dz5..dz_{6-t}] of the dense data-gradient matrix Wt_{5-t}, stored after Wt_0..Wt_{4-t}.
+    const size_t layer_off = bwd ? (size_t)9 * TF * TF * (15 - k * (k + 1) / 2) : (size_t)9 * TF * TF * (k - 1) * k / 2;
     out[e] = __float2bfloat16_rn(src[layer_off + ((size_t)tap * (TF * k) + ci) * TF + co]);
   }
 }
 
 }  // namespace
 
-int pack_trunk_slices(const float* pk_first_dense, void* dst_bf16, int n_db, cudaStream_t st) {
+int pack_trunk_slices(const float* pk_first_dense, void* dst_bf16, int n_db, int bwd, cudaStream_t st) {
   if (n_db <= 0) return 0;
-  pack_trunk_kernel<<<dim3(32, n_db), 256, 0, st>>>(pk_first_dense, (bf16*)dst_bf16, n_db);
+  pack_trunk_kernel<<<dim3(32, n_db), 256, 0, st>>>(pk_first_dense, (bf16*)dst_bf16, n_db, bwd);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+int trunk_bwd_fused(const void* g_in, void* g_out, void* const* fwd_bufs_dev, void* const* d_bufs_dev, const void* w_slices,
+                    int R, int B, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DG_CUDA(cudaFuncSetAttribute(trunk_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
+    attr_set = true;
+  }
+  TrunkBwdArgs a;
+  a.g_in = (const bf16*)g_in; a.g_out = (bf16*)g_out;
+  a.fwd_bufs = (const bf16* const*)fwd_bufs_dev; a.d_bufs = (bf16* const*)d_bufs_dev;
+  a.w = (const bf16*)w_slices; a.R = R; a.B = B;
+  const double px = (double)B * 256;
+  Prof prof(PC_DENSE_UMMA, 2.0 * px * 16.0 * 9.0 * 16.0 * 15.0 * 3.0 * R, px * 80.0 * 2.0 * 2.0 * 3.0 * R, st);
+  trunk_bwd_kernel<<<B, 128, T_SMEM, st>>>(a);
   DG_LAUNCH_CHECK();
   return 0;
 }
