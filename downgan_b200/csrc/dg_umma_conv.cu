@@ -28,7 +28,7 @@ namespace {
 
 using namespace um;
 
-constexpr int UMMA_THREADS = 128;
+constexpr int UMMA_THREADS = 256;  // 8 warps: all stage tiles; warps w and w+4 share TMEM lane quarter w and split the epilogue
 constexpr int MAX_SMEM = 227 * 1024 - 2048;  // dynamic limit (static smem of the kernel comes on top)
 enum Mode { S1 = 0, S2_FWD = 1, S2_DGRAD = 2 };
 
@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const UmmaArgs 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const int row_in_tile = (warp & 3) * 32 + (tid & 31), ehalf = warp >> 2;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   const int ncls = (mode == S2_DGRAD) ? 4 : 1;
   const uint32_t idesc = instr_desc(128, a.NT);
   const int kcs = a.nplanes >> 1;
@@ -264,14 +265,16 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const UmmaArgs 
     const int n = tile / a.tiles_per_img;
     const int y0 = (tile - n * a.tiles_per_img) * a.TH;
     const int rows = min(a.TH, a.Ht - y0);
+    int piece = 0;  // 16-column pieces alternate between the two warps of a lane quarter
     for (int mt = 0; mt < a.n_mt; ++mt) {
-      const int q = mt * 128 + tid;
+      const int q = mt * 128 + row_in_tile;
       const int r = (int)__umulhi((unsigned)q, a.magic_pw), c = q - r * PW;
       const bool valid = (r < rows) && (c < a.Wt);
       for (int cls = 0; cls < ncls; ++cls) {
         int yo = y0 + r, xo = c;
         if (mode == S2_DGRAD) { yo = 2 * yo + (cls >> 1); xo = 2 * xo + (cls & 1); }
-        for (int nc = 0; nc < a.NT; nc += 16) {
+        for (int nc = 0; nc < a.NT; nc += 16, ++piece) {
+          if ((piece & 1) != ehalf) continue;
           float v[16];
           tmem_ld16(tmem + lane_base + (mt * ncls + cls) * a.NT + nc, v);
           if (valid) epilogue16(op, v, n, yo, xo, co0 + nc);

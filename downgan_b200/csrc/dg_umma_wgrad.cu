@@ -20,7 +20,7 @@ namespace {
 
 using namespace um;
 
-constexpr int WG_THREADS_U = 128;
+constexpr int WG_THREADS_U = 256;  // 8 warps stage tiles; warps w and w+4 share TMEM lane quarter w
 constexpr int WG_MAX_SMEM = 227 * 1024 - 2048;
 
 struct WgArgs {
@@ -153,9 +153,9 @@ __device__ __forceinline__ void wgrad_body(const WgArgs& a, uint8_t* smem, uint6
   }
   tc_fence_after();
   // ---- epilogue: lane = input channel ci, columns = [tap][co chunk]; fp32 reductions into dW
-  const int ci = tid;
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-  for (int tap = 0; tap < 9; ++tap) {
+  const int ci = (warp & 3) * 32 + (tid & 31);
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  for (int tap = (warp >> 2); tap < 9; tap += 2) {   // the two warps of a lane quarter alternate taps
     for (int nc = 0; nc < a.NT; nc += 16) {
       float v[16];
       tmem_ld16(tmem + lane_base + tap * a.NT + nc, v);
