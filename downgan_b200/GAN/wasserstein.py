@@ -194,29 +194,46 @@ class WassersteinGAN:
                 self._copy_stream = torch.cuda.Stream(device=dev)
             main = torch.cuda.current_stream()
 
+            # three fixed staging slots reused round-robin: no allocation (hence no implicit device
+            # synchronisation) in the steady state; a slot is rewritten only after the step that read it
+            if getattr(self, "_slots", None) is None:
+                self._slots = [{"bufs": None, "done": None} for _ in range(3)]
+            self._slot_i = getattr(self, "_slot_i", 0)
+
             def stage(data):
                 if data is None:
                     return None
+                slot = self._slots[self._slot_i % len(self._slots)]
+                self._slot_i += 1
+                src = list(data[:3])
+                shapes = [tuple(t.shape) for t in src]
+                if slot["bufs"] is None or [tuple(b.shape) for b in slot["bufs"]] != shapes:
+                    slot["bufs"] = [torch.empty(s, device=dev, dtype=torch.float32) for s in shapes]
+                    slot["done"] = None
                 with torch.cuda.stream(self._copy_stream):
-                    ts = [t.to(device=dev, dtype=torch.float32, non_blocking=True) for t in data[:3]]
+                    if slot["done"] is not None:
+                        self._copy_stream.wait_event(slot["done"])
+                    for b, t in zip(slot["bufs"], src):
+                        b.copy_(t, non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(self._copy_stream)
-                return ts, ev
+                return slot, ev
 
             it = iter(dataloader)
             nxt = stage(next(it, None))
             logs = []
             while nxt is not None:
-                (ts, ev), nxt = nxt, stage(next(it, None))
+                (slot, ev), nxt = nxt, stage(next(it, None))
                 main.wait_event(ev)
-                for t in ts:
-                    t.record_stream(main)
+                ts = slot["bufs"]
                 coarse, fine = ts[0], ts[1]
                 alpha = ts[2] if len(ts) > 2 else None
                 self._critic_train_iteration(coarse, fine, alpha)
                 if self.num_steps % hp.critic_iterations == 0:
                     self._generator_train_iteration(coarse, fine)
                 self.num_steps += 1
+                slot["done"] = torch.cuda.Event()
+                slot["done"].record(main)
                 k = len(logs)
                 if getattr(self, "_log_host", None) is None or k >= self._log_host.shape[0]:
                     main.synchronize()  # growing the pinned ring: rare (every 1024 steps)

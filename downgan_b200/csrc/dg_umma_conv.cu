@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const UmmaArgs 
   if ((int)blockIdx.x >= a.tiles_total) return;
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)a.tmem_cols);
-  if (tid == 32) mbar_init(smem_u32(&mbar), 1);
+  const int nissue = min(UMMA_THREADS / 32, a.n_mt * ((mode == S2_DGRAD) ? 4 : 1));
+  if (tid == 32) mbar_init(smem_u32(&mbar), (uint32_t)nissue);
 
   const uint32_t sa0 = smem_u32(smem);
   const uint32_t sw = sa0 + a.w_off;
@@ -209,46 +210,34 @@ __global__ void __launch_bounds__(UMMA_THREADS) conv_umma_kernel(const UmmaArgs 
   int it = 0;
   for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x, ++it) {
     const uint32_t sa = sa0 + ((a.nbuf == 2) ? (it & 1) * a.a_bytes : 0u);
-    // ---- one thread issues every MMA of the tile
-    if (tid == 0) {
-      if (mode != S2_DGRAD) {
-        for (int mt = 0; mt < a.n_mt; ++mt) {
-          uint32_t acc = 0;
-          for (int tap = 0; tap < 9; ++tap) {
-            const int ky = tap / 3, kx = tap - 3 * ky;
-            int sub = 0, shift;
-            if (mode == S1) shift = ky * PW + kx;
-            else { sub = ((ky == 1) ? 0 : 2) + ((kx == 1) ? 0 : 1); shift = ((ky == 0) ? 0 : 1) * PW + ((kx == 0) ? 0 : 1); }
-            const uint32_t a0 = sa + sub * a.nplanes * a.PB + (mt * 128 + shift) * 16;
-            const uint32_t b0 = sw + tap * a.nplanes * wplane;
-            for (int kc = 0; kc < kcs; ++kc) {
-              umma_f16(tmem + mt * a.NT, smem_desc(a0 + 2 * kc * a.PB, a.PB, 128),
-                       smem_desc(b0 + 2 * kc * wplane, wplane, 128), idesc, acc);
-              acc = 1;
-            }
+    // ---- MMA issue, spread over warps: unit u = (M-tile, parity class) is issued by lane 0 of warp
+    //      u % nissue; descriptors are built once per tap and advanced by plain adds per K-step
+    if ((tid & 31) == 0 && warp < nissue) {
+      const uint64_t kstepA = (uint64_t)((2 * a.PB) >> 4), kstepB = (uint64_t)((2 * wplane) >> 4);
+      for (int u = warp; u < a.n_mt * ncls; u += nissue) {
+        const int mt = u / ncls, cls = u - mt * ncls;
+        const int py = cls >> 1, px = cls & 1;
+        uint32_t acc = 0;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap - 3 * ky;
+          int sub = 0, shift;
+          if (mode == S1) {
+            shift = ky * PW + kx;
+          } else if (mode == S2_FWD) {
+            sub = ((ky == 1) ? 0 : 2) + ((kx == 1) ? 0 : 1);
+            shift = ((ky == 0) ? 0 : 1) * PW + ((kx == 0) ? 0 : 1);
+          } else {
+            // output parity class (py,px): taps ky in {1} (py=0) or {0,2} (py=1); ky=0 reads dy one row below
+            if (((py == 0) != (ky == 1)) || ((px == 0) != (kx == 1))) continue;
+            shift = ((ky == 0) ? 1 : 0) * PW + ((kx == 0) ? 1 : 0);
+          }
+          uint64_t ad = smem_desc(sa + sub * a.nplanes * a.PB + (mt * 128 + shift) * 16, a.PB, 128);
+          uint64_t bd = smem_desc(sw + tap * a.nplanes * wplane, wplane, 128);
+          for (int kc = 0; kc < kcs; ++kc, ad += kstepA, bd += kstepB) {
+            umma_f16(tmem + u * a.NT, ad, bd, idesc, acc);
+            acc = 1;
           }
         }
-      } else {
-        // output parity class (py,px): taps ky in {1} (py=0) or {0,2} (py=1); ky=0 reads dy one row below
-        for (int mt = 0; mt < a.n_mt; ++mt)
-          for (int cls = 0; cls < 4; ++cls) {
-            const int py = cls >> 1, px = cls & 1;
-            uint32_t acc = 0;
-            for (int ky = 0; ky < 3; ++ky) {
-              if ((py == 0) != (ky == 1)) continue;
-              for (int kx = 0; kx < 3; ++kx) {
-                if ((px == 0) != (kx == 1)) continue;
-                const int shift = ((ky == 0) ? 1 : 0) * PW + ((kx == 0) ? 1 : 0);
-                const uint32_t a0 = sa + (mt * 128 + shift) * 16;
-                const uint32_t b0 = sw + (ky * 3 + kx) * a.nplanes * wplane;
-                for (int kc = 0; kc < kcs; ++kc) {
-                  umma_f16(tmem + (mt * 4 + cls) * a.NT, smem_desc(a0 + 2 * kc * a.PB, a.PB, 128),
-                           smem_desc(b0 + 2 * kc * wplane, wplane, 128), idesc, acc);
-                  acc = 1;
-                }
-              }
-            }
-          }
       }
       umma_commit(smem_u32(&mbar));
     }
