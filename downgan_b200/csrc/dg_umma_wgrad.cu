@@ -48,7 +48,7 @@ __device__ __forceinline__ void wgrad_body(const WgArgs& a, uint8_t* smem, uint6
   float bsum = 0.f;
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)a.tmem_cols);
-  if (tid == 32) { mbar_init(smem_u32(&mbar[0]), 1); mbar_init(smem_u32(&mbar[1]), 1); }
+  if (tid == 32) { mbar_init(smem_u32(&mbar[0]), WG_THREADS_U / 32); mbar_init(smem_u32(&mbar[1]), WG_THREADS_U / 32); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -119,11 +119,12 @@ __device__ __forceinline__ void wgrad_body(const WgArgs& a, uint8_t* smem, uint6
       for (int pos = bslice; pos < a.npos16; pos += bstep)
         bsum += __bfloat162float(*reinterpret_cast<const bf16*>(dz + pos * 16));
     }
-    if (tid == 0) {
+    // MMA issue spread over the warps: lane 0 of warp w issues taps w, w + 8 (each tap has its own
+    // TMEM accumulator, so the issue streams are independent); every issuing warp commits.
+    if ((tid & 31) == 0) {
       tc_fence_after();
-      uint64_t ad0[9];
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
+      const uint64_t bd0 = smem_desc(sd, 128, a.PBd);
+      for (int tap = warp; tap < 9; tap += WG_THREADS_U / 32) {
         const int ky = tap / 3, kx = tap - 3 * ky;
         int sub = 0, shift;
         if (s == 1) {
@@ -132,14 +133,10 @@ __device__ __forceinline__ void wgrad_body(const WgArgs& a, uint8_t* smem, uint6
           sub = ((ky == 1) ? 0 : 2) + ((kx == 1) ? 0 : 1);
           shift = ((ky == 0) ? 0 : 1) * a.PWt + ((kx == 0) ? 0 : 1);
         }
-        ad0[tap] = smem_desc(sx + sub * a.nplx * a.PBx + shift * 16, 128, a.PBx);
-      }
-      const uint64_t bd0 = smem_desc(sd, 128, a.PBd);
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
-        const uint64_t kadv = (uint64_t)(ks * 16);  // 16 positions x 16 B, in 16-byte descriptor units
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) umma_f16(tmem + tap * a.NT, ad0[tap] + kadv, bd0 + kadv, idesc, acc);
+        uint64_t ad = smem_desc(sx + sub * a.nplx * a.PBx + shift * 16, 128, a.PBx);
+        uint64_t bd = bd0;
+        for (int ks = 0; ks < ksteps; ++ks, ad += 16, bd += 16)  // +16 positions x 16 B, in descriptor units
+          umma_f16(tmem + tap * a.NT, ad, bd, idesc, (it > 0 || ks > 0) ? 1u : 0u);
       }
       umma_commit(smem_u32(&mbar[buf]));
     }
