@@ -190,7 +190,19 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created; keep stdout for the
+        # single JSON line by pointing fd 1 at stderr during initialisation and the first collective.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     lib = _lib.load()
 
     B = CFG["batch"]
@@ -297,8 +309,13 @@ def main():
         dom = max(conv, key=lambda k: prof[k]["ms"])
         d = prof[dom]
         ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        if os.path.exists(tpath):  # dram__bytes_read+write per launch from the committed ncu --set full captures
+            with open(tpath) as f:
+                traffic = json.load(f).get(dom, {}).get("bytes_per_launch")
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s",
-                    "frac": ach / tf_sus, "traffic": None, "peak_source": f"{which} (sustained cuBLAS bf16)",
+                    "frac": ach / tf_sus, "traffic": traffic, "peak_source": f"{which} (sustained cuBLAS bf16)",
                     "launches": d["launches"], "avg_launch_us": 1e3 * d["ms"] / d["launches"],
                     "share_of_profiled_time": d["ms"] / sum(v["ms"] for v in prof.values()),
                     "whole_step_algorithmic_tflops": alg_flops_per_rank / (ms * 1e-3) / 1e12,
