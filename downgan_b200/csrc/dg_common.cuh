@@ -213,3 +213,9 @@ int pack_trunk_slices(const float* pk_first_dense, void* dst_bf16, int n_db, int
 int trunk_bwd_fused(const void* g_in, void* g_out, void* const* fwd_bufs_dev, void* const* d_bufs_dev, const void* w_slices,
                     int R, int B, cudaStream_t st);
 }  // namespace dg
+
+namespace dg {
+// tcgen05 weight gradient with the taps folded into N via an im2col tile (dg_umma_wgrad_im2col.cu)
+bool wgrad_im2col_supported(const WgradOp& op);
+int wgrad_im2col(const WgradOp& op, cudaStream_t st);
+}  // namespace dg
