@@ -45,7 +45,7 @@ __device__ __forceinline__ void sts16(uint32_t addr, uint4 v) {
 template <int CI>
 __device__ __forceinline__ void gather_tile(const WgradOp& op, uint32_t sB, long long p0, long long total_pos, int tid) {
   constexpr int NV = (9 * CI + 15) / 16 * 16;
-  const int H = op.Hin, W = op.Win;
+  const int H = op.Hout, W = op.Wout, Hi = op.Hin, Wi = op.Win, st = op.stride;
   for (int pos = tid; pos < IC_TPOS; pos += IC_THREADS) {
     const long long p = p0 + pos;
     float v[NV];
@@ -57,9 +57,9 @@ __device__ __forceinline__ void gather_tile(const WgradOp& op, uint32_t sB, long
       const int y = (int)(q % H);
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
-        const int gy = y + tap / 3 - 1, gx = x + tap % 3 - 1;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-          const size_t base = ((size_t)(q - y + gy) * W + gx) * op.x.pitch + op.x.coff;
+        const int gy = st * y + tap / 3 - 1, gx = st * x + tap % 3 - 1;
+        if (gy >= 0 && gy < Hi && gx >= 0 && gx < Wi) {
+          const size_t base = (((size_t)(q / H) * Hi + gy) * Wi + gx) * op.x.pitch + op.x.coff;
 #pragma unroll
           for (int c = 0; c < CI; ++c) v[tap * CI + c] = ldx(op.x.p, op.x.bf, base + c);
         }
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(IC_THREADS) wgrad_im2col_kernel(const IcArgs a
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t idesc = instr_desc(128, a.NR, 1, 1);
-  const int H = op.Hin, W = op.Win, Ci = op.Ci;
+  const int H = op.Hout, W = op.Wout, Hi = op.Hin, Wi = op.Win, Ci = op.Ci, cst = op.stride;
   const bf16* db = (const bf16*)op.dy.p;
 
   int it = 0;
@@ -121,9 +121,9 @@ __global__ void __launch_bounds__(IC_THREADS) wgrad_im2col_kernel(const IcArgs a
           const int x = (int)(p % W);
           const long long q = p / W;
           const int y = (int)(q % H);
-          const int gy = y + tap / 3 - 1, gx = x + tap % 3 - 1;
-          ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
-          src = xb + ((size_t)(q - y + gy) * W + gx) * op.x.pitch + op.x.coff + g * 8;
+          const int gy = cst * y + tap / 3 - 1, gx = cst * x + tap % 3 - 1;
+          ok = gy >= 0 && gy < Hi && gx >= 0 && gx < Wi;
+          src = xb + (((size_t)(q / H) * Hi + gy) * Wi + gx) * op.x.pitch + op.x.coff + g * 8;
         }
         cp_async16(sB + (tap * gpt + g) * IC_PB + pos * 16, ok ? src : xb, ok ? 16 : 0);
       }
@@ -171,7 +171,9 @@ __global__ void __launch_bounds__(IC_THREADS) wgrad_im2col_kernel(const IcArgs a
 }
 
 bool plan_ic(const WgradOp& op, IcArgs& a) {
-  if (op.stride != 1 || op.Hin != op.Hout || op.Win != op.Wout) return false;
+  if (op.stride == 1) { if (op.Hin != op.Hout || op.Win != op.Wout) return false; }
+  else if (op.stride == 2) { if (op.Hin != 2 * op.Hout || op.Win != 2 * op.Wout) return false; }
+  else return false;
   if (!op.dy.bf || op.Co % 16 || op.Co > 128 || op.dy.pitch % 8 || op.dy.coff % 8) return false;
   const bool vec = (op.Ci % 8 == 0) && op.x.bf && op.x.pitch % 8 == 0 && op.x.coff % 8 == 0;
   if (!vec && op.Ci > 3) return false;
@@ -196,7 +198,8 @@ unsigned ic_smem(const IcArgs& a) { return a.a_off + 16 * IC_PB; }
 
 bool wgrad_im2col_supported(const WgradOp& op) {
   IcArgs a;
-  return plan_ic(op, a) && ic_smem(a) <= 227 * 1024 - 2048;
+  // policy: stride-2 layers run faster on the parity-sub-image kernel (measured), the kernel itself handles both
+  return op.stride == 1 && plan_ic(op, a) && ic_smem(a) <= 227 * 1024 - 2048;
 }
 
 int wgrad_im2col(const WgradOp& op, cudaStream_t st) {
