@@ -275,7 +275,7 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
   GA(g->l1, 64);
   // backward
   GA(g->D, B * pc * 5 * F * g->esz);
-  if (g->bf && F % 16 == 0 && g->R > 0) {
+  if (g->bf && F % 16 == 0 && 5 * F <= 128 && g->R > 0) {  // the tcgen05 wgrad kernel takes Ci <= 128
     g->Dall.assign((size_t)g->R * 3, nullptr);
     g->Dall[0] = g->D;
     for (int i = 1; i < g->R * 3; ++i) GA(g->Dall[i], B * pc * 5 * F * g->esz);

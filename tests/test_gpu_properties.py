@@ -1,0 +1,137 @@
+"""Size-independent properties of the CUDA path at BASELINE.json's full single-GPU size (cfg-2:
+B=64, 2-ch 16x16 -> 128x128, F=16, 16 RRDB) and on the other configs' shapes, where the CPU oracle
+would take minutes: batch-split linearity of the gradients, a directional-derivative check of the
+critic loss against its analytic gradient, ragged / single-sample batches, cfg-3 and cfg-4 shapes."""
+import pytest
+import torch
+
+from downgan_b200 import _lib
+from downgan_b200.synthetic import synth_batch
+from oracle import networks as onet
+from oracle import trainer as otr
+
+import parity_util as pu
+from test_gpu_parity import _run_steps
+
+pytestmark = pytest.mark.gpu
+
+CFG2_G = onet.GeneratorSpec(filters=16, channels=2)
+CFG2_C = onet.CriticSpec(coarse_dim=16, fine_dim=128, nc=2)
+
+
+def _flat(d):
+    return torch.cat([v.reshape(-1).double() for v in d.values()])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_batch_split_linearity_cfg2(precision):
+    """Every loss term is a mean over independent samples (GP included): the B=64 gradients must equal
+    the average of the gradients of the two B=32 halves (same kernels, different tiling / batching)."""
+    G, C, _, _ = pu.build_pair(CFG2_G, CFG2_C, precision, seed=0, critic_scale=1.9)
+    coarse, fine, alpha = synth_batch(64, 2, 16)
+    sc, cg, sg, gg = _run_steps(G, C, coarse, fine, alpha)
+    halves = [_run_steps(G, C, coarse[i:i + 32], fine[i:i + 32], alpha[i:i + 32]) for i in (0, 32)]
+    cg2 = 0.5 * (_flat(halves[0][1]) + _flat(halves[1][1]))
+    gg2 = 0.5 * (_flat(halves[0][3]) + _flat(halves[1][3]))
+    tol = 1e-4 if precision == "fp32" else 2e-3
+    assert float((_flat(cg) - cg2).norm() / cg2.norm()) < tol
+    assert float((_flat(gg) - gg2).norm() / gg2.norm()) < tol
+    # scalars: losses are means too
+    assert abs(float(sc[0]) - 0.5 * (float(halves[0][0][0]) + float(halves[1][0][0]))) < 1e-3 * abs(float(sc[0]))
+    assert abs(float(sg[0]) - 0.5 * (float(halves[0][2][0]) + float(halves[1][2][0]))) < 1e-3 * abs(float(sg[0]))
+
+
+def test_directional_derivative_of_critic_loss_cfg2(monkeypatch):
+    """d/de L_C(theta + e*v) at e=0 by central differences of the fp32-mode loss against <grad, v>
+    from dg_critic_step, at full cfg-2 size.  The Wasserstein part E[C(fake)] - E[C(real)] is continuous
+    and piecewise smooth in the weights, so finite differences are meaningful; the gradient penalty is
+    not (||dC/dx|| jumps whenever a LeakyReLU mask flips), it is checked against autograd instead
+    (test_gp_standalone, test_steps_*), so gp_lambda is 0 here."""
+    from downgan_b200.config import hyperparams as hpm
+    monkeypatch.setattr(hpm, "gp_lambda", 0.0)
+    G, C, _, _ = pu.build_pair(CFG2_G, CFG2_C, "fp32", seed=0, critic_scale=1.9)
+    coarse, fine, alpha = synth_batch(64, 2, 16)
+    sc, cg, _sg, _gg = _run_steps(G, C, coarse, fine, alpha)
+    grad = _flat(cg)
+    flat = C.flat_params()
+    # direction = the gradient itself: the directional derivative is then ||grad||, far above the
+    # resolution of an fp32 loss value of ~90 (a random direction gives a derivative lost in rounding)
+    v = grad / grad.norm()
+    base = flat.detach().clone()
+    eps = 1e-2 / float(grad.norm())
+    losses = []
+    for sgn in (+1.0, -1.0):
+        with torch.no_grad():
+            flat.copy_(base + (sgn * eps * v).float().cuda())
+        C.mark_params_changed()
+        s, *_ = _run_steps(G, C, coarse, fine, alpha)
+        losses.append(float(s[0]))
+    with torch.no_grad():
+        flat.copy_(base)
+    C.mark_params_changed()
+    fd = (losses[0] - losses[1]) / (2 * eps)
+    an = float(torch.dot(grad, v))
+    assert an > 0 and abs(fd - an) <= 3e-2 * an, (fd, an)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("batch", [1, 5])
+def test_ragged_and_single_sample_batches(precision, batch):
+    """The reference mis-shapes ragged batches (wasserstein.py:110 uses hp.batch_size); here any batch works."""
+    G, C, g_sd, c_sd = pu.build_pair(CFG2_G, CFG2_C, precision, seed=1)
+    coarse, fine, alpha = synth_batch(batch, 2, 16, seed=77)
+    hp = otr.Hyper()
+    oc = otr.critic_loss_and_grads(g_sd, CFG2_G, c_sd, CFG2_C, coarse, fine, alpha, hp)
+    sc, cg, sg, gg = _run_steps(G, C, coarse, fine, alpha)
+    tol = 1e-3 if precision == "fp32" else 2e-2
+    assert abs(float(sc[0]) - float(oc["loss"])) <= tol * abs(float(oc["loss"]))
+    _w, _k, flat = pu.grad_report(cg, oc["grads"])
+    # a single sample has no averaging over the batch: the bf16 mask-flip floor is a little higher
+    assert flat < (1e-3 if precision == "fp32" else 1.5e-1)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cfg3_seven_covariates_step(precision):
+    """cfg-3 shapes: 7 input channels (land-sea mask channel is 0/1)."""
+    gspec = onet.GeneratorSpec(filters=16, channels=7)
+    G, C, g_sd, c_sd = pu.build_pair(gspec, CFG2_C, precision, seed=2)
+    coarse, fine, alpha = synth_batch(4, 7, 16)
+    hp = otr.Hyper()
+    og = otr.generator_loss_and_grads(g_sd, gspec, c_sd, CFG2_C, coarse, fine, hp)
+    _sc, _cg, sg, gg = _run_steps(G, C, coarse, fine, alpha)
+    tol = 1e-3 if precision == "fp32" else 2e-2
+    assert abs(float(sg[0]) - float(og["loss"])) <= tol * abs(float(og["loss"]))
+    _w, _k, flat = pu.grad_report(gg, og["grads"])
+    assert flat < (1e-3 if precision == "fp32" else 1e-1)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cfg4_like_shapes_step(precision):
+    """cfg-4 family (F = 32, coarse 32x32 -> 256x256) at reduced depth (2 RRDB) and batch 2: exercises the
+    per-layer tcgen05 kernels with 32..256-channel layers and the non-fused trunk path."""
+    gspec = onet.GeneratorSpec(filters=32, channels=7, num_res_blocks=2)
+    cspec = onet.CriticSpec(coarse_dim=32, fine_dim=256, nc=2)
+    G, C, g_sd, c_sd = pu.build_pair(gspec, cspec, precision, seed=3)
+    coarse, fine, alpha = synth_batch(2, 7, 32)
+    hp = otr.Hyper()
+    oc = otr.critic_loss_and_grads(g_sd, gspec, c_sd, cspec, coarse, fine, alpha, hp)
+    og = otr.generator_loss_and_grads(g_sd, gspec, c_sd, cspec, coarse, fine, hp)
+    sc, cg, sg, gg = _run_steps(G, C, coarse, fine, alpha)
+    tol = 1e-3 if precision == "fp32" else 2e-2
+    assert abs(float(sc[0]) - float(oc["loss"])) <= tol * abs(float(oc["loss"]))
+    assert abs(float(sg[0]) - float(og["loss"])) <= tol * abs(float(og["loss"]))
+    for got, ref in ((cg, oc["grads"]), (gg, og["grads"])):
+        _w, _k, flat = pu.grad_report(got, ref)
+        assert flat < (2e-3 if precision == "fp32" else 1.5e-1), flat
+
+
+def test_inference_tiles_cfg5_like():
+    """cfg-5: generator-only inference under no_grad on a larger tile (fully convolutional forward)."""
+    gspec = onet.GeneratorSpec(filters=16, channels=7, num_res_blocks=2)
+    G, _C, g_sd, _ = pu.build_pair(gspec, CFG2_C, "bf16", seed=4)
+    coarse, _f, _a = synth_batch(2, 7, 64)
+    with torch.no_grad():
+        out = G(coarse.cuda())
+        ref = onet.generator_forward(g_sd, gspec, coarse)
+    assert out.shape == (2, 2, 512, 512)
+    assert pu.rel(out, ref) < 2e-2
