@@ -326,7 +326,12 @@ bool plan(const ConvOp& op, UmmaArgs& a) {
     if (smem > (size_t)MAX_SMEM) break;
     if ((TH + 2) * PW * nplanes >= 65536) break;  // loader index arithmetic is exact below 2^16
     const int ntiles = (Ht + TH - 1) / TH;
-    const double eff = (double)(Ht * Wt) / ((double)ntiles * n_mt * 128);
+    // score = MMA row efficiency x halo re-read efficiency x chip fill (tiny tiles pay ~us of fixed
+    // per-tile latency and re-stage their halo rows; too few tiles leave SMs idle)
+    const double row_eff = (double)(Ht * Wt) / ((double)ntiles * n_mt * 128);
+    const double halo_eff = (double)TH / (TH + ((mode == S1) ? 2 : 1));
+    const double fill = std::min(1.0, (double)ntiles * op.B / 296.0);
+    const double eff = row_eff * halo_eff * fill;
     if (eff > best + 1e-9) { best = eff; bestTH = TH; best_mt = n_mt; }
   }
   if (bestTH == 0) return false;
