@@ -44,6 +44,7 @@ _SIGNATURES = {
     "dg_has_tcgen05": (C.c_int, []),
     "dg_launch_count": (C.c_int64, []),
     "dg_profile": (C.c_int, [C.c_int]),
+    "dg_set_tuning": (C.c_int, [C.c_int, C.c_int]),
     "dg_profile_report": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
     "dg_generator_create": (C.c_int, [C.POINTER(GeneratorConfig), C.POINTER(_P)]),
     "dg_generator_destroy": (C.c_int, [_P]),

@@ -62,6 +62,7 @@ enum ProfClass {
   PC_L1, PC_GP_NORMS, PC_ADAM, PC_INTERP, PC_LAYOUT, PC_COUNT
 };
 extern bool g_prof_on;
+extern int g_tune[];  // dg_set_tuning switches
 struct Prof {
   int idx = -1;
   cudaStream_t st;
@@ -177,6 +178,9 @@ int gen_scalars(const float* scores, int B, const float* l1, float gamma, float 
 // tcgen05 path (dg_umma.cu)
 bool umma_supported(const ConvOp& op);
 int conv_umma(const ConvOp& op, cudaStream_t st);
+// warp-specialised persistent variant (dg_umma_conv_ws.cu); DG_CONV_WS=0 in the environment falls back to conv_umma
+bool umma_ws_supported(const ConvOp& op);
+int conv_umma_ws(const ConvOp& op, cudaStream_t st);
 // bf16 re-pack of fp32 packed conv weights [tap][Ci][CoP] into the tcgen05 B-operand image
 // [(tap*Ci/8 + ci/8)][CoP][8]; element offsets are shared with the fp32 packed buffer.
 struct UmmaPackDesc { long long off; int Ci, CoP; };

@@ -748,4 +748,13 @@ extern "C" int dg_profile_report(double* out, int n_classes) {
   }
   return 0;
 }
+namespace dg { int g_tune[DG_TUNE_KEYS] = {1, 1, 1, 1, 1, 1, 1, 1}; }
+extern "C" int dg_set_tuning(int key, int value) {
+  if (key < 0 || key >= DG_TUNE_KEYS) { dg::set_error("dg_set_tuning: unknown key %d", key); return DG_ERR_INVALID; }
+  const int prev = dg::g_tune[key];
+  dg::g_tune[key] = value;
+  if (key == 1)  // device-wide L1/shared split preference for kernels without their own (avoids carveout flips between launches)
+    cudaDeviceSetCacheConfig(value ? cudaFuncCachePreferShared : cudaFuncCachePreferNone);
+  return prev;
+}
 extern "C" int64_t dg_launch_count(void) { return (int64_t)dg::g_launches.load(); }

@@ -3,6 +3,7 @@
 // Reference statements replaced are cited per function (paths under
 // /root/reference/DoWnGAN).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -57,6 +58,8 @@ int run_wgrad(const WgradOp& w, cudaStream_t st) {
 
 int run_conv(const ConvOp& op, cudaStream_t st) {
   if (conv_skinny_supported(op)) return conv_skinny(op, st);
+  static const bool ws = !(getenv("DG_CONV_WS") && atoi(getenv("DG_CONV_WS")) == 0);
+  if (ws && g_tune[0] && op.w_umma && umma_ws_supported(op)) return conv_umma_ws(op, st);
   if (op.w_umma && umma_supported(op)) return conv_umma(op, st);
   return conv_direct(op, st);
 }
