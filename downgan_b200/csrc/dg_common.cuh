@@ -180,6 +180,9 @@ bool umma_supported(const ConvOp& op);
 int conv_umma(const ConvOp& op, cudaStream_t st);
 // warp-specialised persistent variant (dg_umma_conv_ws.cu); DG_CONV_WS=0 in the environment falls back to conv_umma
 bool umma_ws_supported(const ConvOp& op);
+// TMA-fed weight gradient on swizzled NHWC tiles (dg_umma_wgrad_ws.cu)
+bool wgrad_ws_supported(const WgradOp& op);
+int wgrad_ws(const WgradOp& op, cudaStream_t st);
 int conv_umma_ws(const ConvOp& op, cudaStream_t st);
 // bf16 re-pack of fp32 packed conv weights [tap][Ci][CoP] into the tcgen05 B-operand image
 // [(tap*Ci/8 + ci/8)][CoP][8]; element offsets are shared with the fp32 packed buffer.

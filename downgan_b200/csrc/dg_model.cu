@@ -50,6 +50,7 @@ int dev_alloc(std::vector<void*>& pool, void** out, size_t bytes) {
 }
 
 int run_wgrad(const WgradOp& w, cudaStream_t st) {
+  if (g_tune[2] && wgrad_ws_supported(w)) return wgrad_ws(w, st);
   if (wgrad_im2col_supported(w)) return wgrad_im2col(w, st);
   if (wgrad_skinny_supported(w)) return wgrad_skinny(w, st);
   if (wgrad_umma_supported(w)) return wgrad_umma(w, st);
