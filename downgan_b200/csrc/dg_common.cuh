@@ -142,8 +142,9 @@ struct PackDesc {
   int src_ci_total;    // Ci of the source weight (j*F)
   int dst_row_off;     // row (input channel of the dgrad op) where this slice starts
   int dst_CoP;         // CoP of the destination op
+  int umma;            // 1: also emit the bf16 tcgen05 B-operand image (same element offset) while packing
 };
-int pack_weights(const float* params, float* packed, const PackDesc* table_dev, int n, int max_elems, cudaStream_t st);
+int pack_weights(const float* params, float* packed, void* packed_umma, const PackDesc* table_dev, int n, int max_elems, cudaStream_t st);
 int unpack_wgrads(const float* packed, float* grads, const PackDesc* table_dev, int n, int max_elems, cudaStream_t st);
 
 int nchw_to_nhwc(const float* src, TV dst, int B, int C, int H, int W, cudaStream_t st);

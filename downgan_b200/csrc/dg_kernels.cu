@@ -306,8 +306,70 @@ __global__ void colsum_kernel(TV dy, size_t pixels, int C, float* out, size_t pi
   }
   if (threadIdx.x == 0 && threadIdx.y == 0) g_colsum_done = 0;
 }
+// bf16 rows with C in {16,32,64,128,256}: 16-byte loads (8 channels per thread), four pixels in flight per
+// thread; same fp64 last-block combine as colsum_kernel.
+__global__ void __launch_bounds__(256) colsum_vec_kernel(TV dy, size_t pixels, int C, float* out, size_t pix_per_block) {
+  __shared__ float sh[256 * 8];
+  __shared__ bool last;
+  const int cpp = C >> 3;              // 16-byte chunks per pixel (a power of two <= 32)
+  const int chunk = threadIdx.x & (cpp - 1), pl = threadIdx.x / cpp, npl = 256 / cpp;
+  const size_t p0 = (size_t)blockIdx.x * pix_per_block;
+  const size_t p1 = min(pixels, p0 + pix_per_block);
+  const bf16* base = (const bf16*)dy.p + dy.coff + chunk * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  auto add8 = [&](const uint4& q) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      acc[2 * k] += __uint_as_float(w[k] << 16);
+      acc[2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+    }
+  };
+  size_t p = p0 + pl;
+  for (; p + 3 * (size_t)npl < p1; p += 4 * (size_t)npl) {
+    const uint4 q0 = *reinterpret_cast<const uint4*>(base + p * dy.pitch);
+    const uint4 q1 = *reinterpret_cast<const uint4*>(base + (p + npl) * dy.pitch);
+    const uint4 q2 = *reinterpret_cast<const uint4*>(base + (p + 2 * (size_t)npl) * dy.pitch);
+    const uint4 q3 = *reinterpret_cast<const uint4*>(base + (p + 3 * (size_t)npl) * dy.pitch);
+    add8(q0); add8(q1); add8(q2); add8(q3);
+  }
+  for (; p < p1; p += npl) add8(*reinterpret_cast<const uint4*>(base + p * dy.pitch));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[threadIdx.x * 8 + j] = acc[j];
+  __syncthreads();
+  if ((int)threadIdx.x < C) {
+    const int c = threadIdx.x, ch = c >> 3, j = c & 7;
+    float t = 0.f;
+    for (int q = 0; q < npl; ++q) t += sh[(q * cpp + ch) * 8 + j];
+    g_colsum_part[(size_t)blockIdx.x * C + c] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(&g_colsum_done, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    double t = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) t += (double)g_colsum_part[(size_t)b * C + c];
+    out[c] += (float)t;
+  }
+  if (threadIdx.x == 0) g_colsum_done = 0;
+}
 int colsum(TV dy, size_t pixels, int C, float* out, cudaStream_t st) {
   DG_CHECK(C <= COLSUM_MAX_C, "colsum: %d channels > %d", C, COLSUM_MAX_C);
+  const bool vec = dy.bf && (C == 16 || C == 32 || C == 64 || C == 128 || C == 256) && dy.pitch % 8 == 0 && dy.coff % 8 == 0 &&
+                   pixels >= 4096;
+  if (vec) {
+    size_t ppb = (pixels + 148 * 4 - 1) / (148 * 4);
+    if (ppb < 256) ppb = 256;
+    const unsigned grid = (unsigned)((pixels + ppb - 1) / ppb);
+    colsum_vec_kernel<<<grid, 256, 0, st>>>(dy, pixels, C, out, ppb);
+    DG_LAUNCH_CHECK();
+    return 0;
+  }
   size_t ppb = (pixels + 148 * 4 - 1) / (148 * 4);
   if (ppb < 64) ppb = 64;
   unsigned grid = (unsigned)((pixels + ppb - 1) / ppb);
@@ -319,63 +381,69 @@ int colsum(TV dy, size_t pixels, int C, float* out, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 // table-driven packing (one launch per network)
 // ---------------------------------------------------------------------------
-__global__ void pack_kernel(const float* __restrict__ src, float* __restrict__ dst, const PackDesc* __restrict__ tab,
-                            int unpack) {
+// One pass per table entry: OIHW fp32 -> packed fp32 [tap][row][CoP] and (d.umma) the bf16 tcgen05 B-operand
+// image [(tap*R/8 + row/8)][CoP][8] at the same element offset of `udst`.  32-bit index arithmetic.
+__global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src, float* __restrict__ dst, bf16* __restrict__ udst,
+                                                   const PackDesc* __restrict__ tab, int unpack) {
   const PackDesc d = tab[blockIdx.y];
-  long long n;
-  if (d.mode == 5) n = d.Co;
-  else if (d.mode == 4) n = (long long)d.Co * d.Ci;
-  else n = (long long)d.Co * d.Ci * 9;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+  unsigned n;
+  if (d.mode == 5) n = (unsigned)d.Co;
+  else if (d.mode == 4) n = (unsigned)d.Co * (unsigned)d.Ci;
+  else n = (unsigned)d.Co * (unsigned)d.Ci * 9u;
+  const float* s_base = src + (unpack ? d.dst_off : d.src_off);
+  float* d_base = dst + (unpack ? d.src_off : d.dst_off);
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     if (d.mode == 5) {  // bias copy
-      if (unpack) dst[d.src_off + e] = src[d.dst_off + e];
-      else dst[d.dst_off + e] = src[d.src_off + e];
+      d_base[e] = s_base[e];
       continue;
     }
     if (d.mode == 4) {
       // linear weight (Co=N rows, Ci=K cols) with NCHW->NHWC column permutation: K = C*HW, C = slice_off
-      const int C = d.slice_off, HW = d.Ci / C;
-      const int j = (int)(e / d.Ci), k = (int)(e % d.Ci);  // k in NCHW order: c*HW + hw
-      const int c = k / HW, hw = k % HW;
-      const long long pk = (long long)j * d.Ci + (long long)hw * C + c;
-      if (unpack) dst[d.src_off + e] = src[d.dst_off + pk];
-      else dst[d.dst_off + pk] = src[d.src_off + e];
+      const unsigned C = (unsigned)d.slice_off, HW = (unsigned)d.Ci / C;
+      const unsigned j = e / (unsigned)d.Ci, k = e - j * (unsigned)d.Ci;  // k in NCHW order: c*HW + hw
+      const unsigned c = k / HW, hw = k - c * HW;
+      const unsigned pk = j * (unsigned)d.Ci + hw * C + c;
+      if (unpack) d_base[e] = s_base[pk];
+      else d_base[pk] = s_base[e];
       continue;
     }
-    const int tap = (int)(e % 9);
-    const long long r = e / 9;
-    long long s_idx, p_idx;
+    const unsigned r = e / 9u, tap = e - 9u * r;
+    const unsigned co = r / (unsigned)d.Ci, ci = r - co * (unsigned)d.Ci;
+    unsigned s_idx, tp, row, col, R, cols;
     if (d.mode == 3) {
       // slice of a dense-block weight W_j[co][slice_off+ci][tap] -> row dst_row_off+co, col ci, flipped tap
-      const int ci = (int)(r % d.Ci), co = (int)(r / d.Ci);
-      s_idx = ((long long)co * d.src_ci_total + d.slice_off + ci) * 9 + tap;
-      p_idx = ((long long)(8 - tap) * d.CoP /*rows_total*/ + d.dst_row_off + co) * d.dst_CoP + ci;
+      s_idx = (co * (unsigned)d.src_ci_total + (unsigned)d.slice_off + ci) * 9u + tap;
+      tp = 8u - tap; row = (unsigned)d.dst_row_off + co; col = ci; R = (unsigned)d.CoP /*rows_total*/; cols = (unsigned)d.dst_CoP;
     } else {
-      const int ci = (int)(r % d.Ci), co = (int)(r / d.Ci);
-      s_idx = ((long long)co * d.Ci + ci) * 9 + tap;
-      if (d.mode == 0) p_idx = ((long long)tap * d.Ci + ci) * d.CoP + co;
-      else if (d.mode == 1) p_idx = ((long long)(8 - tap) * d.Co + co) * d.CoP + ci;   // CoP = round16(Ci)
-      else p_idx = ((long long)tap * d.Co + co) * d.CoP + ci;                          // mode 2
+      s_idx = e;  // (co*Ci + ci)*9 + tap
+      if (d.mode == 0) { tp = tap; row = ci; col = co; R = (unsigned)d.Ci; }
+      else if (d.mode == 1) { tp = 8u - tap; row = co; col = ci; R = (unsigned)d.Co; }  // CoP = round16(Ci)
+      else { tp = tap; row = co; col = ci; R = (unsigned)d.Co; }                          // mode 2
+      cols = (unsigned)d.CoP;
     }
-    if (unpack) dst[d.src_off + s_idx] = src[d.dst_off + p_idx];
-    else dst[d.dst_off + p_idx] = src[d.src_off + s_idx];
+    const unsigned p_idx = (tp * R + row) * cols + col;
+    if (unpack) {
+      d_base[s_idx] = s_base[p_idx];
+    } else {
+      const float v = s_base[s_idx];
+      d_base[p_idx] = v;
+      if (d.umma) udst[d.dst_off + (((tp * (R >> 3) + (row >> 3)) * cols + col) << 3) + (row & 7u)] = __float2bfloat16_rn(v);
+    }
   }
 }
-int pack_weights(const float* params, float* packed, const PackDesc* tab, int n, int max_elems, cudaStream_t st) {
+static inline int pack_blocks(int max_elems) {
+  int bx = (max_elems + 1023) / 1024;  // ~4 elements per thread
+  return bx < 1 ? 1 : (bx > 512 ? 512 : bx);
+}
+int pack_weights(const float* params, float* packed, void* packed_umma, const PackDesc* tab, int n, int max_elems, cudaStream_t st) {
   if (n == 0) return 0;
-  int bx = (max_elems + 255) / 256;
-  if (bx > 64) bx = 64;
-  if (bx < 1) bx = 1;
-  pack_kernel<<<dim3(bx, n), 256, 0, st>>>(params, packed, tab, 0);
+  pack_kernel<<<dim3(pack_blocks(max_elems), n), 256, 0, st>>>(params, packed, (bf16*)packed_umma, tab, 0);
   DG_LAUNCH_CHECK();
   return 0;
 }
 int unpack_wgrads(const float* packed, float* grads, const PackDesc* tab, int n, int max_elems, cudaStream_t st) {
   if (n == 0) return 0;
-  int bx = (max_elems + 255) / 256;
-  if (bx > 64) bx = 64;
-  if (bx < 1) bx = 1;
-  pack_kernel<<<dim3(bx, n), 256, 0, st>>>(packed, grads, tab, 1);
+  pack_kernel<<<dim3(pack_blocks(max_elems), n), 256, 0, st>>>(packed, grads, nullptr, tab, 1);
   DG_LAUNCH_CHECK();
   return 0;
 }

@@ -189,6 +189,7 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
   for (auto& l : g->layers) {
     l.pk_off = pk; pk += (long long)packed_w_elems(l.Ci, l.Co);
     PackDesc d{}; d.src_off = l.w_off; d.dst_off = l.pk_off; d.Ci = l.Ci; d.Co = l.Co; d.CoP = round_up(l.Co, 16); d.mode = 0;
+    d.umma = g->bf && umma_ok(l.Ci, l.Co);
     tf.push_back(d);
     maxf = std::max(maxf, l.Ci * l.Co * 9);
   }
@@ -203,6 +204,7 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
     Layer& l = g->layers[li];
     l.pkd_off = pkd; pkd += (long long)packed_w_elems(l.Co, l.Ci);
     PackDesc d{}; d.src_off = l.w_off; d.dst_off = l.pkd_off; d.Ci = l.Ci; d.Co = l.Co; d.CoP = round_up(l.Ci, 16); d.mode = 1;
+    d.umma = g->bf && umma_ok(l.Co, l.Ci);
     td.push_back(d);
     maxd = std::max(maxd, l.Ci * l.Co * 9);
   };
@@ -225,6 +227,7 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
           PackDesc d{};
           d.src_off = l.w_off; d.dst_off = base; d.Ci = F; d.Co = F; d.CoP = rows; d.mode = 3;
           d.slice_off = k * F; d.src_ci_total = j * F; d.dst_row_off = (5 - j) * F; d.dst_CoP = round_up(F, 16);
+          d.umma = g->bf && F % 16 == 0;
           td.push_back(d);
           maxd = std::max(maxd, F * F * 9);
         }
@@ -310,10 +313,8 @@ extern "C" int dg_generator_destroy(dg_generator* g) {
 extern "C" int dg_generator_pack(dg_generator* g, const float* params, void* stream) {
   DG_CHECK(g && params, "dg_generator_pack: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  DG_TRY(pack_weights(params, g->pk, g->tab_fwd, g->n_fwd, g->max_fwd, st));
-  DG_TRY(pack_weights(params, g->pkd, g->tab_dgrad, g->n_dgrad, g->max_dgrad, st));
-  DG_TRY(pack_umma(g->pk, g->pk_u, g->utab_fwd, g->n_ufwd, g->max_ufwd, st));
-  DG_TRY(pack_umma(g->pkd, g->pkd_u, g->utab_dgrad, g->n_udgrad, g->max_udgrad, st));
+  DG_TRY(pack_weights(params, g->pk, g->pk_u, g->tab_fwd, g->n_fwd, g->max_fwd, st));
+  DG_TRY(pack_weights(params, g->pkd, g->pkd_u, g->tab_dgrad, g->n_dgrad, g->max_dgrad, st));
   if (trunk_fused_supported(g->F, g->Hc, g->R, g->bf))
   {
     DG_TRY(pack_trunk_slices(g->pk + g->layers[g->idx_db(0, 0, 1)].pk_off, g->pk_trunk, g->R * 3, 0, st));
@@ -654,11 +655,13 @@ extern "C" int dg_critic_create(const dg_critic_config* cfg, dg_critic** out) {
     Layer& l = c->L[i];
     l.pk_off = pk; pk += (long long)packed_w_elems(l.Ci, l.Co);
     PackDesc d{}; d.src_off = l.w_off; d.dst_off = l.pk_off; d.Ci = l.Ci; d.Co = l.Co; d.CoP = round_up(l.Co, 16); d.mode = 0;
+    d.umma = c->bf && umma_ok(l.Ci, l.Co);
     tf.push_back(d);
     maxf = std::max(maxf, l.Ci * l.Co * 9);
     l.pkd_off = pkd; pkd += (long long)packed_w_elems(l.Co, l.Ci);
     PackDesc e{}; e.src_off = l.w_off; e.dst_off = l.pkd_off; e.Ci = l.Ci; e.Co = l.Co; e.CoP = round_up(l.Ci, 16);
     e.mode = (l.stride == 2) ? 2 : 1;
+    e.umma = c->bf && umma_ok(l.Co, l.Ci);
     td.push_back(e);
     maxd = std::max(maxd, l.Ci * l.Co * 9);
   }
@@ -735,10 +738,8 @@ extern "C" int dg_critic_destroy(dg_critic* c) {
 extern "C" int dg_critic_pack(dg_critic* c, const float* params, void* stream) {
   DG_CHECK(c && params, "dg_critic_pack: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  DG_TRY(pack_weights(params, c->pk, c->tab_fwd, c->n_fwd, c->max_fwd, st));
-  DG_TRY(pack_weights(params, c->pkd, c->tab_dgrad, c->n_dgrad, c->max_dgrad, st));
-  DG_TRY(pack_umma(c->pk, c->pk_u, c->utab_fwd, c->n_ufwd, c->max_ufwd, st));
-  DG_TRY(pack_umma(c->pkd, c->pkd_u, c->utab_dgrad, c->n_udgrad, c->max_udgrad, st));
+  DG_TRY(pack_weights(params, c->pk, c->pk_u, c->tab_fwd, c->n_fwd, c->max_fwd, st));
+  DG_TRY(pack_weights(params, c->pkd, c->pkd_u, c->tab_dgrad, c->n_dgrad, c->max_dgrad, st));
   c->packed = true;
   return 0;
 }
@@ -1045,7 +1046,7 @@ static int prim_setup(Scratch& s, int precision, const float* w, int ci, int co,
   DG_TRY(dev_alloc(s.pool, (void**)&dev, sizeof(PackDesc)));
   DG_CUDA(cudaMemcpyAsync(dev, &d, sizeof(d), cudaMemcpyHostToDevice, st));
   DG_CUDA(cudaStreamSynchronize(st));
-  DG_TRY(pack_weights(w, *pk, dev, 1, ci * co * 9, st));
+  DG_TRY(pack_weights(w, *pk, nullptr, dev, 1, ci * co * 9, st));
   if (pk_u) {
     *pk_u = nullptr;
     const int oci = dgrad ? co : ci, oco = dgrad ? ci : co;

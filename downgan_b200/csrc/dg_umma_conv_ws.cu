@@ -57,6 +57,7 @@ struct WsArgs {
   int perm;       // 1: PixelShuffle store, weight rows staged (i,j)-major
   int Fsh;        // channels after the shuffle (Co/4) when perm
   unsigned tile_tx;  // bytes one tile's TMA loads deliver
+  unsigned over;     // tail pad: bytes the last M-tile's rows may read past the last box region
   unsigned long long* trace;  // debug timeline (DG_WS_TRACE=1), null otherwise
 };
 
@@ -476,41 +477,45 @@ bool plan_ws(const ConvOp& op, WsArgs& a, int& ctas_per_sm) {
   const int hrows = (mode == S1) ? 2 : 1;
   const int Cb = std::min(op.Ci, 64), nblk = op.Ci / Cb;
   if (PW * ((mode == S2_FWD) ? 2 : 1) > 256) return false;  // TMA box extent (traversal) per dimension
-  int NT = 0;
+  // joint choice of the output-channel chunk NT (weights staged per CTA), CTAs per SM and tile height:
+  // minimise (waves of tiles per CTA) x (bytes staged + accumulator rows drained + fixed cost).  A TMA box
+  // region holds exactly its (rows x PW) positions; the MMA rows of the last M-tile may read past it (into
+  // the next region / the weights / a tail pad) - those rows are discarded in the epilogue.
+  double best = 1e300;
+  int bestTH = 0, best_mt = 0, best_stage = 0, best_cps = 1, NT = 0;
+  size_t best_over = 0;
   for (int cand : {256, 128, 64, 32, 16}) {
     if (cand > op.Co || op.Co % cand) continue;
-    if ((size_t)9 * op.Ci * cand * 2 > 80 * 1024) continue;
     if (ncls * cand > 256) continue;
-    NT = cand;
-    break;
-  }
-  if (NT == 0) return false;
-  const size_t wbytes = (size_t)9 * op.Ci * NT * 2;
-  const int n_chunks = op.Co / NT;
-  // tile height: minimise (waves of tiles per CTA) x (bytes staged + accumulator rows drained + fixed cost);
-  // two co-resident CTAs per SM (8 epilogue warps) when their rings and accumulators fit side by side
-  double best = 1e300;
-  int bestTH = 0, best_mt = 0, best_stage = 0, best_cps = 1;
-  for (int cps = 2; cps >= 1; --cps) {
-    const size_t budget = ((cps == 2) ? (size_t)(113 * 1024 - 2048) : (size_t)WS_MAX_SMEM) - 1024;
-    const int acc_max = (cps == 2) ? 128 : 256;
-    for (int TH = 1; TH <= Ht; ++TH) {
-      const int span = TH * PW - (PW - Wt);
-      const int n_mt = (span + 127) / 128;
-      if (n_mt > 8 || n_mt * ncls * NT > acc_max) break;
-      const size_t reg_b = (((size_t)(n_mt * 128 + halo) * Cb * 2) + 1023) & ~(size_t)1023;
-      const size_t tile_b = (size_t)nsub * nblk * reg_b;
-      if (wbytes + 2 * tile_b > budget) break;
-      if ((TH + hrows) * ((mode == S2_FWD) ? 2 : 1) > 256) break;  // TMA box extent (traversal) per dimension
-      int stages = (int)std::min<size_t>(WS_MAX_STAGE, (budget - wbytes) / tile_b);
-      const int ntiles = (Ht + TH - 1) / TH;
-      const long long tiles_total = (long long)ntiles * op.B;
-      const int G = std::max(1, (148 * cps) / n_chunks);
-      const double waves = (double)((tiles_total + G - 1) / G);
-      const double in_b = (double)(TH + hrows) * PW * nsub * op.Ci * 2.0;
-      const double out_b = (double)n_mt * 128 * ncls * NT * 2.0;
-      const double cost = waves * cps * (in_b + out_b + 6144.0) * (cps == 2 ? 0.85 : 1.0) * (stages >= 3 ? 1.0 : 1.15);
-      if (cost < best - 1e-9) { best = cost; bestTH = TH; best_mt = n_mt; best_stage = stages; best_cps = cps; }
+    const size_t wbytes = (size_t)9 * op.Ci * cand * 2;
+    if (wbytes > 112 * 1024) continue;
+    const int n_chunks = op.Co / cand;
+    for (int cps = 2; cps >= 1; --cps) {
+      const size_t budget = ((cps == 2) ? (size_t)(113 * 1024 - 2048) : (size_t)WS_MAX_SMEM) - 1024;
+      const int acc_max = (cps == 2) ? 128 : 256;
+      for (int TH = 1; TH <= Ht; ++TH) {
+        const int span = TH * PW - (PW - Wt);
+        const int n_mt = (span + 127) / 128;
+        if (n_mt > 8 || n_mt * ncls * cand > acc_max) break;
+        if ((TH + hrows) * ((mode == S2_FWD) ? 2 : 1) > 256) break;  // TMA box extent (traversal) per dimension
+        const size_t box_pos = (size_t)(TH + hrows) * PW;
+        const size_t reg_b = ((box_pos * Cb * 2) + 1023) & ~(size_t)1023;
+        const size_t tile_b = (size_t)nsub * nblk * reg_b;
+        const size_t need_pos = (size_t)n_mt * 128 + halo;
+        const size_t over = need_pos * Cb * 2 > reg_b ? need_pos * Cb * 2 - reg_b : 0;
+        if (wbytes + over + 2 * tile_b > budget) break;
+        const int stages = (int)std::min<size_t>(WS_MAX_STAGE, (budget - wbytes - over) / tile_b);
+        const int ntiles = (Ht + TH - 1) / TH;
+        const long long tiles_total = (long long)ntiles * op.B;
+        const int G = std::max(1, (148 * cps) / n_chunks);
+        const double waves = (double)((tiles_total + G - 1) / G);
+        const double in_b = (double)(TH + hrows) * PW * nsub * op.Ci * 2.0;
+        const double out_b = (double)n_mt * 128 * ncls * cand * 2.0;
+        const double cost = waves * cps * (in_b + out_b + 6144.0) * (cps == 2 ? 0.85 : 1.0) * (stages >= 3 ? 1.0 : 1.15);
+        if (cost < best - 1e-9) {
+          best = cost; bestTH = TH; best_mt = n_mt; best_stage = stages; best_cps = cps; NT = cand; best_over = over;
+        }
+      }
     }
   }
   if (bestTH == 0) return false;
@@ -518,7 +523,8 @@ bool plan_ws(const ConvOp& op, WsArgs& a, int& ctas_per_sm) {
   a.mode = mode; a.Ht = Ht; a.Wt = Wt;
   a.TH = bestTH; a.PW = PW; a.n_mt = best_mt; a.NT = NT; a.nplanes = nplanes; a.nsub = nsub;
   a.CoP = round_up(op.Co, 16);
-  a.RB = (int)((((size_t)(best_mt * 128 + halo) * Cb * 2) + 1023) & ~(size_t)1023);
+  a.RB = (int)((((size_t)(bestTH + hrows) * PW * Cb * 2) + 1023) & ~(size_t)1023);
+  a.over = (unsigned)best_over;
   a.nblk = nblk; a.Cb = Cb;
   a.tiles_per_img = (Ht + bestTH - 1) / bestTH;
   a.acc_cols = best_mt * ncls * NT;
@@ -587,7 +593,7 @@ int conv_umma_ws(const ConvOp& op, cudaStream_t st) {
   WsArgs a;
   int cps = 1;
   if (!plan_ws(op, a, cps)) { set_error("conv_umma_ws: unsupported shape"); return DG_ERR_INVALID; }
-  const size_t smem = (size_t)a.w_off + (size_t)9 * op.Ci * a.NT * 2 + 1024;
+  const size_t smem = (size_t)a.w_off + (size_t)9 * op.Ci * a.NT * 2 + a.over + 1024;
   const long long total = (long long)op.B * op.Hout * op.Wout;
   const double taps = op.transposed ? 2.25 : 9.0;
   Prof prof(PC_CONV_UMMA, 2.0 * total * op.Co * op.Ci * taps,
@@ -599,6 +605,10 @@ int conv_umma_ws(const ConvOp& op, cudaStream_t st) {
   const int per = (a.tiles_total + gx - 1) / gx;
   gx = (a.tiles_total + per - 1) / per;
   const dim3 grid(gx, n_chunks);
+  static const bool show_plan = getenv("DG_WS_PLAN") != nullptr;
+  if (show_plan)
+    fprintf(stderr, "[ws plan] mode %d Ci %d Co %d H %d B %d shuffle %d: TH %d n_mt %d NT %d stages %d cps %d grid %d x %d tiles %d smem %zu\n",
+            a.mode, op.Ci, op.Co, op.Hout, op.B, op.shuffle, a.TH, a.n_mt, a.NT, a.nstage, cps, gx, n_chunks, a.tiles_total, smem);
   CUtensorMap tmap;
   DG_TRY(get_map(op, a, &tmap));
   static const bool tracing = getenv("DG_WS_TRACE") != nullptr;
