@@ -237,11 +237,13 @@ def main():
                 tr.last_critic.cpu()  # D2H of the step's loss scalars (synchronises, as a logging caller would)
 
     def timed(steps, batches, read_scalars):
+        # the public epoch loop on DEVICE-resident batches (schedule + look-ahead generator forward included)
+        tr.num_steps = 0
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.dg_launch_count()
         e0.record()
-        run(steps, batches, read_scalars)
+        tr._train_epoch([batches[s % NBATCH] for s in range(steps)])
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -252,6 +254,8 @@ def main():
 
     # warm-up (also creates the native handles and workspaces)
     run(args.warmup, devb, False)
+    tr.num_steps = 0
+    tr._train_epoch([devb[s % NBATCH] for s in range(max(args.warmup, 6))])
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:

@@ -99,6 +99,7 @@ class WassersteinGAN:
         self.last_generator: Optional[torch.Tensor] = None  # 8 floats on device, see GENERATOR_SCALARS
         self._c_scal = None
         self._g_scal = None
+        self.lookahead = True  # _train_epoch computes the fakes of the critic steps between two generator updates in one pass
 
     # ---- helpers -------------------------------------------------------------
     @property
@@ -124,8 +125,9 @@ class WassersteinGAN:
         return dp.allreduce_sum_(grads)
 
     # ---- iterations ------------------------------------------------------------
-    def _critic_train_iteration(self, coarse, fine, alpha: Optional[torch.Tensor] = None):
-        """One critic update (wasserstein.py:27-55)."""
+    def _critic_train_iteration(self, coarse, fine, alpha: Optional[torch.Tensor] = None, _fake_offset: Optional[int] = None):
+        """One critic update (wasserstein.py:27-55).  `_fake_offset` (set by `_train_epoch`'s look-ahead) takes
+        fake = G(coarse) from the generator's look-ahead buffer instead of recomputing it."""
         coarse, fine = self._prep(coarse), self._prep(fine)
         b = coarse.shape[0]
         with torch.cuda.device(self.device):
@@ -137,11 +139,26 @@ class WassersteinGAN:
                 self._c_scal = torch.zeros(8, device=self.device)
             grads = self.C.flat_grads()
             hyp = self._hyper()
-            _lib.check(_lib.load().dg_critic_step(g, c, hyp, coarse.data_ptr(), fine.data_ptr(), alpha.data_ptr(), b,
-                                                  grads.data_ptr(), self._c_scal.data_ptr(), _lib.stream_ptr()))
+            if _fake_offset is None:
+                _lib.check(_lib.load().dg_critic_step(g, c, hyp, coarse.data_ptr(), fine.data_ptr(), alpha.data_ptr(), b,
+                                                      grads.data_ptr(), self._c_scal.data_ptr(), _lib.stream_ptr()))
+            else:
+                _lib.check(_lib.load().dg_critic_step_fake(g, c, hyp, int(_fake_offset), fine.data_ptr(), alpha.data_ptr(),
+                                                           b, grads.data_ptr(), self._c_scal.data_ptr(),
+                                                           _lib.stream_ptr()))
             scale = self._allreduce(grads)
             self._c_adam.step(grads, scale)
         self.last_critic = self._c_scal
+
+    def _generator_lookahead(self, coarse_all: torch.Tensor) -> None:
+        """fake = G(coarse) for several upcoming critic batches in one pass (same generator weights: the
+        generator is only updated every `critic_iterations` steps, wasserstein.py:136-137)."""
+        coarse_all = self._prep(coarse_all)
+        total, _, h, _ = coarse_all.shape
+        with torch.cuda.device(self.device):
+            g = self.G.native(h, total)
+            self.G.ensure_packed(g)
+            _lib.check(_lib.load().dg_generator_lookahead(g, coarse_all.data_ptr(), total, _lib.stream_ptr()))
 
     def _generator_train_iteration(self, coarse, fine):
         """One generator update (wasserstein.py:58-83)."""
@@ -194,15 +211,14 @@ class WassersteinGAN:
                 self._copy_stream = torch.cuda.Stream(device=dev)
             main = torch.cuda.current_stream()
 
-            # three fixed staging slots reused round-robin: no allocation (hence no implicit device
-            # synchronisation) in the steady state; a slot is rewritten only after the step that read it
-            if getattr(self, "_slots", None) is None:
-                self._slots = [{"bufs": None, "done": None} for _ in range(3)]
+            # fixed staging slots reused round-robin: no allocation (hence no implicit device synchronisation)
+            # in the steady state; a slot is rewritten only after the step that read it
+            n_critic = int(hp.critic_iterations)
+            if getattr(self, "_slots", None) is None or len(self._slots) != n_critic + 3:
+                self._slots = [{"bufs": None, "done": None} for _ in range(n_critic + 3)]
             self._slot_i = getattr(self, "_slot_i", 0)
 
             def stage(data):
-                if data is None:
-                    return None
                 slot = self._slots[self._slot_i % len(self._slots)]
                 self._slot_i += 1
                 src = list(data[:3])
@@ -220,16 +236,41 @@ class WassersteinGAN:
                 return slot, ev
 
             it = iter(dataloader)
-            nxt = stage(next(it, None))
+            pending = []  # staged batches, oldest first
+
+            def fill(n):
+                while len(pending) < n:
+                    data = next(it, None)
+                    if data is None:
+                        return
+                    pending.append(stage(data))
+
+            fill(2)
+            offsets = []  # look-ahead: sample offsets of the fakes of the next critic steps
             logs = []
-            while nxt is not None:
-                (slot, ev), nxt = nxt, stage(next(it, None))
+            while pending:
+                s = self.num_steps
+                if getattr(self, "lookahead", True) and not offsets and n_critic > 1 and s % n_critic != 0:
+                    # steps s .. next multiple of n_critic all see the current generator weights
+                    fill(n_critic - (s % n_critic) + 1)
+                    group = pending[:n_critic - (s % n_critic) + 1]
+                    if len(group) > 1:
+                        for _, ev in group:
+                            main.wait_event(ev)
+                        coarse_all = torch.cat([sl["bufs"][0] for sl, _ in group], dim=0)
+                        self._generator_lookahead(coarse_all)
+                        off = 0
+                        for sl, _ in group:
+                            offsets.append(off)
+                            off += sl["bufs"][0].shape[0]
+                slot, ev = pending.pop(0)
+                fill(2)
                 main.wait_event(ev)
                 ts = slot["bufs"]
                 coarse, fine = ts[0], ts[1]
                 alpha = ts[2] if len(ts) > 2 else None
-                self._critic_train_iteration(coarse, fine, alpha)
-                if self.num_steps % hp.critic_iterations == 0:
+                self._critic_train_iteration(coarse, fine, alpha, _fake_offset=offsets.pop(0) if offsets else None)
+                if self.num_steps % n_critic == 0:
                     self._generator_train_iteration(coarse, fine)
                 self.num_steps += 1
                 slot["done"] = torch.cuda.Event()

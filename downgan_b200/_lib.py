@@ -66,6 +66,8 @@ _SIGNATURES = {
                                C.c_int, C.c_float, _P]),
     "dg_critic_step": (C.c_int, [_P, _P, C.POINTER(Hyper), _P, _P, _P, C.c_int, _P, _P, _P]),
     "dg_generator_step": (C.c_int, [_P, _P, C.POINTER(Hyper), _P, _P, C.c_int, _P, _P, _P]),
+    "dg_generator_lookahead": (C.c_int, [_P, _P, C.c_int, _P]),
+    "dg_critic_step_fake": (C.c_int, [_P, _P, C.POINTER(Hyper), C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     "dg_conv3x3_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_float, C.c_int, _P]),
     "dg_conv3x3_dgrad": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
@@ -93,6 +95,10 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    # DG_TUNE="key=value,...": kernel-selection switches for A/B measurements (dg_set_tuning)
+    for kv in filter(None, os.environ.get("DG_TUNE", "").split(",")):
+        k, v = kv.split("=")
+        lib.dg_set_tuning(int(k), int(v))
     _lib = lib
     return lib
 

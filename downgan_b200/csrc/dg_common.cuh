@@ -1,5 +1,6 @@
 // Shared declarations for libdowngan_b200.so (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -69,6 +70,12 @@ struct Prof {
   Prof(int cls, double flops, double bytes, cudaStream_t s);
   ~Prof();
 };
+
+// cuTensorMapEncodeTiled resolved through the runtime (cudaGetDriverEntryPoint): the library does not link
+// libcuda, so it still loads (symbol check, host logic) on a machine without a driver.
+CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank, void* addr, const cuuint64_t* dims,
+                      const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapInterleave il,
+                      CUtensorMapSwizzle sw, CUtensorMapL2promotion l2, CUtensorMapFloatOOBfill oob);
 
 // ---- tensor views ---------------------------------------------------------
 // NHWC activation view: element (n,y,x,c) lives at p[((n*H + y)*W + x)*pitch + coff + c].
@@ -162,6 +169,8 @@ int fc_fwd(const void* x, int x_bf, const float* w, const float* bias, float* y,
 int fc_dgrad(const float* dz, const float* w, void* dx, int dx_bf, int NB, int K, int N,
              const void* mask, int mask_bf, float slope, cudaStream_t st);  // dx = (dz W) * lrelu'(mask)
 int fc_wgrad(const float* dz, const void* x, int x_bf, float* dw, int NB, int K, int N, cudaStream_t st);  // dw += dz^T x
+int critic_small_grads(const float* dz9, const float* seed, const float* a9, const float* vfc, int n0, int nv, int N, float* d_fc1b,
+                       float* d_fc2w, float* d_fc2b, cudaStream_t st);
 int fc2_fwd(const float* a, const float* w, const float* bias, float* s, int NB, int K, cudaStream_t st);
 int fc2_seed(const float* a9, const float* w2, const float* seed, float* dz9, int NB, int K, float slope, cudaStream_t st);
 

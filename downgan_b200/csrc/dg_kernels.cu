@@ -5,6 +5,8 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "dg_common.cuh"
 
 namespace dg {
@@ -541,7 +543,79 @@ int fill(float* p, float v, long long n, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 // critic classifier (critic.py:94-99)
 // ---------------------------------------------------------------------------
-// y[b][j] = act(sum_k x[b][k] w[j][k] + bias[j]); one warp per (b, j)
+// y[b][j] = act(sum_k x[b][k] w[j][k] + bias[j]).  Split-K tiled GEMM on CUDA cores (0.3 GFLOP at cfg-2: the
+// bound is re-reading x and w, so a block keeps a 32-sample x 104-unit tile over its K chunk in registers,
+// operands staged through shared memory) + a tiny finish kernel for bias / activation.
+constexpr int FCF_BM = 32, FCF_BN = 104, FCF_BK = 32, FCF_WP = FCF_BK + 4;  // w tile row pitch (floats): 16-byte rows, conflict-free
+__device__ __forceinline__ void fc_cp16(void* dst, const void* src, bool ok) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(ok ? 16 : 0) : "memory");
+}
+// K % 8 == 0 and kchunk % 32 == 0 (checked by the host): 16-byte cp.async chunks, double-buffered k-tiles
+template <bool XBF>
+__global__ void __launch_bounds__(256) fc_fwd_tiled_kernel(const void* __restrict__ x, const float* __restrict__ w,
+                                                            float* __restrict__ y, int NB, int K, int N, int kchunk) {
+  __shared__ __align__(16) float ws[2][FCF_BN][FCF_WP];
+  __shared__ __align__(16) unsigned char xs_raw[2][FCF_BM * FCF_BK * (XBF ? 2 : 4)];
+  const int b0 = blockIdx.x * FCF_BM;
+  const int k_begin = blockIdx.y * kchunk, k_end = min(K, k_begin + kchunk);
+  const int tb = threadIdx.x >> 3, tj = threadIdx.x & 7;
+  const int ntiles = (k_end - k_begin + FCF_BK - 1) / FCF_BK;
+  constexpr int XE = XBF ? 8 : 4;              // x elements per 16-byte chunk
+  constexpr int XCH = FCF_BM * FCF_BK / XE;    // x chunks per tile
+  auto stage = [&](int t, int buf) {
+    const int k0 = k_begin + t * FCF_BK;
+    for (int i = threadIdx.x; i < XCH; i += 256) {
+      const int r = i / (FCF_BK / XE), c = (i - r * (FCF_BK / XE)) * XE;
+      const bool ok = (b0 + r < NB) && (k0 + c < k_end);
+      const size_t off = ok ? (size_t)(b0 + r) * K + k0 + c : 0;
+      fc_cp16(xs_raw[buf] + (size_t)(r * FCF_BK + c) * (XBF ? 2 : 4), (const char*)x + off * (XBF ? 2 : 4), ok);
+    }
+    for (int i = threadIdx.x; i < FCF_BN * (FCF_BK / 4); i += 256) {
+      const int r = i >> 3, c = (i & 7) * 4;
+      const bool ok = (r < N) && (k0 + c < k_end);
+      fc_cp16(&ws[buf][r][c], w + (ok ? (size_t)r * K + k0 + c : 0), ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float acc[FCF_BN / 8];
+#pragma unroll
+  for (int i = 0; i < FCF_BN / 8; ++i) acc[i] = 0.f;
+  if (ntiles > 0) stage(0, 0);
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < ntiles) { stage(t + 1, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < FCF_BK; ++c) {
+      float xv;
+      if (XBF) xv = __bfloat162float(reinterpret_cast<const bf16*>(xs_raw[buf])[tb * FCF_BK + c]);
+      else xv = reinterpret_cast<const float*>(xs_raw[buf])[tb * FCF_BK + c];
+#pragma unroll
+      for (int i = 0; i < FCF_BN / 8; ++i) acc[i] = fmaf(xv, ws[buf][tj + 8 * i][c], acc[i]);
+    }
+    __syncthreads();
+  }
+  if (b0 + tb < NB) {
+#pragma unroll
+    for (int i = 0; i < FCF_BN / 8; ++i) {
+      const int j = tj + 8 * i;
+      if (j < N) atomicAdd(&y[(size_t)(b0 + tb) * N + j], acc[i]);
+    }
+  }
+}
+__global__ void fc_finish_kernel(float* __restrict__ y, const float* __restrict__ bias, int NB, int N, int act, float slope,
+                                 const float* __restrict__ mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NB * N) return;
+  float s = y[i];
+  if (bias) s += bias[i % N];
+  if (act == ACT_LRELU) s = s > 0.f ? s : s * slope;
+  else if (act == ACT_MASK) s *= lrelu_d(mask[i], slope);
+  y[i] = s;
+}
+// fallback for wide layers (N > 104): one warp per (b, j)
 __global__ void fc_fwd_kernel(const void* __restrict__ x, int x_bf, const float* __restrict__ w,
                               const float* __restrict__ bias, float* __restrict__ y, int NB, int K, int N, int act,
                               float slope, const float* __restrict__ mask) {
@@ -560,48 +634,158 @@ __global__ void fc_fwd_kernel(const void* __restrict__ x, int x_bf, const float*
 }
 int fc_fwd(const void* x, int x_bf, const float* w, const float* bias, float* y, int NB, int K, int N, int act,
            float slope, const float* mask, cudaStream_t st) {
-  const long long threads = (long long)NB * N * 32;
   Prof prof(PC_FC, 2.0 * NB * N * K, (double)N * K * 4.0 + (double)NB * K * (x_bf ? 2 : 4), st);
-  fc_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, x_bf, w, bias, y, NB, K, N, act, slope, mask);
+  if (N > FCF_BN || K % 8) {
+    const long long threads = (long long)NB * N * 32;
+    fc_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, x_bf, w, bias, y, NB, K, N, act, slope, mask);
+    DG_LAUNCH_CHECK();
+    return 0;
+  }
+  const int nbt = (NB + FCF_BM - 1) / FCF_BM;
+  int splits = (296 + nbt - 1) / nbt;
+  splits = std::max(1, std::min(splits, (K + 63) / 64));
+  const int kchunk = ((K + splits - 1) / splits + FCF_BK - 1) / FCF_BK * FCF_BK;
+  splits = (K + kchunk - 1) / kchunk;
+  DG_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)NB * N, st));
+  if (x_bf) fc_fwd_tiled_kernel<true><<<dim3(nbt, splits), 256, 0, st>>>(x, w, y, NB, K, N, kchunk);
+  else fc_fwd_tiled_kernel<false><<<dim3(nbt, splits), 256, 0, st>>>(x, w, y, NB, K, N, kchunk);
+  DG_LAUNCH_CHECK();
+  fc_finish_kernel<<<(NB * N + 255) / 256, 256, 0, st>>>(y, bias, NB, N, act, slope, mask);
   DG_LAUNCH_CHECK();
   return 0;
 }
 
-// dx[b][k] = (sum_j dz[b][j] w[j][k]) * lrelu'(mask[b][k])
-__global__ void fc_dgrad_kernel(const float* __restrict__ dz, const float* __restrict__ w, void* __restrict__ dx,
-                                int dx_bf, int K, int N, const void* __restrict__ mask, int mask_bf, float slope) {
-  extern __shared__ float sdz[];
-  const int b = blockIdx.y;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) sdz[j] = dz[(size_t)b * N + j];
+// dx[b][k] = (sum_j dz[b][j] w[j][k]) * lrelu'(mask[b][k]); a thread owns one k for 16 samples (w read once per 16)
+constexpr int FCD_BB = 16;
+__global__ void __launch_bounds__(256) fc_dgrad_kernel(const float* __restrict__ dz, const float* __restrict__ w, void* __restrict__ dx,
+                                                        int dx_bf, int NB, int K, int N, const void* __restrict__ mask, int mask_bf,
+                                                        float slope) {
+  extern __shared__ __align__(16) float sdz[];  // [N][FCD_BB]
+  const int b0 = blockIdx.y * FCD_BB;
+  for (int i = threadIdx.x; i < N * FCD_BB; i += blockDim.x) {
+    const int j = i / FCD_BB, bb = i - j * FCD_BB;
+    sdz[i] = (b0 + bb < NB) ? dz[(size_t)(b0 + bb) * N + j] : 0.f;
+  }
   __syncthreads();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
-  float s = 0.f;
-  for (int j = 0; j < N; ++j) s = fmaf(sdz[j], w[(size_t)j * K + k], s);
-  if (mask) s *= lrelu_d(ldv(mask, mask_bf, (size_t)b * K + k), slope);
-  stv(dx, dx_bf, (size_t)b * K + k, s);
+  float acc[FCD_BB];
+#pragma unroll
+  for (int i = 0; i < FCD_BB; ++i) acc[i] = 0.f;
+  for (int j = 0; j < N; ++j) {
+    const float wv = w[(size_t)j * K + k];
+    const float4* p = reinterpret_cast<const float4*>(sdz + j * FCD_BB);
+#pragma unroll
+    for (int q = 0; q < FCD_BB / 4; ++q) {
+      const float4 d = p[q];
+      acc[4 * q] = fmaf(d.x, wv, acc[4 * q]);
+      acc[4 * q + 1] = fmaf(d.y, wv, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(d.z, wv, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(d.w, wv, acc[4 * q + 3]);
+    }
+  }
+#pragma unroll
+  for (int bb = 0; bb < FCD_BB; ++bb) {
+    if (b0 + bb >= NB) break;
+    float s = acc[bb];
+    const size_t o = (size_t)(b0 + bb) * K + k;
+    if (mask) s *= lrelu_d(ldv(mask, mask_bf, o), slope);
+    stv(dx, dx_bf, o, s);
+  }
 }
 int fc_dgrad(const float* dz, const float* w, void* dx, int dx_bf, int NB, int K, int N, const void* mask, int mask_bf,
              float slope, cudaStream_t st) {
   Prof prof(PC_FC, 2.0 * NB * N * K, (double)N * K * 4.0 + (double)NB * K * (dx_bf ? 2 : 4), st);
-  fc_dgrad_kernel<<<dim3((K + 255) / 256, NB), 256, N * sizeof(float), st>>>(dz, w, dx, dx_bf, K, N, mask, mask_bf, slope);
+  fc_dgrad_kernel<<<dim3((K + 255) / 256, (NB + FCD_BB - 1) / FCD_BB), 256, N * FCD_BB * sizeof(float), st>>>(
+      dz, w, dx, dx_bf, NB, K, N, mask, mask_bf, slope);
   DG_LAUNCH_CHECK();
   return 0;
 }
 
-// dw[j][k] += sum_b dz[b][j] x[b][k]
-__global__ void fc_wgrad_kernel(const float* __restrict__ dz, const void* __restrict__ x, int x_bf,
-                                float* __restrict__ dw, int NB, int K, int N) {
+// dw[j][k] += sum_b dz[b][j] x[b][k]; a thread owns one k for 10 output units (x read once per 10)
+constexpr int FCW_BJ = 10, FCW_MAXB = 1024;
+__global__ void __launch_bounds__(256) fc_wgrad_kernel(const float* __restrict__ dz, const void* __restrict__ x, int x_bf,
+                                                        float* __restrict__ dw, int NB, int K, int N) {
+  extern __shared__ __align__(16) float sdz[];  // [NB][FCW_BJ]
+  const int j0 = blockIdx.y * FCW_BJ;
+  for (int i = threadIdx.x; i < NB * FCW_BJ; i += blockDim.x) {
+    const int b = i / FCW_BJ, jj = i - b * FCW_BJ;
+    sdz[i] = (j0 + jj < N) ? dz[(size_t)b * N + j0 + jj] : 0.f;
+  }
+  __syncthreads();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y;
   if (k >= K) return;
-  float s = 0.f;
-  for (int b = 0; b < NB; ++b) s = fmaf(dz[(size_t)b * N + j], ldv(x, x_bf, (size_t)b * K + k), s);
-  dw[(size_t)j * K + k] += s;
+  float acc[FCW_BJ];
+#pragma unroll
+  for (int i = 0; i < FCW_BJ; ++i) acc[i] = 0.f;
+  int b = 0;
+  for (; b + 3 < NB; b += 4) {
+    float xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) xv[u] = ldv(x, x_bf, (size_t)(b + u) * K + k);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int jj = 0; jj < FCW_BJ; ++jj) acc[jj] = fmaf(sdz[(b + u) * FCW_BJ + jj], xv[u], acc[jj]);
+  }
+  for (; b < NB; ++b) {
+    const float xv = ldv(x, x_bf, (size_t)b * K + k);
+#pragma unroll
+    for (int jj = 0; jj < FCW_BJ; ++jj) acc[jj] = fmaf(sdz[b * FCW_BJ + jj], xv, acc[jj]);
+  }
+#pragma unroll
+  for (int jj = 0; jj < FCW_BJ; ++jj)
+    if (j0 + jj < N) dw[(size_t)(j0 + jj) * K + k] += acc[jj];
 }
 int fc_wgrad(const float* dz, const void* x, int x_bf, float* dw, int NB, int K, int N, cudaStream_t st) {
+  DG_CHECK(NB <= FCW_MAXB, "fc_wgrad: batch %d > %d", NB, FCW_MAXB);
   Prof prof(PC_FC, 2.0 * NB * N * K, (double)N * K * 8.0 + (double)NB * K * (x_bf ? 2 : 4), st);
-  fc_wgrad_kernel<<<dim3((K + 255) / 256, N), 256, 0, st>>>(dz, x, x_bf, dw, NB, K, N);
+  fc_wgrad_kernel<<<dim3((K + 255) / 256, (N + FCW_BJ - 1) / FCW_BJ), 256, (size_t)NB * FCW_BJ * sizeof(float), st>>>(dz, x, x_bf, dw,
+                                                                                                                   NB, K, N);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+// The small classifier gradients of the fused critic step in ONE launch (fp64 partial sums: the bias gradients
+// are sums of cancelling real/fake halves):
+//   d_fc1b[j] += sum_{b<n0} dz9[b][j];   d_fc2w[j] += sum_{b<n0} seed[b]*a9[b][j] + sum_{b<nv} vfc[b][j];
+//   d_fc2b    += sum_{b<n0} seed[b]
+__global__ void __launch_bounds__(256) critic_small_grads_kernel(const float* __restrict__ dz9, const float* __restrict__ seed,
+                                                                  const float* __restrict__ a9, const float* __restrict__ vfc, int n0,
+                                                                  int nv, int N, float* __restrict__ d_fc1b, float* __restrict__ d_fc2w,
+                                                                  float* __restrict__ d_fc2b) {
+  __shared__ double sh[3][8][32];
+  const int jl = threadIdx.x & 31, g = threadIdx.x >> 5, j = blockIdx.x * 32 + jl;
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (j < N) {
+    for (int b = g; b < n0; b += 8) {
+      s1 += (double)dz9[(size_t)b * N + j];
+      s2 += (double)seed[b] * (double)a9[(size_t)b * N + j];
+    }
+    for (int b = g; b < nv; b += 8) s2 += (double)vfc[(size_t)b * N + j];
+  }
+  if (blockIdx.x == 0)
+    for (int b = threadIdx.x; b < n0; b += 256) s3 += (double)seed[b];
+  sh[0][g][jl] = s1; sh[1][g][jl] = s2; sh[2][g][jl] = s3;
+  __syncthreads();
+  if (g == 0) {
+    double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { t1 += sh[0][q][jl]; t2 += sh[1][q][jl]; }
+    if (j < N) { d_fc1b[j] += (float)t1; d_fc2w[j] += (float)t2; }
+    if (blockIdx.x == 0) {
+      double t3 = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t3 += sh[2][q][jl];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t3 += __shfl_xor_sync(0xffffffffu, t3, o);
+      if (jl == 0) d_fc2b[0] += (float)t3;
+    }
+  }
+}
+int critic_small_grads(const float* dz9, const float* seed, const float* a9, const float* vfc, int n0, int nv, int N, float* d_fc1b,
+                       float* d_fc2w, float* d_fc2b, cudaStream_t st) {
+  critic_small_grads_kernel<<<(N + 31) / 32, 256, 0, st>>>(dz9, seed, a9, vfc, n0, nv, N, d_fc1b, d_fc2w, d_fc2b);
   DG_LAUNCH_CHECK();
   return 0;
 }
@@ -816,7 +1000,23 @@ extern "C" int dg_profile_report(double* out, int n_classes) {
   }
   return 0;
 }
-namespace dg { int g_tune[DG_TUNE_KEYS] = {1, 1, 1, 1, 1, 1, 1, 1}; }
+namespace dg {
+CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank, void* addr, const cuuint64_t* dims,
+                      const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapInterleave il,
+                      CUtensorMapSwizzle sw, CUtensorMapL2promotion l2, CUtensorMapFloatOOBfill oob) {
+  typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                         const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return CUDA_ERROR_NOT_FOUND;
+    fn = (Fn)p;
+  }
+  return fn(map, dt, rank, addr, dims, strides, box, estr, il, sw, l2, oob);
+}
+}  // namespace dg
+namespace dg { int g_tune[DG_TUNE_KEYS] = {1, 1, 1, 0, 1, 1, 1, 1}; }
 extern "C" int dg_set_tuning(int key, int value) {
   if (key < 0 || key >= DG_TUNE_KEYS) { dg::set_error("dg_set_tuning: unknown key %d", key); return DG_ERR_INVALID; }
   const int prev = dg::g_tune[key];

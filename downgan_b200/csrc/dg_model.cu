@@ -108,6 +108,7 @@ struct dg_generator {
   float* fine_nhwc = nullptr;
   float* l1 = nullptr;
   int saved_batch = 0;
+  int lookahead = 0;  // samples of g->fake produced by the last dg_generator_lookahead (0: none / overwritten)
 
   int idx_conv1() const { return 0; }
   int idx_db(int r, int d, int k) const { return 1 + (r * 3 + d) * 5 + (k - 1); }
@@ -404,6 +405,7 @@ extern "C" int dg_generator_fwd(dg_generator* g, const float* coarse, int batch,
   if (!g->packed) { set_error("dg_generator_fwd: dg_generator_pack has not been called"); return DG_ERR_STATE; }
   cudaStream_t st = (cudaStream_t)stream;
   DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), batch, g->Cin, g->Hc, g->Hc, st));
+  g->lookahead = 0;
   DG_TRY(gen_forward_internal(g, batch, save != 0, st));
   if (fake) DG_TRY(nhwc_to_nchw(tv(g->fake, 0, g->Cout), fake, batch, g->Cout, g->Hf, g->Hf, st));
   return 0;
@@ -874,12 +876,11 @@ static int critic_second_order_and_wgrads(dg_critic* c, int B, cudaStream_t st) 
   }
   // classifier: dW_fc1 over all 3B rows at once; v_fc and dW_fc2 as in critic_gp_second_order
   DG_TRY(fc_wgrad(c->dz9, c->a[8], c->bf, c->gpk + c->pk_fc1w, 3 * B, c->fc_in, FC_HIDDEN, st));
-  DG_TRY(colsum(tv(c->dz9, 0, FC_HIDDEN), (size_t)n0, FC_HIDDEN, c->gpk + c->pk_fc1b, st));
-  DG_TRY(fc_wgrad(c->seed, c->a9, 0, c->gpk + c->pk_fc2w, n0, FC_HIDDEN, 1, st));
-  DG_TRY(colsum(tv(c->seed, 0, 1), (size_t)n0, 1, c->gpk + c->pk_fc2b, st));
   DG_TRY(fc_fwd(v.p, c->bf, c->pk + c->pk_fc1w, nullptr, c->vfc, B, c->fc_in, FC_HIDDEN, ACT_MASK, C_SLOPE,
                 c->a9 + (size_t)n0 * FC_HIDDEN, st));
-  DG_TRY(colsum(tv(c->vfc, 0, FC_HIDDEN), (size_t)B, FC_HIDDEN, c->gpk + c->pk_fc2w, st));
+  // classifier.0.bias, classifier.2.weight (incl. the GP term sum_b v_fc) and classifier.2.bias in one launch
+  DG_TRY(critic_small_grads(c->dz9, c->seed, c->a9, c->vfc, n0, B, FC_HIDDEN, c->gpk + c->pk_fc1b, c->gpk + c->pk_fc2w,
+                            c->gpk + c->pk_fc2b, st));
   for (int i = 0; i < 8; ++i) {
     const Layer& l = c->L[i];
     WgradOp w;
@@ -954,7 +955,27 @@ __global__ void critic_seed_kernel(float* seed, int B) {
   if (i < 3 * B) seed[i] = i < B ? -1.f / B : (i < 2 * B ? 1.f / B : 1.f);
 }
 
-// _critic_train_iteration, wasserstein.py:35-52 (everything except C_optimizer.step()).
+// _critic_train_iteration, wasserstein.py:35-52 (everything except C_optimizer.step()), given fake = G(coarse)
+// as an NHWC fp32 tensor.
+static int critic_step_body(dg_generator* g, dg_critic* c, const dg_hyper* hp, const float* fake_nhwc, const float* fine,
+                            const float* alpha, int B, float* c_grads_flat, float* scalars, cudaStream_t st) {
+  // one 3B critic batch: [real ; fake ; alpha*real + (1-alpha)*fake]   (:37-38, :91-97)
+  DG_TRY(build_critic_input(fine, fake_nhwc, 0, alpha, c->a0, B, c->nc, c->Hf, c->Hf, 0, st));
+  DG_TRY(critic_forward_internal(c, 3 * B, st));
+  DG_TRY(critic_means(c->scores, B, scalars, st));
+  critic_seed_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(c->seed, B);
+  DG_LAUNCH_CHECK();
+  DG_TRY(critic_backward_chain(c, 3 * B, 2 * B, B, c->g, st));
+  DG_TRY(critic_gp_first_order(c, hp, 2 * B, B, scalars, 1, nullptr, st,
+                               c->a0 + (size_t)2 * B * c->Hf * c->Hf * c->nc));  // u overwrites the interpolates
+  DG_CUDA(cudaMemsetAsync(c->gpk, 0, sizeof(float) * c->pk_elems, st));
+  DG_TRY(critic_second_order_and_wgrads(c, B, st));
+  DG_TRY(unpack_wgrads(c->gpk, c_grads_flat, c->tab_fwd, c->n_fwd, c->max_fwd, st));
+  c->saved_batch = 0;
+  (void)g;
+  return 0;
+}
+
 extern "C" int dg_critic_step(dg_generator* g, dg_critic* c, const dg_hyper* hp, const float* coarse, const float* fine,
                               const float* alpha, int batch, float* c_grads_flat, float* scalars, void* stream) {
   DG_CHECK(g && c && hp && coarse && fine && alpha && c_grads_flat && scalars, "dg_critic_step: null argument");
@@ -968,20 +989,42 @@ extern "C" int dg_critic_step(dg_generator* g, dg_critic* c, const dg_hyper* hp,
   DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), B, g->Cin, g->Hc, g->Hc, st));
   DG_TRY(gen_forward_internal(g, B, false, st));
   g->saved_batch = 0;
-  // one 3B critic batch: [real ; fake ; alpha*real + (1-alpha)*fake]   (:37-38, :91-97)
-  DG_TRY(build_critic_input(fine, g->fake, 0, alpha, c->a0, B, c->nc, c->Hf, c->Hf, 0, st));
-  DG_TRY(critic_forward_internal(c, 3 * B, st));
-  DG_TRY(critic_means(c->scores, B, scalars, st));
-  critic_seed_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(c->seed, B);
-  DG_LAUNCH_CHECK();
-  DG_TRY(critic_backward_chain(c, 3 * B, 2 * B, B, c->g, st));
-  DG_TRY(critic_gp_first_order(c, hp, 2 * B, B, scalars, 1, nullptr, st,
-                               c->a0 + (size_t)2 * B * c->Hf * c->Hf * c->nc));  // u overwrites the interpolates
-  DG_CUDA(cudaMemsetAsync(c->gpk, 0, sizeof(float) * c->pk_elems, st));
-  DG_TRY(critic_second_order_and_wgrads(c, B, st));
-  DG_TRY(unpack_wgrads(c->gpk, c_grads_flat, c->tab_fwd, c->n_fwd, c->max_fwd, st));
-  c->saved_batch = 0;
+  g->lookahead = 0;
+  return critic_step_body(g, c, hp, g->fake, fine, alpha, B, c_grads_flat, scalars, st);
+}
+
+// Look-ahead generator forward: the critic iterations between two generator updates all see the SAME generator
+// weights (wasserstein.py:131-147), so fake = G(coarse) of the next `total` samples (several batches, concatenated)
+// is computed in one pass: the persistent trunk kernel then has one CTA per sample for ALL of them (a single batch
+// of 64 fills 64 of the 148 SMs).  The fakes stay in the generator's NHWC output buffer until the next
+// generator forward; dg_critic_step_fake consumes them by sample offset.
+extern "C" int dg_generator_lookahead(dg_generator* g, const float* coarse, int total, void* stream) {
+  DG_CHECK(g && coarse, "dg_generator_lookahead: null argument");
+  DG_CHECK(total >= 1 && total <= g->maxB, "dg_generator_lookahead: %d samples outside [1,%d]", total, g->maxB);
+  if (!g->packed) { set_error("dg_generator_lookahead: dg_generator_pack has not been called"); return DG_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), total, g->Cin, g->Hc, g->Hc, st));
+  DG_TRY(gen_forward_internal(g, total, false, st));
+  g->saved_batch = 0;
+  g->lookahead = total;
   return 0;
+}
+
+extern "C" int dg_critic_step_fake(dg_generator* g, dg_critic* c, const dg_hyper* hp, int fake_offset, const float* fine,
+                                   const float* alpha, int batch, float* c_grads_flat, float* scalars, void* stream) {
+  DG_CHECK(g && c && hp && fine && alpha && c_grads_flat && scalars, "dg_critic_step_fake: null argument");
+  DG_CHECK(batch >= 1 && batch <= c->maxB, "dg_critic_step_fake: batch %d too large", batch);
+  DG_CHECK(g->Hf == c->Hf && g->Cout == c->nc, "dg_critic_step_fake: generator output does not match critic input");
+  if (fake_offset < 0 || fake_offset + batch > g->lookahead) {
+    set_error("dg_critic_step_fake: samples [%d,%d) are not covered by the last dg_generator_lookahead (%d samples)", fake_offset,
+              fake_offset + batch, g->lookahead);
+    return DG_ERR_STATE;
+  }
+  if (!c->packed) { set_error("dg_critic_step_fake: weights not packed"); return DG_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(float), st));
+  const float* fake = g->fake + (size_t)fake_offset * g->Hf * g->Hf * g->Cout;
+  return critic_step_body(g, c, hp, fake, fine, alpha, batch, c_grads_flat, scalars, st);
 }
 
 // _generator_train_iteration, wasserstein.py:65-80 (everything except G_optimizer.step()).
@@ -996,6 +1039,7 @@ extern "C" int dg_generator_step(dg_generator* g, dg_critic* c, const dg_hyper* 
   const long long n = (long long)B * g->Hf * g->Hf * g->Cout;
   DG_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(float), st));
   DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), B, g->Cin, g->Hc, g->Hc, st));
+  g->lookahead = 0;
   DG_TRY(gen_forward_internal(g, B, true, st));
   // c_fake = C(fake); adversarial seed d(-gamma*mean)/dscore = -gamma/B
   DG_CUDA(cudaMemcpyAsync(c->a0, g->fake, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));

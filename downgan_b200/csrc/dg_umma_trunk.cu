@@ -10,6 +10,8 @@
 // of the previous layer).  Three warps issue the MMAs of the three M-tiles in parallel; the
 // accumulators (3 x 16 TMEM columns) are read back by all four warps.  With `db_bufs` set, every
 // slice is also stored to the per-block global concat buffers for the backward pass.
+#include <stdlib.h>
+
 #include "dg_umma.cuh"
 
 namespace dg {
@@ -38,8 +40,30 @@ struct TrunkArgs {
   const bf16* w;                            // slice-major B-operand images, 5 per dense block (pack_trunk_slices)
   const float* bias;                        // 16 floats per dense conv, consecutive
   int R, B;
+  int order;                                // MMA issue order, see trunk_issue_round
+  unsigned long long* trace;                // debug timeline (DG_TRUNK_TRACE), null otherwise
 };
 
+__device__ __forceinline__ unsigned long long gtimer_t() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TR_TRACE(ev)                                                                                   \
+  do {                                                                                                 \
+    if (a.trace && blockIdx.x == 0 && tid == 0 && L >= 30 && L < 62) a.trace[(L - 30) * 8 + (ev)] = gtimer_t(); \
+  } while (0)
+__device__ __forceinline__ uint32_t elect_one_sync_t() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred;
+}
 __device__ __forceinline__ void st_shared16(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -61,9 +85,61 @@ __device__ __forceinline__ void unpack8(uint4 q, float* v) {
   }
 }
 
+
+// MMA round of slice j for the three M-tiles.  order 0: warps 0..2 each issue their own M-tile (three
+// independent accumulate chains interleave in the tensor pipe); 1: one thread, M-tile after M-tile (M-tile 0
+// completes first); 2: one thread, tap-major (chains interleaved).  Every M-tile commits to its own mbarrier.
+__device__ __forceinline__ void trunk_issue_round(int order, int warp, uint32_t tmem, uint32_t sX, uint32_t wb, int j, int Nj,
+                                                  uint64_t* mbar) {
+  const uint32_t idj = instr_desc(128, Nj);
+  const uint32_t wplane = Nj * 16;
+  const uint64_t bd0 = smem_desc(wb, wplane, 128);
+  const uint32_t accf = (j > 0) ? 1u : 0u;
+  if (order == 0) {
+    if (warp < TNMT) {
+      if (elect_one_sync_t()) {
+        const uint64_t ad0 = smem_desc(sX + 2 * j * TPB + (warp * 128) * 16, TPB, 128);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+          umma_f16(tmem + warp * T_COLS_MT + j * TF, ad0 + (uint64_t)((tap / 3) * TPW + tap % 3), bd0 + (uint64_t)((tap * 2 * wplane) >> 4), idj,
+                   (tap > 0) ? 1u : accf);
+        umma_commit(smem_u32(&mbar[warp]));
+      }
+      __syncwarp();
+    }
+    return;
+  }
+  if (warp == 0) {
+    if (elect_one_sync_t()) {
+      if (order == 1) {
+#pragma unroll
+        for (int mt = 0; mt < TNMT; ++mt) {
+          const uint64_t ad0 = smem_desc(sX + 2 * j * TPB + (mt * 128) * 16, TPB, 128);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap)
+            umma_f16(tmem + mt * T_COLS_MT + j * TF, ad0 + (uint64_t)((tap / 3) * TPW + tap % 3), bd0 + (uint64_t)((tap * 2 * wplane) >> 4), idj,
+                     (tap > 0) ? 1u : accf);
+          umma_commit(smem_u32(&mbar[mt]));
+        }
+      } else {
+        const uint64_t ad0 = smem_desc(sX + 2 * j * TPB, TPB, 128);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+          for (int mt = 0; mt < TNMT; ++mt)
+            umma_f16(tmem + mt * T_COLS_MT + j * TF, ad0 + (uint64_t)(mt * 128 + (tap / 3) * TPW + tap % 3),
+                     bd0 + (uint64_t)((tap * 2 * wplane) >> 4), idj, (tap > 0) ? 1u : accf);
+#pragma unroll
+        for (int mt = 0; mt < TNMT; ++mt) umma_commit(smem_u32(&mbar[mt]));
+      }
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(128) trunk_fwd_kernel(const TrunkArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t mbar[TNMT];  // one per M-tile: its epilogue starts while the other tiles' MMAs run
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.x;
@@ -71,7 +147,7 @@ __global__ void __launch_bounds__(128) trunk_fwd_kernel(const TrunkArgs a) {
   const uint32_t sW = sX + T_X_BYTES;
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), T_TMEM_COLS);
-  if (tid == 32) mbar_init(smem_u32(&mbar), TNMT);
+  if (tid == 32) { for (int i = 0; i < TNMT; ++i) mbar_init(smem_u32(&mbar[i]), 1); }
   // zero the whole concat tile: halo ring and pad columns are the convolution's zero padding
   for (int i = tid; i < T_X_BYTES / 16; i += 128) st_shared16(sX + i * 16, make_uint4(0, 0, 0, 0));
   __syncthreads();
@@ -122,19 +198,9 @@ __global__ void __launch_bounds__(128) trunk_fwd_kernel(const TrunkArgs a) {
       }
     }
     // ---- MMA round of slice j: warp w issues M-tile w (9 taps, K = 16 channels, N = Nj)
-    if (warp < TNMT && lane == 0) {
-      const uint32_t idj = instr_desc(128, Nj);
-      const uint32_t wplane = Nj * 16;
-      for (int tap = 0; tap < 9; ++tap) {
-        const int dy = tap / 3, dx = tap - 3 * dy;
-        const uint32_t a0 = sX + 2 * j * TPB + (warp * 128 + dy * TPW + dx) * 16;
-        const uint32_t b0 = wb + tap * 2 * wplane;
-        umma_f16(tmem + warp * T_COLS_MT + j * TF, smem_desc(a0, TPB, 128), smem_desc(b0, wplane, 128), idj,
-                 (j > 0 || tap > 0) ? 1u : 0u);
-      }
-      umma_commit(smem_u32(&mbar));
-    }
-    __syncwarp();
+    TR_TRACE(0);
+    trunk_issue_round(a.order, warp, tmem, sX, wb, j, Nj, mbar);
+    TR_TRACE(1);
     // ---- prefetch the next slice's weights into the other buffer while the tensor pipe runs
     const size_t w_next = w_elem + (size_t)9 * TF * Nj;
     if (L + 1 < total) {
@@ -146,13 +212,14 @@ __global__ void __launch_bounds__(128) trunk_fwd_kernel(const TrunkArgs a) {
     float bias[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) bias[j] = __ldg(a.bias + (size_t)L * 16 + j);
-    mbar_wait(smem_u32(&mbar), L & 1);
-    tc_fence_after();
-    // ---- epilogue
+    // ---- epilogue, M-tile by M-tile as their MMAs complete
     bf16* save_cur = a.db_bufs ? a.db_bufs[db] : nullptr;
     bf16* save_next = (a.db_bufs && db + 1 < a.R * 3) ? a.db_bufs[db + 1] : nullptr;
 #pragma unroll
     for (int mt = 0; mt < TNMT; ++mt) {
+      mbar_wait(smem_u32(&mbar[mt]), L & 1);
+      TR_TRACE(2 + mt);
+      tc_fence_after();
       float v[16];
       tmem_ld16(tmem + lane_base + mt * T_COLS_MT + j * TF, v);
       if (!valid[mt]) continue;
@@ -196,11 +263,13 @@ __global__ void __launch_bounds__(128) trunk_fwd_kernel(const TrunkArgs a) {
       }
     }
     w_elem = w_next;
+    TR_TRACE(5);
     cp_async_wait_all();
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    TR_TRACE(6);
   }
   if (warp == 0) tmem_dealloc(tmem, T_TMEM_COLS);
 }
@@ -221,11 +290,12 @@ struct TrunkBwdArgs {
   bf16* const* d_bufs;         // [3R] dz buffers (pitch 80), written here
   const bf16* w;               // slice-major images of the dense data-gradient matrices, 5 per block
   int R, B;
+  int order;
 };
 
 __global__ void __launch_bounds__(128) trunk_bwd_kernel(const TrunkBwdArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t mbar[TNMT];  // one per M-tile: its epilogue starts while the other tiles' MMAs run
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.x;
@@ -234,7 +304,7 @@ __global__ void __launch_bounds__(128) trunk_bwd_kernel(const TrunkBwdArgs a) {
   const int n_db = a.R * 3;
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), T_TMEM_COLS);
-  if (tid == 32) mbar_init(smem_u32(&mbar), TNMT);
+  if (tid == 32) { for (int i = 0; i < TNMT; ++i) mbar_init(smem_u32(&mbar[i]), 1); }
   for (int i = tid; i < T_X_BYTES / 16; i += 128) st_shared16(sX + i * 16, make_uint4(0, 0, 0, 0));
   // weights of the LAST block's slice 0 -> buffer 0
   {
@@ -303,19 +373,7 @@ __global__ void __launch_bounds__(128) trunk_bwd_kernel(const TrunkBwdArgs a) {
       const int t = j + 1;  // output of this round: dz_{5-t} (t < 5) or the block-input gradient (t == 5)
       const int Nj = TF * (5 - j);
       const uint32_t wb = sW + (L & 1) * T_W_BYTES;
-      if (warp < TNMT && lane == 0) {
-        const uint32_t idj = instr_desc(128, Nj);
-        const uint32_t wplane = Nj * 16;
-        for (int tap = 0; tap < 9; ++tap) {
-          const int dy = tap / 3, dx = tap - 3 * dy;
-          const uint32_t a0 = sX + 2 * j * TPB + (warp * 128 + dy * TPW + dx) * 16;
-          const uint32_t b0 = wb + tap * 2 * wplane;
-          umma_f16(tmem + warp * T_COLS_MT + j * TF, smem_desc(a0, TPB, 128), smem_desc(b0, wplane, 128), idj,
-                   (j > 0 || tap > 0) ? 1u : 0u);
-        }
-        umma_commit(smem_u32(&mbar));
-      }
-      __syncwarp();
+      trunk_issue_round(a.order, warp, tmem, sX, wb, j, Nj, mbar);
       // prefetch the next slice's weights (next slice of this block, or slice 0 of the previous block)
       const size_t w_next = (j < 4) ? w_elem + (size_t)9 * TF * Nj : (size_t)(db - 1) * T_DB_ELEMS_;
       if (j < 4 || db > 0) {
@@ -333,10 +391,10 @@ __global__ void __launch_bounds__(128) trunk_bwd_kernel(const TrunkBwdArgs a) {
           mk[mt][0] = m[0]; mk[mt][1] = m[1];
         }
       }
-      mbar_wait(smem_u32(&mbar), L & 1);
-      tc_fence_after();
 #pragma unroll
       for (int mt = 0; mt < TNMT; ++mt) {
+        mbar_wait(smem_u32(&mbar[mt]), L & 1);
+        tc_fence_after();
         float v[16];
         tmem_ld16(tmem + lane_base + mt * T_COLS_MT + j * TF, v);
         if (!valid[mt]) continue;
@@ -429,7 +487,7 @@ int trunk_bwd_fused(const void* g_in, void* g_out, void* const* fwd_bufs_dev, vo
   TrunkBwdArgs a;
   a.g_in = (const bf16*)g_in; a.g_out = (bf16*)g_out;
   a.fwd_bufs = (const bf16* const*)fwd_bufs_dev; a.d_bufs = (bf16* const*)d_bufs_dev;
-  a.w = (const bf16*)w_slices; a.R = R; a.B = B;
+  a.w = (const bf16*)w_slices; a.R = R; a.B = B; a.order = g_tune[3];
   const double px = (double)B * 256;
   Prof prof(PC_DENSE_UMMA, 2.0 * px * 16.0 * 9.0 * 16.0 * 15.0 * 3.0 * R, px * 80.0 * 2.0 * 2.0 * 3.0 * R, st);
   trunk_bwd_kernel<<<B, 128, T_SMEM, st>>>(a);
@@ -452,11 +510,28 @@ int trunk_fwd_fused(const void* x_in, int in_pitch, int in_coff, void* y_out, in
   a.x_in = (const bf16*)x_in; a.in_pitch = in_pitch; a.in_coff = in_coff;
   a.y_out = (bf16*)y_out; a.out_pitch = out_pitch;
   a.db_bufs = (bf16* const*)db_bufs_dev;
-  a.w = (const bf16*)w_umma; a.bias = bias; a.R = R; a.B = B;
+  a.w = (const bf16*)w_umma; a.bias = bias; a.R = R; a.B = B; a.order = g_tune[3];
+  a.trace = nullptr;
+  static const bool tracing = getenv("DG_TRUNK_TRACE") != nullptr;
+  if (tracing) { cudaMalloc(&a.trace, 32 * 8 * 8); cudaMemset(a.trace, 0, 32 * 8 * 8); }
   const double px = (double)B * 256;
   Prof prof(PC_DENSE_UMMA, 2.0 * px * 16.0 * 9.0 * 16.0 * 15.0 * 3.0 * R, px * 16.0 * 2.0 * 2.0, st);
   trunk_fwd_kernel<<<B, 128, T_SMEM, st>>>(a);
   DG_LAUNCH_CHECK();
+  if (tracing) {
+    unsigned long long h[32 * 8];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, a.trace, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(a.trace);
+    double sum[7] = {0};
+    for (int l = 0; l < 32; ++l) {
+      const unsigned long long* e = h + l * 8;
+      // [issue, wait mt0, wait mt1, wait mt2 (incl. epilogues before), epilogue tail, sync]
+      for (int k = 0; k < 6; ++k) sum[k] += (double)(e[k + 1] - e[k]);
+    }
+    fprintf(stderr, "[trunk trace] order %d, layers 30..61 of CTA 0, mean ns: issue %.0f | ->mt0 ready %.0f | epi0+->mt1 %.0f | epi1+->mt2 %.0f | epi2 %.0f | sync %.0f | layer %.0f\n",
+            a.order, sum[0] / 32, sum[1] / 32, sum[2] / 32, sum[3] / 32, sum[4] / 32, sum[5] / 32, (double)(h[31 * 8 + 6] - h[0]) / 32);
+  }
   return 0;
 }
 

@@ -303,7 +303,7 @@ int get_map_w(const TV& t, int C, int W, int H, int B, int bc, int bw, int bh, i
   cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
   const CUtensorMapSwizzle swz = bc == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : (bc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
   CUtensorMap m;
-  const CUresult r = cuTensorMapEncodeTiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(k.base), dims, strides, box, estr,
+  const CUresult r = encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(k.base), dims, strides, box, estr,
                                             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

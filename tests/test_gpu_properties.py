@@ -135,3 +135,28 @@ def test_inference_tiles_cfg5_like():
         ref = onet.generator_forward(g_sd, gspec, coarse)
     assert out.shape == (2, 2, 512, 512)
     assert pu.rel(out, ref) < 2e-2
+
+
+def test_lookahead_epoch_equals_plain_iterations():
+    """`_train_epoch` with the look-ahead generator forward (fakes of the critic steps between two generator
+    updates computed in one pass) must reproduce the step-by-step schedule exactly: same kernels per sample."""
+    from downgan_b200.synthetic import synth_batch
+    batches = [synth_batch(4, 2, 16, seed=50 + i, aseed=90 + i) for i in range(12)]
+    logs = {}
+    for la in (False, True):
+        G, C, _, _ = pu.build_pair(onet.GeneratorSpec(filters=16, channels=2), onet.CriticSpec(coarse_dim=16, fine_dim=128, nc=2),
+                                   "bf16", seed=3)
+        from downgan_b200.GAN.wasserstein import WassersteinGAN
+        tr = WassersteinGAN(G, C, torch.optim.Adam(G.parameters(), 2.5e-4, betas=(0.9, 0.99)),
+                            torch.optim.Adam(C.parameters(), 2.5e-4, betas=(0.9, 0.99)))
+        tr.lookahead = la
+        logs[la] = tr._train_epoch(batches).clone()
+        params = torch.cat([p.detach().flatten().cpu() for p in list(G.parameters()) + list(C.parameters())])
+        logs[(la, "p")] = params
+    assert torch.isfinite(logs[True]).all()
+    # fp32 reductions across CTAs use atomics (summation order varies run to run), so this is a tolerance, not
+    # bit equality.  Parameters: Adam's first steps move every weight by about +-lr whatever the gradient's
+    # magnitude, so order noise on near-zero gradients appears at ~steps*lr/|w|; a wrong fake (offset bug)
+    # would instead show up in the critic scalars at O(1).
+    assert pu.rel(logs[True], logs[False]) < 1e-3
+    assert pu.rel(logs[(True, "p")], logs[(False, "p")]) < 2e-2
