@@ -288,7 +288,8 @@ def main():
     prof = None
     if not args.no_profile:
         lib.dg_profile(1)
-        run(args.steps, devb, False)
+        tr.num_steps = 0
+        tr._train_epoch([devb[s % NBATCH] for s in range(args.steps)])
         buf = (C.c_double * (4 * len(_lib.PROFILE_CLASSES)))()
         _lib.check(lib.dg_profile_report(buf, len(_lib.PROFILE_CLASSES)))
         lib.dg_profile(0)

@@ -76,9 +76,20 @@ __global__ void __launch_bounds__(128) conv_ci2_kernel(ConvOp op) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * op.slope;
     } else if (op.act == ACT_MASK) {
+      const size_t mo = p * op.mask.pitch + op.mask.coff + co0;
+      if (op.mask.bf && ((mo & 7) == 0)) {  // 16 bf16 mask values as two 16-byte loads
+        const uint4* mp = reinterpret_cast<const uint4*>((const bf16*)op.mask.p + mo);
+        const uint4 m0 = mp[0], m1 = mp[1];
+        const uint32_t w[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        v[j] *= (ldv(op.mask.p, op.mask.bf, p * op.mask.pitch + op.mask.coff + co0 + j) > 0.f ? 1.f : op.slope);
+        for (int k = 0; k < 8; ++k) {
+          v[2 * k] *= (__uint_as_float(w[k] << 16) > 0.f ? 1.f : op.slope);
+          v[2 * k + 1] *= (__uint_as_float(w[k] & 0xFFFF0000u) > 0.f ? 1.f : op.slope);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] *= (ldv(op.mask.p, op.mask.bf, mo + j) > 0.f ? 1.f : op.slope);
+      }
     }
     const size_t o = p * op.y.pitch + op.y.coff + co0;
     if (op.y.bf) {

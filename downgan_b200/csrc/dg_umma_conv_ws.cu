@@ -623,6 +623,7 @@ int conv_umma_ws(const ConvOp& op, cudaStream_t st) {
     static bool attr_set = false;                                                                                 \
     if (!attr_set) {                                                                                              \
       DG_CUDA(cudaFuncSetAttribute(conv_ws_kernel<M, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_MAX_SMEM)); \
+      DG_CUDA(cudaFuncSetAttribute(conv_ws_kernel<M, K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
       attr_set = true;                                                                                            \
     }                                                                                                             \
     conv_ws_kernel<M, K><<<grid, WS_THREADS, smem, st>>>(tmap, a);                                                      \

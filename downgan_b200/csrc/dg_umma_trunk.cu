@@ -482,6 +482,8 @@ int trunk_bwd_fused(const void* g_in, void* g_out, void* const* fwd_bufs_dev, vo
   static bool attr_set = false;
   if (!attr_set) {
     DG_CUDA(cudaFuncSetAttribute(trunk_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
+    // two CTAs (images) per SM need the full 228 KB carve-out: one CTA's epilogue then overlaps the other's MMAs
+    DG_CUDA(cudaFuncSetAttribute(trunk_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   TrunkBwdArgs a;
@@ -504,6 +506,7 @@ int trunk_fwd_fused(const void* x_in, int in_pitch, int in_coff, void* y_out, in
   static bool attr_set = false;
   if (!attr_set) {
     DG_CUDA(cudaFuncSetAttribute(trunk_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
+    DG_CUDA(cudaFuncSetAttribute(trunk_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   TrunkArgs a;

@@ -352,6 +352,7 @@ int wgrad_ws(const WgradOp& op, cudaStream_t st) {
     static bool attr_set = false;                                                                                      \
     if (!attr_set) {                                                                                                   \
       DG_CUDA(cudaFuncSetAttribute(wgrad_ws_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, WW_MAX_SMEM));  \
+      DG_CUDA(cudaFuncSetAttribute(wgrad_ws_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
       attr_set = true;                                                                                                 \
     }                                                                                                                  \
     wgrad_ws_kernel<MODE><<<grid, WW_THREADS, smem, st>>>(mx, md, a);                                                  \

@@ -16,7 +16,7 @@ for r in rows[start:]:
     L.append((name, float(r[I["Metric Value"]]) / 1000.0, r[I["Grid Size"]]))
 # cycles are delimited by the generator step's trunk_bwd_kernel; take the launches between the last two of them
 idx = [i for i, l in enumerate(L) if l[0].startswith("trunk_bwd_kernel")]
-if len(idx) >= 2:
+if len(idx) >= 2 and '--all' not in sys.argv:
     # a cycle = from just after the gen step's final adam (after trunk_bwd) ... simpler: window between consecutive trunk_bwd launches
     L = L[idx[-2]:idx[-1]]
 tot = sum(l[1] for l in L)
@@ -30,5 +30,6 @@ for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"| `{n}` | {c} | {t:.1f} | {t/c:.2f} | {100*t/tot:.1f}% |")
 text = "\n".join(out)
 print(text)
-if len(sys.argv) > 2:
-    open(sys.argv[2], "w").write(text + "\n")
+outs = [a for a in sys.argv[2:] if not a.startswith('--')]
+if outs:
+    open(outs[0], "w").write(text + "\n")

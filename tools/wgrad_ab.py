@@ -21,7 +21,7 @@ def prof_ms(lib, cls="wgrad_tcgen05"):
 
 def main():
     lib = _lib.load()
-    cases = [(192, 16, 16, 128, 2), (192, 16, 32, 64, 1), (192, 32, 32, 64, 2), (192, 32, 64, 32, 1),
+    cases = [(192, 2, 16, 128, 1), (64, 2, 16, 128, 1), (192, 16, 16, 128, 2), (192, 16, 32, 64, 1), (192, 32, 32, 64, 2), (192, 32, 64, 32, 1),
              (192, 64, 64, 32, 2), (192, 64, 128, 16, 1), (192, 128, 128, 16, 2),
              (64, 16, 16, 128, 1), (64, 16, 64, 64, 1), (64, 16, 64, 16, 1), (3, 16, 16, 20, 1), (2, 32, 16, 12, 2), (5, 64, 32, 10, 1)]
     if len(sys.argv) > 1 and sys.argv[1] == "quick":
