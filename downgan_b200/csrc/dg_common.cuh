@@ -127,6 +127,9 @@ struct WgradOp {
   int stride = 1;
   float* dw = nullptr;   // packed [9][Ci][CoP] fp32, accumulated with atomics
   float* dbias = nullptr;  // [Co] accumulated, may be null
+  // channel-block ops (dg_umma_wgrad_ws.cu): this op covers input channels [dw_ci_off, dw_ci_off + Ci) of a layer with
+  // dw_ci_total input channels; dw rows are tap * dw_ci_total + dw_ci_off + ci   (0 / 0: the op is the whole layer)
+  int dw_ci_total = 0, dw_ci_off = 0;
 };
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -193,6 +196,11 @@ bool umma_ws_supported(const ConvOp& op);
 // TMA-fed weight gradient on swizzled NHWC tiles (dg_umma_wgrad_ws.cu)
 bool wgrad_ws_supported(const WgradOp& op);
 int wgrad_ws(const WgradOp& op, cudaStream_t st);
+// many weight gradients in two launches (one per kernel mode, blockIdx.z = op; device table of plans + tensor maps)
+size_t wgrad_ws_batch_bytes(int n_ops);
+int wgrad_ws_batched(const WgradOp* ops, int n, void* table_dev, std::vector<unsigned char>& shadow, int S_per_op, cudaStream_t st);
+// bias gradients of all dense blocks: out[(b*5 + k-1)*16 + c] += sum over rows of D_b[:, (5-k)*16 + c]   (F = 16)
+int colsum_dense_blocks(void* const* d_bufs_dev, int n_blocks, size_t rows, float* out, cudaStream_t st);
 int conv_umma_ws(const ConvOp& op, cudaStream_t st);
 // bf16 re-pack of fp32 packed conv weights [tap][Ci][CoP] into the tcgen05 B-operand image
 // [(tap*Ci/8 + ci/8)][CoP][8]; element offsets are shared with the fp32 packed buffer.

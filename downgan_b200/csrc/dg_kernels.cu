@@ -380,6 +380,47 @@ int colsum(TV dy, size_t pixels, int C, float* out, cudaStream_t st) {
   return 0;
 }
 
+// Bias gradients of every dense conv of the generator trunk in one launch (F = 16): the dz buffer of block b is
+// (rows, 80) bf16 = [dz5 | dz4 | dz3 | dz2 | dz1]; out[(b*5 + k-1)*16 + c] += sum_rows D_b[row][(5-k)*16 + c].
+__global__ void __launch_bounds__(320) colsum_dense_kernel(void* const* __restrict__ d_bufs, size_t rows, size_t rows_per_cta,
+                                                            float* __restrict__ out) {
+  __shared__ float sh[32][80];
+  const int b = blockIdx.y;
+  const bf16* D = (const bf16*)d_bufs[b];
+  const int chunk = threadIdx.x % 10, rl = threadIdx.x / 10;  // 10 16-byte chunks per row, 32 rows in flight
+  const size_t r0 = (size_t)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (size_t r = r0 + rl; r < r1; r += 32) {
+    const uint4 q = *reinterpret_cast<const uint4*>(D + r * 80 + chunk * 8);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      acc[2 * k] += __uint_as_float(w[k] << 16);
+      acc[2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[rl][chunk * 8 + j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 80) {
+    float t = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) t += sh[q][threadIdx.x];
+    const int slice = threadIdx.x >> 4, c = threadIdx.x & 15;  // slice t holds dz_{5-t}
+    atomicAdd(out + ((size_t)b * 5 + (4 - slice)) * 16 + c, t);
+  }
+}
+int colsum_dense_blocks(void* const* d_bufs_dev, int n_blocks, size_t rows, float* out, cudaStream_t st) {
+  if (n_blocks <= 0) return 0;
+  const unsigned gx = 8;
+  const size_t rpc = (rows + gx - 1) / gx;
+  colsum_dense_kernel<<<dim3(gx, (unsigned)n_blocks), 320, 0, st>>>(d_bufs_dev, rows, rpc, out);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------
 // table-driven packing (one launch per network)
 // ---------------------------------------------------------------------------

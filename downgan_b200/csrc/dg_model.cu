@@ -103,6 +103,8 @@ struct dg_generator {
   std::vector<void*> Dall;        // per-dense-block dz buffers (bf16 mode: weight gradients are batched after the dgrad chain)
   void* wg_table_dev = nullptr;   // device table of the batched weight-gradient launch
   std::vector<unsigned char> wg_shadow;
+  void* wgws_table_dev = nullptr; // same for the TMA-fed kernel (plans + tensor maps)
+  std::vector<unsigned char> wgws_shadow;
   void *D = nullptr, *gR = nullptr, *gx0 = nullptr, *gx1 = nullptr, *gT1 = nullptr, *gA = nullptr, *gB = nullptr;
   float* dfake = nullptr;  // NHWC fp32
   float* fine_nhwc = nullptr;
@@ -288,6 +290,7 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
     g->Dall[0] = g->D;
     for (int i = 1; i < g->R * 3; ++i) GA(g->Dall[i], B * pc * 5 * F * g->esz);
     GA(g->wg_table_dev, wgrad_umma_args_size() * (size_t)g->R * 15);
+    GA(g->wgws_table_dev, wgrad_ws_batch_bytes(g->R * 15 * 2));
     GA(g->d_ptrs_dev, sizeof(void*) * g->Dall.size());
     if (cudaMemcpy(g->d_ptrs_dev, g->Dall.data(), sizeof(void*) * g->Dall.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
       set_error("cudaMemcpy(d_ptrs) failed"); dg_generator_destroy(g); return DG_ERR_CUDA;
@@ -540,8 +543,32 @@ static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_co
     }
   }
   g->D = D0;
-  if (batched_wgrad && !wops.empty())  // all 15R dense-conv weight + bias gradients in one tcgen05 launch
-    DG_TRY(wgrad_umma_batched(wops.data(), (int)wops.size(), g->wg_table_dev, g->wg_shadow, 2, st));
+  if (batched_wgrad && !wops.empty()) {
+    if (g_tune[4] && F == 16 && fused_bwd) {
+      // TMA-fed kernel: every layer (Ci = 16k input channels) as power-of-two channel blocks, two launches for all
+      // of them; bias gradients = column sums of the dz buffers in one more launch
+      std::vector<WgradOp> blk;
+      blk.reserve(wops.size() * 2);
+      for (const WgradOp& w : wops) {
+        int c0 = 0;
+        while (c0 < w.Ci) {
+          int cb = 64;
+          while (cb > w.Ci - c0) cb >>= 1;
+          WgradOp o = w;
+          o.x.coff = w.x.coff + c0; o.Ci = cb; o.dbias = nullptr;
+          o.dw_ci_total = w.Ci; o.dw_ci_off = c0;
+          blk.push_back(o);
+          c0 += cb;
+        }
+      }
+      DG_TRY(wgrad_ws_batched(blk.data(), (int)blk.size(), g->wgws_table_dev, g->wgws_shadow, 2, st));
+      const Layer& l0 = g->layers[g->idx_db(0, 0, 1)];
+      DG_TRY(colsum_dense_blocks((void* const*)g->d_ptrs_dev, g->R * 3, (size_t)B * Hc * Hc, g->gpk + l0.pkb_off, st));
+    } else {
+      // all 15R dense-conv weight + bias gradients in one tcgen05 launch
+      DG_TRY(wgrad_umma_batched(wops.data(), (int)wops.size(), g->wg_table_dev, g->wg_shadow, 2, st));
+    }
+  }
   // dL/d(out1) = gR (through the trunk / conv2) + gT1 (long skip)
   DG_TRY(scale_add(g->act(g->gx0, F), g->act(g->gR, F), 1.f, g->act(g->gT1, F), 1.f, pix, F, st));
   DG_TRY(wgrad(g->idx_conv1(), g->act(g->x0, g->Cin), Hc, g->act(g->gx0, F)));

@@ -21,6 +21,7 @@
 //   all     epilogue once per CTA: tcgen05.ld, red.global.add.v4.f32 into dW (fp32, [tap][ci][CoP])
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -50,6 +51,7 @@ struct WwArgs {
   unsigned stage_bytes, d_off;  // ring slot size, offset of the dy region inside a slot
   unsigned tx_bytes;
   int tiles_per_img, tiles_total, tiles_per_cta, nstage, tmem_cols;
+  int ci_total, ci_off;  // dw row = tap * ci_total + ci_off + ci
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -93,11 +95,9 @@ __device__ __forceinline__ uint64_t mn_desc(uint32_t lbo, uint32_t rowbytes) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(WW_THREADS) wgrad_ws_kernel(const __grid_constant__ CUtensorMap mapx,
-                                                               const __grid_constant__ CUtensorMap mapd, const WwArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bars[2 * WW_MAX_STAGE + 1];
-  __shared__ uint32_t tmem_slot;
+__device__ __forceinline__ void wgrad_ws_body(const CUtensorMap* mapx_p, const CUtensorMap* mapd_p, const WwArgs& a, uint8_t* smem,
+                                              uint64_t* bars, uint32_t* tmem_slot_p) {
+  uint32_t& tmem_slot = *tmem_slot_p;
   constexpr int UNITS = (MODE == W_S1_FOLD) ? 3 : 9;
   const WgradOp& op = a.op;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(WW_THREADS) wgrad_ws_kernel(const __grid_const
   const int t_begin = blockIdx.x * a.tiles_per_cta;
   const int t_end = min(a.tiles_total, t_begin + a.tiles_per_cta);
   const int my_tiles = max(0, t_end - t_begin);
+  if (my_tiles == 0 || co0 >= op.Co) return;  // batched launches are sized for the largest op (uniform exit, before any barrier)
   const int S = a.nstage;
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -145,9 +146,9 @@ __global__ void __launch_bounds__(WW_THREADS) wgrad_ws_kernel(const __grid_const
           if (MODE == W_S2_TAPS) { cx = -2 + (sub & 1); cy = 2 * (y0 - 1) + (sub >> 1); }
           else { cx = -1; cy = y0 - 1; }
           for (int blk = 0; blk < a.nblkx; ++blk)
-            tma_load_4d(sx + (sub * a.nblkx + blk) * a.xreg, &mapx, blk * 64, cx, cy, n, full_bar(s));
+            tma_load_4d(sx + (sub * a.nblkx + blk) * a.xreg, mapx_p, blk * 64, cx, cy, n, full_bar(s));
         }
-        tma_load_4d(sd, &mapd, co0, 0, y0, n, full_bar(s));
+        tma_load_4d(sd, mapd_p, co0, 0, y0, n, full_bar(s));
       }
       __syncwarp();
     }
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(WW_THREADS) wgrad_ws_kernel(const __grid_const
         float v[16];
         tmem_ld16(tmem + lane_base + u * a.NT + nc, v);
         if (valid) {
-          float* dst = op.dw + ((size_t)tap * op.Ci + ci) * a.CoP + co0 + nc;
+          float* dst = op.dw + ((size_t)tap * a.ci_total + a.ci_off + ci) * a.CoP + co0 + nc;
 #pragma unroll
           for (int q = 0; q < 4; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
@@ -225,6 +226,33 @@ __global__ void __launch_bounds__(WW_THREADS) wgrad_ws_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, (uint32_t)a.tmem_cols);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(WW_THREADS) wgrad_ws_kernel(const __grid_constant__ CUtensorMap mapx,
+                                                               const __grid_constant__ CUtensorMap mapd, const WwArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[2 * WW_MAX_STAGE + 1];
+  __shared__ uint32_t tmem_slot;
+  wgrad_ws_body<MODE>(&mapx, &mapd, a, smem, bars, &tmem_slot);
+}
+
+// one launch for many ops of the same MODE: blockIdx.z selects the op; plans and tensor maps live in a device table
+template <int MODE>
+__global__ void __launch_bounds__(WW_THREADS) wgrad_ws_batched_kernel(const WwArgs* __restrict__ args, const CUtensorMap* __restrict__ maps,
+                                                                       const int* __restrict__ op_index) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[2 * WW_MAX_STAGE + 1];
+  __shared__ uint32_t tmem_slot;
+  __shared__ WwArgs sa;
+  const int z = op_index[blockIdx.z];
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(args + z);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sa);
+    for (int i = threadIdx.x; i < (int)(sizeof(WwArgs) / 4); i += WW_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  wgrad_ws_body<MODE>(maps + 2 * z, maps + 2 * z + 1, sa, smem, bars, &tmem_slot);
 }
 
 bool plan_ww(const WgradOp& op, WwArgs& a) {
@@ -266,6 +294,21 @@ bool plan_ww(const WgradOp& op, WwArgs& a) {
     b.tx_bytes = (unsigned)((size_t)nsub * (TH + hrows) * PW * op.Ci * 2 + (size_t)TH * PW * drow);
   }
   if (bestTH == 0) return false;
+  if (bestTH < op.Hout) {  // balance the tiles of an image (e.g. 16 rows: 8 + 8 instead of 14 + 2)
+    const int nt = (op.Hout + bestTH - 1) / bestTH;
+    const int TH = (op.Hout + nt - 1) / nt;
+    if (TH < bestTH) {
+      const int nks = (TH * PW + 15) / 16;
+      const size_t xpos = std::max((size_t)(TH + hrows) * PW, (size_t)nks * 16 + max_shift + 8);
+      const size_t xreg = (xpos * xrow + 1023) & ~(size_t)1023;
+      const size_t dreg = ((size_t)nks * 16 * drow + 1023) & ~(size_t)1023;
+      bestTH = TH;
+      b.TH = TH; b.nks = nks; b.xreg = (unsigned)xreg; b.dreg = (unsigned)dreg;
+      b.stage_bytes = (unsigned)(xreg * nblkx * nsub + dreg);
+      b.d_off = (unsigned)(xreg * nblkx * nsub);
+      b.tx_bytes = (unsigned)((size_t)nsub * (TH + hrows) * PW * op.Ci * 2 + (size_t)TH * PW * drow);
+    }
+  }
   a = b;
   a.op = op;
   a.mode = mode; a.units = units;
@@ -280,6 +323,8 @@ bool plan_ww(const WgradOp& op, WwArgs& a) {
   int pc = 32;
   while (pc < units * NT) pc <<= 1;
   a.tmem_cols = pc;
+  a.ci_total = op.dw_ci_total > 0 ? op.dw_ci_total : op.Ci;
+  a.ci_off = op.dw_ci_total > 0 ? op.dw_ci_off : 0;
   return true;
 }
 
@@ -364,6 +409,79 @@ int wgrad_ws(const WgradOp& op, cudaStream_t st) {
   }
   DG_LAUNCH_CHECK();
   if (op.dbias) DG_TRY(colsum(op.dy, (size_t)total, op.Co, op.dbias, st));
+  return 0;
+}
+
+
+size_t wgrad_ws_batch_bytes(int n_ops) {
+  return (size_t)n_ops * (sizeof(WwArgs) + 2 * sizeof(CUtensorMap) + sizeof(int)) + 256;
+}
+
+// Table layout: [CUtensorMap x 2n (64-byte aligned)] [WwArgs x n] [int x n: op indices grouped by mode]
+int wgrad_ws_batched(const WgradOp* ops, int n, void* table_dev, std::vector<unsigned char>& shadow, int S_per_op, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const size_t maps_bytes = (size_t)n * 2 * sizeof(CUtensorMap), args_bytes = (size_t)n * sizeof(WwArgs);
+  std::vector<unsigned char> tab(maps_bytes + args_bytes + (size_t)n * sizeof(int));
+  CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(tab.data());
+  WwArgs* args = reinterpret_cast<WwArgs*>(tab.data() + maps_bytes);
+  int* order = reinterpret_cast<int*>(tab.data() + maps_bytes + args_bytes);
+  unsigned smem[3] = {0, 0, 0}, gx[3] = {1, 1, 1};
+  int count[3] = {0, 0, 0};
+  double flops = 0, bytes = 0;
+  for (int i = 0; i < n; ++i) {
+    WwArgs a;
+    if (!plan_ww(ops[i], a)) { set_error("wgrad_ws_batched: op %d unsupported", i); return DG_ERR_INVALID; }
+    if (ops[i].Co != a.NT) { set_error("wgrad_ws_batched: op %d needs output-channel chunks", i); return DG_ERR_INVALID; }
+    long long S = std::max(1, std::min(S_per_op, a.tiles_total));
+    a.tiles_per_cta = (int)((a.tiles_total + S - 1) / S);
+    S = (a.tiles_total + a.tiles_per_cta - 1) / a.tiles_per_cta;
+    const int s = ops[i].stride, hrows = (s == 1) ? 2 : 1;
+    CUtensorMap mx, md;
+    DG_TRY(get_map_w(ops[i].x, ops[i].Ci, ops[i].Win, ops[i].Hin, ops[i].B, std::min(ops[i].Ci, 64), a.PW * s, (a.TH + hrows) * s, s, &mx));
+    DG_TRY(get_map_w(ops[i].dy, ops[i].Co, ops[i].Wout, ops[i].Hout, ops[i].B, a.NT, a.PW, a.TH, 1, &md));
+    memcpy(&maps[2 * i], &mx, sizeof(CUtensorMap));
+    memcpy(&maps[2 * i + 1], &md, sizeof(CUtensorMap));
+    memcpy(&args[i], &a, sizeof(WwArgs));
+    gx[a.mode] = std::max(gx[a.mode], (unsigned)S);
+    smem[a.mode] = std::max(smem[a.mode], (unsigned)((size_t)a.nstage * a.stage_bytes + 1024));
+    ++count[a.mode];
+    const double total = (double)ops[i].B * ops[i].Hout * ops[i].Wout;
+    flops += 2.0 * total * ops[i].Co * ops[i].Ci * 9.0;
+    bytes += total * ops[i].Co * 2.0 + (double)ops[i].B * ops[i].Hin * ops[i].Win * ops[i].Ci * 2.0;
+  }
+  int start[3], pos = 0;
+  for (int m = 0; m < 3; ++m) {
+    start[m] = pos;
+    for (int i = 0; i < n; ++i)
+      if (args[i].mode == m) order[pos++] = i;
+  }
+  if (shadow.size() != tab.size() || memcmp(shadow.data(), tab.data(), tab.size()) != 0) {
+    shadow = tab;
+    DG_CUDA(cudaMemcpyAsync(table_dev, shadow.data(), shadow.size(), cudaMemcpyHostToDevice, st));
+  }
+  const CUtensorMap* dmaps = reinterpret_cast<const CUtensorMap*>(table_dev);
+  const WwArgs* dargs = reinterpret_cast<const WwArgs*>((const unsigned char*)table_dev + maps_bytes);
+  const int* dorder = reinterpret_cast<const int*>((const unsigned char*)table_dev + maps_bytes + args_bytes);
+  Prof prof(PC_WGRAD_UMMA, flops, bytes, st);
+#define WWB_LAUNCH(MODE)                                                                                                      \
+  do {                                                                                                                        \
+    if (count[MODE] > 0) {                                                                                                    \
+      static bool attr_set = false;                                                                                           \
+      if (!attr_set) {                                                                                                        \
+        DG_CUDA(cudaFuncSetAttribute(wgrad_ws_batched_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, WW_MAX_SMEM)); \
+        DG_CUDA(cudaFuncSetAttribute(wgrad_ws_batched_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,           \
+                                     cudaSharedmemCarveoutMaxShared));                                                        \
+        attr_set = true;                                                                                                      \
+      }                                                                                                                       \
+      wgrad_ws_batched_kernel<MODE><<<dim3(gx[MODE], 1, (unsigned)count[MODE]), WW_THREADS, smem[MODE], st>>>(dargs, dmaps,   \
+                                                                                                              dorder + start[MODE]); \
+      DG_LAUNCH_CHECK();                                                                                                      \
+    }                                                                                                                         \
+  } while (0)
+  WWB_LAUNCH(W_S1_FOLD);
+  WWB_LAUNCH(W_S1_TAPS);
+  WWB_LAUNCH(W_S2_TAPS);
+#undef WWB_LAUNCH
   return 0;
 }
 
