@@ -222,6 +222,11 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_ws_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // Programmatic dependent launch: everything above (TMEM allocation, barrier init, weight staging - weights are
+  // never written by the kernel launched just before a conv) may overlap the tail of the previous kernel; the
+  // activations it produced are only touched after this wait.  Our own dependents may start their prologue now.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t tmem = tmem_slot;
   constexpr int ncls = (MODE == S2_DGRAD) ? 4 : 1;
   const int my_tiles = ((int)blockIdx.x < a.tiles_total) ? (a.tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -626,7 +631,13 @@ int conv_umma_ws(const ConvOp& op, cudaStream_t st) {
       DG_CUDA(cudaFuncSetAttribute(conv_ws_kernel<M, K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
       attr_set = true;                                                                                            \
     }                                                                                                             \
-    conv_ws_kernel<M, K><<<grid, WS_THREADS, smem, st>>>(tmap, a);                                                      \
+    cudaLaunchConfig_t cfg = {};                                                                                  \
+    cfg.gridDim = grid; cfg.blockDim = dim3(WS_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;            \
+    cudaLaunchAttribute attr[1];                                                                                  \
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                              \
+    attr[0].val.programmaticStreamSerializationAllowed = g_tune[5] ? 1 : 0;                                       \
+    cfg.attrs = attr; cfg.numAttrs = 1;                                                                           \
+    DG_CUDA(cudaLaunchKernelEx(&cfg, conv_ws_kernel<M, K>, tmap, a));                                                      \
   } while (0)
 #define WS_LAUNCH_K(M)                     \
   do {                                     \

@@ -127,6 +127,9 @@ __device__ __forceinline__ void wgrad_ws_body(const CUtensorMap* mapx_p, const C
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // programmatic dependent launch: the prologue above touched no global memory
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t tmem = tmem_slot;
 
   if (warp == 0) {
@@ -400,7 +403,13 @@ int wgrad_ws(const WgradOp& op, cudaStream_t st) {
       DG_CUDA(cudaFuncSetAttribute(wgrad_ws_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
       attr_set = true;                                                                                                 \
     }                                                                                                                  \
-    wgrad_ws_kernel<MODE><<<grid, WW_THREADS, smem, st>>>(mx, md, a);                                                  \
+    cudaLaunchConfig_t cfg = {};                                                                                       \
+    cfg.gridDim = grid; cfg.blockDim = dim3(WW_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;                 \
+    cudaLaunchAttribute attr[1];                                                                                       \
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                   \
+    attr[0].val.programmaticStreamSerializationAllowed = g_tune[5] ? 1 : 0;                                            \
+    cfg.attrs = attr; cfg.numAttrs = 1;                                                                                \
+    DG_CUDA(cudaLaunchKernelEx(&cfg, wgrad_ws_kernel<MODE>, mx, md, a));                                               \
   } while (0)
   if (a.mode == W_S1_FOLD) WW_LAUNCH(W_S1_FOLD);
   else if (a.mode == W_S1_TAPS) WW_LAUNCH(W_S1_TAPS);
