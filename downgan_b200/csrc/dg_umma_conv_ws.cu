@@ -400,8 +400,13 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_ws_kernel(const __grid_con
             for (int j = 0; j < 16; ++j) v[j] = fmaf(op.s2, t[j], v[j]);
           }
           if (op.act == ACT_LRELU) {
+            if (op.slope >= 0.f && op.slope <= 1.f) {  // max(v, slope*v) == LeakyReLU for 0 <= slope <= 1
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * op.slope;
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * op.slope);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * op.slope;
+            }
           } else if (op.act == ACT_MASK) {
             if (pre_mask) {
               const uint32_t w[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
