@@ -193,6 +193,9 @@ bool umma_supported(const ConvOp& op);
 int conv_umma(const ConvOp& op, cudaStream_t st);
 // warp-specialised persistent variant (dg_umma_conv_ws.cu); DG_CONV_WS=0 in the environment falls back to conv_umma
 bool umma_ws_supported(const ConvOp& op);
+// tcgen05 forward conv of the few-channel fp32 boundary layer (dg_umma_conv_l1.cu)
+bool conv_l1_supported(const ConvOp& op);
+int conv_l1(const ConvOp& op, cudaStream_t st);
 // TMA-fed weight gradient on swizzled NHWC tiles (dg_umma_wgrad_ws.cu)
 bool wgrad_ws_supported(const WgradOp& op);
 int wgrad_ws(const WgradOp& op, cudaStream_t st);

@@ -58,6 +58,7 @@ int run_wgrad(const WgradOp& w, cudaStream_t st) {
 }
 
 int run_conv(const ConvOp& op, cudaStream_t st) {
+  if (g_tune[6] && conv_l1_supported(op)) return conv_l1(op, st);
   if (conv_skinny_supported(op)) return conv_skinny(op, st);
   static const bool ws = !(getenv("DG_CONV_WS") && atoi(getenv("DG_CONV_WS")) == 0);
   if (ws && g_tune[0] && op.w_umma && umma_ws_supported(op)) return conv_umma_ws(op, st);
