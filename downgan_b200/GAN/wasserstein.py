@@ -150,18 +150,21 @@ class WassersteinGAN:
             self._c_adam.step(grads, scale)
         self.last_critic = self._c_scal
 
-    def _generator_lookahead(self, coarse_all: torch.Tensor) -> None:
+    def _generator_lookahead(self, coarse_all: torch.Tensor, save_first: int = 0) -> None:
         """fake = G(coarse) for several upcoming critic batches in one pass (same generator weights: the
-        generator is only updated every `critic_iterations` steps, wasserstein.py:136-137)."""
+        generator is only updated every `critic_iterations` steps, wasserstein.py:136-137).  The first
+        `save_first` samples keep their activations for the generator iteration on that batch."""
         coarse_all = self._prep(coarse_all)
         total, _, h, _ = coarse_all.shape
         with torch.cuda.device(self.device):
             g = self.G.native(h, total)
             self.G.ensure_packed(g)
-            _lib.check(_lib.load().dg_generator_lookahead(g, coarse_all.data_ptr(), total, _lib.stream_ptr()))
+            _lib.check(_lib.load().dg_generator_lookahead(g, coarse_all.data_ptr(), total, int(save_first),
+                                                          _lib.stream_ptr()))
 
-    def _generator_train_iteration(self, coarse, fine):
-        """One generator update (wasserstein.py:58-83)."""
+    def _generator_train_iteration(self, coarse, fine, _saved_forward: bool = False):
+        """One generator update (wasserstein.py:58-83).  `_saved_forward` (set by `_train_epoch`'s look-ahead):
+        G(coarse) and its activations are still resident from the look-ahead pass and are not recomputed."""
         coarse, fine = self._prep(coarse), self._prep(fine)
         b = coarse.shape[0]
         with torch.cuda.device(self.device):
@@ -170,8 +173,12 @@ class WassersteinGAN:
                 self._g_scal = torch.zeros(8, device=self.device)
             grads = self.G.flat_grads()
             hyp = self._hyper()
-            _lib.check(_lib.load().dg_generator_step(g, c, hyp, coarse.data_ptr(), fine.data_ptr(), b,
-                                                     grads.data_ptr(), self._g_scal.data_ptr(), _lib.stream_ptr()))
+            if _saved_forward:
+                _lib.check(_lib.load().dg_generator_step_saved(g, c, hyp, fine.data_ptr(), b, grads.data_ptr(),
+                                                               self._g_scal.data_ptr(), _lib.stream_ptr()))
+            else:
+                _lib.check(_lib.load().dg_generator_step(g, c, hyp, coarse.data_ptr(), fine.data_ptr(), b,
+                                                         grads.data_ptr(), self._g_scal.data_ptr(), _lib.stream_ptr()))
             scale = self._allreduce(grads)
             self._g_adam.step(grads, scale)
         self.last_generator = self._g_scal
@@ -251,23 +258,33 @@ class WassersteinGAN:
             depth = n_critic + 1 if getattr(self, "lookahead", True) else 2  # host->device copies run this far ahead
             fill(depth)
             offsets = []  # look-ahead: sample offsets of the fakes of the next critic steps
+            saved_steps = set()  # steps whose generator iteration reuses the look-ahead forward
             logs = []
             while pending:
                 s = self.num_steps
                 if getattr(self, "lookahead", True) and not offsets and n_critic > 1 and s % n_critic != 0:
                     # steps s .. next multiple of n_critic all see the current generator weights
                     fill(n_critic - (s % n_critic) + 1)
-                    group = pending[:n_critic - (s % n_critic) + 1]
+                    want = n_critic - (s % n_critic) + 1
+                    group = pending[:want]
                     if len(group) > 1:
                         for _, ev in group:
                             if ev is not None:
                                 main.wait_event(ev)
-                        coarse_all = torch.cat([sl["bufs"][0] for sl, _ in group], dim=0)
-                        self._generator_lookahead(coarse_all)
+                        # the group's LAST batch is the one the generator iteration runs on (step % n_critic == 0):
+                        # it goes first in the pass and keeps its activations, so that iteration needs no forward
+                        full = len(group) == want
+                        order = [len(group) - 1] + list(range(len(group) - 1)) if full else list(range(len(group)))
+                        coarse_all = torch.cat([group[i][0]["bufs"][0] for i in order], dim=0)
+                        save_first = group[-1][0]["bufs"][0].shape[0] if full else 0
+                        self._generator_lookahead(coarse_all, save_first)
+                        offs = [0] * len(group)
                         off = 0
-                        for sl, _ in group:
-                            offsets.append(off)
-                            off += sl["bufs"][0].shape[0]
+                        for i in order:
+                            offs[i] = off
+                            off += group[i][0]["bufs"][0].shape[0]
+                        offsets.extend(offs)
+                        saved_steps = {s + len(group) - 1} if full else set()
                 slot, ev = pending.pop(0)
                 fill(depth)
                 if ev is not None:
@@ -277,7 +294,8 @@ class WassersteinGAN:
                 alpha = ts[2] if len(ts) > 2 else None
                 self._critic_train_iteration(coarse, fine, alpha, _fake_offset=offsets.pop(0) if offsets else None)
                 if self.num_steps % n_critic == 0:
-                    self._generator_train_iteration(coarse, fine)
+                    self._generator_train_iteration(coarse, fine, _saved_forward=self.num_steps in saved_steps)
+                    saved_steps.discard(self.num_steps)
                 self.num_steps += 1
                 slot["done"] = torch.cuda.Event()
                 slot["done"].record(main)

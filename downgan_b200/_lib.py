@@ -66,7 +66,8 @@ _SIGNATURES = {
                                C.c_int, C.c_float, _P]),
     "dg_critic_step": (C.c_int, [_P, _P, C.POINTER(Hyper), _P, _P, _P, C.c_int, _P, _P, _P]),
     "dg_generator_step": (C.c_int, [_P, _P, C.POINTER(Hyper), _P, _P, C.c_int, _P, _P, _P]),
-    "dg_generator_lookahead": (C.c_int, [_P, _P, C.c_int, _P]),
+    "dg_generator_lookahead": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    "dg_generator_step_saved": (C.c_int, [_P, _P, C.POINTER(Hyper), _P, C.c_int, _P, _P, _P]),
     "dg_critic_step_fake": (C.c_int, [_P, _P, C.POINTER(Hyper), C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     "dg_conv3x3_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_float, C.c_int, _P]),

@@ -226,7 +226,7 @@ namespace dg {
 // persistent fused RRDB trunk, forward (dg_umma_trunk.cu)
 bool trunk_fused_supported(int F, int Hc, int R, int bf);
 int trunk_fwd_fused(const void* x_in, int in_pitch, int in_coff, void* y_out, int out_pitch, void* const* db_bufs_dev,
-                    const void* w_umma, const float* bias, int R, int B, cudaStream_t st);
+                    const void* w_umma, const float* bias, int R, int B, int save_count, cudaStream_t st);
 }  // namespace dg
 
 namespace dg {

@@ -331,7 +331,9 @@ extern "C" int dg_generator_pack(dg_generator* g, const float* params, void* str
 
 // Generator.forward, networks/generator.py:83-90 (dense block :36-41, RRDB :52-53).
 // Input already in g->x0 (NHWC); output in g->fake (NHWC fp32).
-static int gen_forward_internal(dg_generator* g, int B, bool save, cudaStream_t st) {
+// `save_count` leading samples keep their activations for a later backward (0: inference / critic iterations).
+static int gen_forward_internal(dg_generator* g, int B, int save_count, cudaStream_t st) {
+  const bool save = save_count > 0;
   const int F = g->F, Hc = g->Hc;
   auto conv = [&](int li, TV x, int H, TV y) {
     const Layer& l = g->layers[li];
@@ -353,7 +355,7 @@ static int gen_forward_internal(dg_generator* g, int B, bool save, cudaStream_t 
     // persistent tcgen05 kernel: the whole RRDB trunk with the concat buffer resident in shared memory
     const Layer& l0 = g->layers[g->idx_db(0, 0, 1)];
     DG_TRY(trunk_fwd_fused(g->db[0], 5 * F, 0, g->trunk_out, F, save ? (void* const*)g->db_ptrs_dev : nullptr,
-                           g->pk_trunk, g->pk + l0.pkb_off, g->R, B, st));
+                           g->pk_trunk, g->pk + l0.pkb_off, g->R, B, save_count, st));
   }
   for (int r = 0; r < (fused_trunk ? 0 : g->R); ++r)
     for (int d = 0; d < 3; ++d) {
@@ -399,7 +401,7 @@ static int gen_forward_internal(dg_generator* g, int B, bool save, cudaStream_t 
     ConvOp op = conv(g->idx_c32(), g->act(g->c30, F), H, tv(g->fake, 0, g->Cout));
     DG_TRY(run_conv(op, st));
   }
-  g->saved_batch = save ? B : 0;
+  g->saved_batch = save_count;
   return 0;
 }
 
@@ -410,7 +412,7 @@ extern "C" int dg_generator_fwd(dg_generator* g, const float* coarse, int batch,
   cudaStream_t st = (cudaStream_t)stream;
   DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), batch, g->Cin, g->Hc, g->Hc, st));
   g->lookahead = 0;
-  DG_TRY(gen_forward_internal(g, batch, save != 0, st));
+  DG_TRY(gen_forward_internal(g, batch, save ? batch : 0, st));
   if (fake) DG_TRY(nhwc_to_nchw(tv(g->fake, 0, g->Cout), fake, batch, g->Cout, g->Hf, g->Hf, st));
   return 0;
 }
@@ -1015,7 +1017,7 @@ extern "C" int dg_critic_step(dg_generator* g, dg_critic* c, const dg_hyper* hp,
   DG_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(float), st));
   // fake = G(coarse): the reference keeps the graph (:35) but discards the generator gradients (:65)
   DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), B, g->Cin, g->Hc, g->Hc, st));
-  DG_TRY(gen_forward_internal(g, B, false, st));
+  DG_TRY(gen_forward_internal(g, B, 0, st));
   g->saved_batch = 0;
   g->lookahead = 0;
   return critic_step_body(g, c, hp, g->fake, fine, alpha, B, c_grads_flat, scalars, st);
@@ -1026,14 +1028,14 @@ extern "C" int dg_critic_step(dg_generator* g, dg_critic* c, const dg_hyper* hp,
 // is computed in one pass: the persistent trunk kernel then has one CTA per sample for ALL of them (a single batch
 // of 64 fills 64 of the 148 SMs).  The fakes stay in the generator's NHWC output buffer until the next
 // generator forward; dg_critic_step_fake consumes them by sample offset.
-extern "C" int dg_generator_lookahead(dg_generator* g, const float* coarse, int total, void* stream) {
+extern "C" int dg_generator_lookahead(dg_generator* g, const float* coarse, int total, int save_first, void* stream) {
   DG_CHECK(g && coarse, "dg_generator_lookahead: null argument");
   DG_CHECK(total >= 1 && total <= g->maxB, "dg_generator_lookahead: %d samples outside [1,%d]", total, g->maxB);
+  DG_CHECK(save_first >= 0 && save_first <= total, "dg_generator_lookahead: save_first %d outside [0,%d]", save_first, total);
   if (!g->packed) { set_error("dg_generator_lookahead: dg_generator_pack has not been called"); return DG_ERR_STATE; }
   cudaStream_t st = (cudaStream_t)stream;
   DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), total, g->Cin, g->Hc, g->Hc, st));
-  DG_TRY(gen_forward_internal(g, total, false, st));
-  g->saved_batch = 0;
+  DG_TRY(gen_forward_internal(g, total, save_first, st));  // sets saved_batch = save_first
   g->lookahead = total;
   return 0;
 }
@@ -1056,19 +1058,10 @@ extern "C" int dg_critic_step_fake(dg_generator* g, dg_critic* c, const dg_hyper
 }
 
 // _generator_train_iteration, wasserstein.py:65-80 (everything except G_optimizer.step()).
-extern "C" int dg_generator_step(dg_generator* g, dg_critic* c, const dg_hyper* hp, const float* coarse, const float* fine,
-                                 int batch, float* g_grads_flat, float* scalars, void* stream) {
-  DG_CHECK(g && c && hp && coarse && fine && g_grads_flat && scalars, "dg_generator_step: null argument");
-  DG_CHECK(batch >= 1 && batch <= g->maxB && batch <= c->maxB, "dg_generator_step: batch %d too large", batch);
-  DG_CHECK(g->Hf == c->Hf && g->Cout == c->nc, "dg_generator_step: generator output does not match critic input");
-  if (!g->packed || !c->packed) { set_error("dg_generator_step: weights not packed"); return DG_ERR_STATE; }
-  cudaStream_t st = (cudaStream_t)stream;
-  const int B = batch;
+// everything of _generator_train_iteration after fake = G(coarse) (activations of `batch` samples saved in g)
+static int generator_step_body(dg_generator* g, dg_critic* c, const dg_hyper* hp, const float* fine, int B, float* g_grads_flat,
+                               float* scalars, cudaStream_t st) {
   const long long n = (long long)B * g->Hf * g->Hf * g->Cout;
-  DG_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(float), st));
-  DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), B, g->Cin, g->Hc, g->Hc, st));
-  g->lookahead = 0;
-  DG_TRY(gen_forward_internal(g, B, true, st));
   // c_fake = C(fake); adversarial seed d(-gamma*mean)/dscore = -gamma/B
   DG_CUDA(cudaMemcpyAsync(c->a0, g->fake, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
   DG_TRY(critic_forward_internal(c, B, st));
@@ -1080,7 +1073,41 @@ extern "C" int dg_generator_step(dg_generator* g, dg_critic* c, const dg_hyper* 
   DG_TRY(gen_scalars(c->scores, B, g->l1, hp->gamma, hp->content_lambda, scalars, st));
   DG_TRY(gen_backward_internal(g, g_grads_flat, nullptr, st));
   c->saved_batch = 0;
+  g->lookahead = 0;  // the backward reuses activation buffers of the look-ahead pass
   return 0;
+}
+
+extern "C" int dg_generator_step(dg_generator* g, dg_critic* c, const dg_hyper* hp, const float* coarse, const float* fine,
+                                 int batch, float* g_grads_flat, float* scalars, void* stream) {
+  DG_CHECK(g && c && hp && coarse && fine && g_grads_flat && scalars, "dg_generator_step: null argument");
+  DG_CHECK(batch >= 1 && batch <= g->maxB && batch <= c->maxB, "dg_generator_step: batch %d too large", batch);
+  DG_CHECK(g->Hf == c->Hf && g->Cout == c->nc, "dg_generator_step: generator output does not match critic input");
+  if (!g->packed || !c->packed) { set_error("dg_generator_step: weights not packed"); return DG_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = batch;
+  DG_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(float), st));
+  DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), B, g->Cin, g->Hc, g->Hc, st));
+  g->lookahead = 0;
+  DG_TRY(gen_forward_internal(g, B, B, st));
+  return generator_step_body(g, c, hp, fine, B, g_grads_flat, scalars, st);
+}
+
+// _generator_train_iteration on the batch whose forward (samples [0, batch) of the last dg_generator_lookahead,
+// save_first == batch) is still resident: the generator weights have not changed since, so G(coarse) is not recomputed.
+extern "C" int dg_generator_step_saved(dg_generator* g, dg_critic* c, const dg_hyper* hp, const float* fine, int batch,
+                                       float* g_grads_flat, float* scalars, void* stream) {
+  DG_CHECK(g && c && hp && fine && g_grads_flat && scalars, "dg_generator_step_saved: null argument");
+  DG_CHECK(batch >= 1 && batch <= c->maxB, "dg_generator_step_saved: batch %d too large", batch);
+  DG_CHECK(g->Hf == c->Hf && g->Cout == c->nc, "dg_generator_step_saved: generator output does not match critic input");
+  if (!g->packed || !c->packed) { set_error("dg_generator_step_saved: weights not packed"); return DG_ERR_STATE; }
+  if (g->saved_batch != batch || g->lookahead < batch) {
+    set_error("dg_generator_step_saved: no saved look-ahead forward for %d samples (saved %d, look-ahead %d)", batch, g->saved_batch,
+              g->lookahead);
+    return DG_ERR_STATE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(float), st));
+  return generator_step_body(g, c, hp, fine, batch, g_grads_flat, scalars, st);
 }
 
 // ===========================================================================

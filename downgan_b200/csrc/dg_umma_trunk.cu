@@ -41,6 +41,7 @@ struct TrunkArgs {
   const float* bias;                        // 16 floats per dense conv, consecutive
   int R, B;
   int order;                                // MMA issue order, see trunk_issue_round
+  int save_count;                           // samples [0, save_count) store their slices to db_bufs
   unsigned long long* trace;                // debug timeline (DG_TRUNK_TRACE), null otherwise
 };
 
@@ -213,8 +214,9 @@ __global__ void __launch_bounds__(128) trunk_fwd_kernel(const TrunkArgs a) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) bias[j] = __ldg(a.bias + (size_t)L * 16 + j);
     // ---- epilogue, M-tile by M-tile as their MMAs complete
-    bf16* save_cur = a.db_bufs ? a.db_bufs[db] : nullptr;
-    bf16* save_next = (a.db_bufs && db + 1 < a.R * 3) ? a.db_bufs[db + 1] : nullptr;
+    const bool saving = a.db_bufs && n < a.save_count;  // activations are kept for the first save_count samples only
+    bf16* save_cur = saving ? a.db_bufs[db] : nullptr;
+    bf16* save_next = (saving && db + 1 < a.R * 3) ? a.db_bufs[db + 1] : nullptr;
 #pragma unroll
     for (int mt = 0; mt < TNMT; ++mt) {
       mbar_wait(smem_u32(&mbar[mt]), L & 1);
@@ -502,7 +504,7 @@ bool trunk_fused_supported(int F, int Hc, int R, int bf) { return bf && F == TF 
 // x_in: conv1 output view; y_out: trunk output (pitch out_pitch); db_bufs_dev: device array of 3R
 // concat-buffer pointers (pitch 80) or nullptr when the activations need not be kept.
 int trunk_fwd_fused(const void* x_in, int in_pitch, int in_coff, void* y_out, int out_pitch, void* const* db_bufs_dev,
-                    const void* w_umma, const float* bias, int R, int B, cudaStream_t st) {
+                    const void* w_umma, const float* bias, int R, int B, int save_count, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     DG_CUDA(cudaFuncSetAttribute(trunk_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
@@ -514,6 +516,7 @@ int trunk_fwd_fused(const void* x_in, int in_pitch, int in_coff, void* y_out, in
   a.y_out = (bf16*)y_out; a.out_pitch = out_pitch;
   a.db_bufs = (bf16* const*)db_bufs_dev;
   a.w = (const bf16*)w_umma; a.bias = bias; a.R = R; a.B = B; a.order = g_tune[3];
+  a.save_count = db_bufs_dev ? save_count : 0;
   a.trace = nullptr;
   static const bool tracing = getenv("DG_TRUNK_TRACE") != nullptr;
   if (tracing) { cudaMalloc(&a.trace, 32 * 8 * 8); cudaMemset(a.trace, 0, 32 * 8 * 8); }

@@ -156,11 +156,15 @@ int dg_generator_step(dg_generator* g, dg_critic* c, const dg_hyper* hp,
  * updates see the same generator weights, so fake = G(coarse) for the next `total` samples (several batches,
  * concatenated along the batch axis, total <= max_batch) is computed in ONE pass and kept in the generator's
  * output buffer until the next generator forward.  dg_critic_step_fake is dg_critic_step with the fake taken
- * from samples [fake_offset, fake_offset + batch) of that buffer instead of being recomputed. */
-int dg_generator_lookahead(dg_generator* g, const float* coarse, int total, void* stream);
+ * from samples [fake_offset, fake_offset + batch) of that buffer instead of being recomputed.  The first
+ * `save_first` samples also keep their activations, so that the generator iteration on that batch
+ * (dg_generator_step_saved = dg_generator_step without the forward) needs no second forward. */
+int dg_generator_lookahead(dg_generator* g, const float* coarse, int total, int save_first, void* stream);
 int dg_critic_step_fake(dg_generator* g, dg_critic* c, const dg_hyper* hp, int fake_offset,
                         const float* fine, const float* alpha, int batch,
                         float* c_grads_flat, float* scalars, void* stream);
+int dg_generator_step_saved(dg_generator* g, dg_critic* c, const dg_hyper* hp, const float* fine, int batch,
+                            float* g_grads_flat, float* scalars_out, void* stream);
 
 /* ---- unit-testable conv primitives (NCHW fp32 in/out, OIHW fp32 weights)
  * 3x3, padding 1, stride 1 or 2.  `precision` selects the kernel family.
