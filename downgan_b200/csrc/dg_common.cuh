@@ -118,6 +118,7 @@ struct ConvOp {
   int shuffle = SHUF_NONE;
   // tcgen05 path extras (bf16 mode)
   const void* w_umma = nullptr;  // packed bf16 weights for the tcgen05 kernel (null -> direct kernel)
+  int narrow_ok = 0;             // Co < 16: w_umma holds a zero-padded 16-column image (set only where one is packed)
 };
 
 struct WgradOp {

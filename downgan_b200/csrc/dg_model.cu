@@ -58,9 +58,11 @@ int run_wgrad(const WgradOp& w, cudaStream_t st) {
 }
 
 int run_conv(const ConvOp& op, cudaStream_t st) {
-  if (g_tune[6] && conv_l1_supported(op)) return conv_l1(op, st);
-  if (conv_skinny_supported(op)) return conv_skinny(op, st);
   static const bool ws = !(getenv("DG_CONV_WS") && atoi(getenv("DG_CONV_WS")) == 0);
+  if (g_tune[6] && conv_l1_supported(op)) return conv_l1(op, st);
+  if (op.Co < 16 && op.narrow_ok && ws && g_tune[0] && g_tune[7] && op.w_umma && umma_ws_supported(op))
+    return conv_umma_ws(op, st);  // narrow output on tensor cores
+  if (conv_skinny_supported(op)) return conv_skinny(op, st);
   if (ws && g_tune[0] && op.w_umma && umma_ws_supported(op)) return conv_umma_ws(op, st);
   if (op.w_umma && umma_supported(op)) return conv_umma(op, st);
   return conv_direct(op, st);
@@ -171,6 +173,8 @@ static int upload_utable(std::vector<void*>& pool, const std::vector<UmmaPackDes
   return 0;
 }
 static inline bool umma_ok(int ci, int co) { return ci % 16 == 0 && co % 16 == 0 && co <= 256; }
+// operand image usable by the TMA conv kernel: narrow outputs (Co < 16) run as N = 16 with zero pad columns
+static inline bool umma_img_ok(int ci, int co) { return ci % 16 == 0 && co <= 256 && (co % 16 == 0 || co < 16); }
 
 extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator** out) {
   DG_CHECK(cfg && out, "dg_generator_create: null argument");
@@ -193,7 +197,7 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
   for (auto& l : g->layers) {
     l.pk_off = pk; pk += (long long)packed_w_elems(l.Ci, l.Co);
     PackDesc d{}; d.src_off = l.w_off; d.dst_off = l.pk_off; d.Ci = l.Ci; d.Co = l.Co; d.CoP = round_up(l.Co, 16); d.mode = 0;
-    d.umma = g->bf && umma_ok(l.Ci, l.Co);
+    d.umma = g->bf && umma_img_ok(l.Ci, l.Co);
     tf.push_back(d);
     maxf = std::max(maxf, l.Ci * l.Co * 9);
   }
@@ -399,6 +403,7 @@ static int gen_forward_internal(dg_generator* g, int B, int save_count, cudaStre
   }
   {
     ConvOp op = conv(g->idx_c32(), g->act(g->c30, F), H, tv(g->fake, 0, g->Cout));
+    op.narrow_ok = g->bf && umma_img_ok(F, g->Cout);
     DG_TRY(run_conv(op, st));
   }
   g->saved_batch = save_count;
@@ -687,13 +692,13 @@ extern "C" int dg_critic_create(const dg_critic_config* cfg, dg_critic** out) {
     Layer& l = c->L[i];
     l.pk_off = pk; pk += (long long)packed_w_elems(l.Ci, l.Co);
     PackDesc d{}; d.src_off = l.w_off; d.dst_off = l.pk_off; d.Ci = l.Ci; d.Co = l.Co; d.CoP = round_up(l.Co, 16); d.mode = 0;
-    d.umma = c->bf && umma_ok(l.Ci, l.Co);
+    d.umma = c->bf && umma_img_ok(l.Ci, l.Co);
     tf.push_back(d);
     maxf = std::max(maxf, l.Ci * l.Co * 9);
     l.pkd_off = pkd; pkd += (long long)packed_w_elems(l.Co, l.Ci);
     PackDesc e{}; e.src_off = l.w_off; e.dst_off = l.pkd_off; e.Ci = l.Ci; e.Co = l.Co; e.CoP = round_up(l.Ci, 16);
     e.mode = (l.stride == 2) ? 2 : 1;
-    e.umma = c->bf && umma_ok(l.Co, l.Ci);
+    e.umma = c->bf && umma_img_ok(l.Co, l.Ci);
     td.push_back(e);
     maxd = std::max(maxd, l.Ci * l.Co * 9);
   }
@@ -818,6 +823,7 @@ static int critic_backward_chain(dg_critic* c, int NB, int n0, int n1, float* g_
     op.x = tv_batch(c->act(c->dz[1], l.Co), c->pix(0), n0); op.Hin = c->Hout[0]; op.Win = c->Hout[0]; op.Ci = l.Co;
     op.y = tv(g_out, 0, l.Ci); op.Hout = c->Hin[0]; op.Wout = c->Hin[0]; op.Co = l.Ci;
     op.B = n1; op.w = c->pkd + l.pkd_off;
+    if (c->bf && umma_img_ok(l.Co, l.Ci)) { op.w_umma = c->pkd_u + l.pkd_off; op.narrow_ok = 1; }
     DG_TRY(run_conv(op, st));
   }
   return 0;

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_ws_kernel(const __grid_con
     for (int row = tid; row < a.NT; row += WS_THREADS) {
       const int colp = co0 + row;
       const int src = a.perm ? 4 * (colp % a.Fsh) + colp / a.Fsh : colp;
-      sbias[row] = op.bias ? op.bias[src] : 0.f;
+      sbias[row] = (op.bias && src < op.Co) ? op.bias[src] : 0.f;
     }
   }
   cp_async_wait_all();
@@ -423,7 +423,20 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_ws_kernel(const __grid_con
               for (int j = 0; j < 16; ++j) v[j] *= (t[j] > 0.f ? 1.f : op.slope);
             }
           }
-          if (op.shuffle == SHUF_NONE) {
+          if (op.Co < 16) {  // narrow layer: only the first Co columns exist
+            const size_t o = pix * op.y.pitch + op.y.coff;
+            if (op.y.bf) {
+#pragma unroll
+              for (int j = 0; j < 15; ++j)  // static indices: v[] must stay in registers
+                if (j < op.Co) ((bf16*)op.y.p)[o + j] = __float2bfloat16_rn(v[j]);
+            } else if (op.Co == 2 && ((o & 1) == 0)) {
+              *reinterpret_cast<float2*>((float*)op.y.p + o) = make_float2(v[0], v[1]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 15; ++j)
+                if (j < op.Co) ((float*)op.y.p)[o + j] = v[j];
+            }
+          } else if (op.shuffle == SHUF_NONE) {
             st16f(op.y, pix * op.y.pitch + op.y.coff + co0 + nc, v);
           } else if (op.shuffle == SHUF_PIXEL) {  // (i,j)-major columns: one piece = 16 channels of one shuffled pixel
             const int colp = co0 + nc;
@@ -458,7 +471,9 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_ws_kernel(const __grid_con
 
 bool plan_ws(const ConvOp& op, WsArgs& a, int& ctas_per_sm) {
   if (!op.w_umma || !op.x.bf) return false;
-  if (op.Ci % 16 || op.Co % 16 || op.Co > 256) return false;
+  const bool narrow = op.Co < 16;  // e.g. conv3.2 (16 -> 2): N = 16 MMA columns, only Co of them stored
+  if (op.Ci % 16 || (!narrow && op.Co % 16) || op.Co > 256 || op.Co < 1) return false;
+  if (narrow && (!op.narrow_ok || op.shuffle != SHUF_NONE || op.r1.p || op.r2.p || op.act == ACT_MASK)) return false;
   if (op.Ci != 16 && op.Ci != 32 && op.Ci != 64 && op.Ci != 128) return false;  // KCS template instances
   if (op.x.pitch % 8 || op.x.coff % 8) return false;
   int mode;
@@ -477,7 +492,7 @@ bool plan_ws(const ConvOp& op, WsArgs& a, int& ctas_per_sm) {
     return t.bf ? (t.pitch % 8 == 0 && t.coff % 8 == 0) : (t.pitch % 4 == 0 && t.coff % 4 == 0);
   };
   if (!aligned(op.r1) || !aligned(op.r2) || !aligned(op.mask)) return false;
-  if (op.shuffle != SHUF_UNPIXEL && !aligned(op.y)) return false;
+  if (op.shuffle != SHUF_UNPIXEL && !narrow && !aligned(op.y)) return false;
   const int perm = op.shuffle == SHUF_PIXEL;
   if (perm && (op.Co % 64)) return false;  // Co/4 shuffled channels in whole 16-column pieces
   const int Ht = (mode == S2_DGRAD) ? op.Hin : op.Hout, Wt = (mode == S2_DGRAD) ? op.Win : op.Wout;
@@ -494,12 +509,13 @@ bool plan_ws(const ConvOp& op, WsArgs& a, int& ctas_per_sm) {
   double best = 1e300;
   int bestTH = 0, best_mt = 0, best_stage = 0, best_cps = 1, NT = 0;
   size_t best_over = 0;
+  const int CoE = narrow ? 16 : op.Co;  // MMA columns
   for (int cand : {256, 128, 64, 32, 16}) {
-    if (cand > op.Co || op.Co % cand) continue;
+    if (cand > CoE || CoE % cand) continue;
     if (ncls * cand > 256) continue;
     const size_t wbytes = (size_t)9 * op.Ci * cand * 2;
     if (wbytes > 112 * 1024) continue;
-    const int n_chunks = op.Co / cand;
+    const int n_chunks = CoE / cand;
     for (int cps = 2; cps >= 1; --cps) {
       const size_t budget = ((cps == 2) ? (size_t)(113 * 1024 - 2048) : (size_t)WS_MAX_SMEM) - 1024;
       const int acc_max = (cps == 2) ? 128 : 256;
@@ -608,7 +624,7 @@ int conv_umma_ws(const ConvOp& op, cudaStream_t st) {
   const double taps = op.transposed ? 2.25 : 9.0;
   Prof prof(PC_CONV_UMMA, 2.0 * total * op.Co * op.Ci * taps,
             (double)total * op.Co * (op.y.bf ? 2 : 4) + (double)op.B * op.Hin * op.Win * op.Ci * 2.0, st);
-  const int n_chunks = op.Co / a.NT;
+  const int n_chunks = std::max(1, op.Co / a.NT);
   int gx = std::max(1, (148 * cps) / n_chunks);
   gx = std::min(gx, a.tiles_total);
   // even out the tail: every CTA walks the same number of tiles (or one fewer)

@@ -197,7 +197,8 @@ int dg_profile_report(double* out, int n_classes);
  * kernel (1) or the cp.async kernels (0); key 3: trunk MMA issue order (0, 1, 2); key 4: dense-block weight
  * gradients on the TMA-fed kernel as channel blocks (1) or the cp.async batched kernel (0); key 5: programmatic
  * dependent launch of the TMA-fed conv / weight-gradient kernels (1) or plain stream order (0); key 6: tcgen05 kernel
- * for the few-channel fp32 boundary conv (1) or the CUDA-core kernel (0).  Returns the previous value, or DG_ERR_INVALID for an unknown key. */
+ * for the few-channel fp32 boundary conv (1) or the CUDA-core kernel (0); key 7: narrow-output convs (Co < 16) on the
+ * TMA-fed kernel with zero pad columns (1) or the CUDA-core kernel (0).  Returns the previous value, or DG_ERR_INVALID for an unknown key. */
 #define DG_TUNE_KEYS 8
 int dg_set_tuning(int key, int value);
 
