@@ -537,7 +537,9 @@ bool plan_ws(const ConvOp& op, WsArgs& a, int& ctas_per_sm) {
         const double waves = (double)((tiles_total + G - 1) / G);
         const double in_b = (double)(TH + hrows) * PW * nsub * op.Ci * 2.0;
         const double out_b = (double)n_mt * 128 * ncls * cand * 2.0;
-        const double cost = waves * cps * (in_b + out_b + 6144.0) * (cps == 2 ? 0.85 : 1.0) * (stages >= 3 ? 1.0 : 1.15);
+        static const double cps2 = getenv("DG_WS_CPS2") ? atof(getenv("DG_WS_CPS2")) : 0.7;  // measured (bench sweep)
+        static const double fixed = getenv("DG_WS_FIXED") ? atof(getenv("DG_WS_FIXED")) : 6144.0;
+        const double cost = waves * cps * (in_b + out_b + fixed) * (cps == 2 ? cps2 : 1.0) * (stages >= 3 ? 1.0 : 1.15);
         if (cost < best - 1e-9) {
           best = cost; bestTH = TH; best_mt = n_mt; best_stage = stages; best_cps = cps; NT = cand; best_over = over;
         }
