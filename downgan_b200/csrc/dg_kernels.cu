@@ -330,12 +330,12 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(TV dy, size_t pixels, i
     }
   };
   size_t p = p0 + pl;
-  for (; p + 3 * (size_t)npl < p1; p += 4 * (size_t)npl) {
-    const uint4 q0 = *reinterpret_cast<const uint4*>(base + p * dy.pitch);
-    const uint4 q1 = *reinterpret_cast<const uint4*>(base + (p + npl) * dy.pitch);
-    const uint4 q2 = *reinterpret_cast<const uint4*>(base + (p + 2 * (size_t)npl) * dy.pitch);
-    const uint4 q3 = *reinterpret_cast<const uint4*>(base + (p + 3 * (size_t)npl) * dy.pitch);
-    add8(q0); add8(q1); add8(q2); add8(q3);
+  for (; p + 7 * (size_t)npl < p1; p += 8 * (size_t)npl) {  // eight 16-byte loads in flight per thread
+    uint4 q[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) q[u] = *reinterpret_cast<const uint4*>(base + (p + (size_t)u * npl) * dy.pitch);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) add8(q[u]);
   }
   for (; p < p1; p += npl) add8(*reinterpret_cast<const uint4*>(base + p * dy.pitch));
 #pragma unroll
@@ -365,7 +365,7 @@ int colsum(TV dy, size_t pixels, int C, float* out, cudaStream_t st) {
   const bool vec = dy.bf && (C == 16 || C == 32 || C == 64 || C == 128 || C == 256) && dy.pitch % 8 == 0 && dy.coff % 8 == 0 &&
                    pixels >= 4096;
   if (vec) {
-    size_t ppb = (pixels + 148 * 4 - 1) / (148 * 4);
+    size_t ppb = (pixels + 148 * 6 - 1) / (148 * 6);
     if (ppb < 256) ppb = 256;
     const unsigned grid = (unsigned)((pixels + ppb - 1) / ppb);
     colsum_vec_kernel<<<grid, 256, 0, st>>>(dy, pixels, C, out, ppb);

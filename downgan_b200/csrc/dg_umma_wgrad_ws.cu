@@ -36,7 +36,14 @@ using namespace um;
 constexpr int WW_THREADS = 128;
 constexpr int WW_MAX_STAGE = 4;
 constexpr int WW_MAX_SMEM = 227 * 1024 - 3072;
-enum WMode { W_S1_FOLD = 0, W_S1_TAPS = 1, W_S2_TAPS = 2 };
+enum WMode { W_S1_FOLD = 0, W_S1_TAPS = 1, W_S2_TAPS = 2, W_S2_FOLD = 3 };
+// stride 2, Ci <= 32: the taps that are consecutive positions of the SAME parity sub-image are folded into M
+// (two atoms): 6 MMAs per K-step instead of 9.  unit -> {sub-image, row shift (x PW), col shift, taps of atom 0 / 1}
+__constant__ int c_s2f_sub[6] = {3, 3, 1, 2, 2, 0};
+__constant__ int c_s2f_dy[6] = {0, 1, 1, 0, 1, 1};
+__constant__ int c_s2f_dx[6] = {0, 0, 0, 1, 1, 1};
+__constant__ int c_s2f_tap0[6] = {0, 6, 3, 1, 7, 4};
+__constant__ int c_s2f_tap1[6] = {2, 8, 5, -1, -1, -1};
 
 struct WwArgs {
   WgradOp op;
@@ -98,7 +105,8 @@ template <int MODE>
 __device__ __forceinline__ void wgrad_ws_body(const CUtensorMap* mapx_p, const CUtensorMap* mapd_p, const WwArgs& a, uint8_t* smem,
                                               uint64_t* bars, uint32_t* tmem_slot_p) {
   uint32_t& tmem_slot = *tmem_slot_p;
-  constexpr int UNITS = (MODE == W_S1_FOLD) ? 3 : 9;
+  constexpr int UNITS = (MODE == W_S1_FOLD) ? 3 : (MODE == W_S2_FOLD ? 6 : 9);
+  constexpr bool STRIDE2 = (MODE == W_S2_TAPS || MODE == W_S2_FOLD);
   const WgradOp& op = a.op;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int co0 = blockIdx.y * a.NT;
@@ -144,9 +152,9 @@ __device__ __forceinline__ void wgrad_ws_body(const CUtensorMap* mapx_p, const C
       if (elect_one_sync_w()) {
         mbar_expect_tx(full_bar(s), a.tx_bytes);
 #pragma unroll
-        for (int sub = 0; sub < ((MODE == W_S2_TAPS) ? 4 : 1); ++sub) {
+        for (int sub = 0; sub < (STRIDE2 ? 4 : 1); ++sub) {
           int cx, cy;
-          if (MODE == W_S2_TAPS) { cx = -2 + (sub & 1); cy = 2 * (y0 - 1) + (sub >> 1); }
+          if (STRIDE2) { cx = -2 + (sub & 1); cy = 2 * (y0 - 1) + (sub >> 1); }
           else { cx = -1; cy = y0 - 1; }
           for (int blk = 0; blk < a.nblkx; ++blk)
             tma_load_4d(sx + (sub * a.nblkx + blk) * a.xreg, mapx_p, blk * 64, cx, cy, n, full_bar(s));
@@ -168,6 +176,8 @@ __device__ __forceinline__ void wgrad_ws_body(const CUtensorMap* mapx_p, const C
     for (int u = 0; u < UNITS; ++u) {
       if (MODE == W_S1_FOLD) {
         uoff[u] = (uint32_t)(u * a.PW) * xr16;
+      } else if (MODE == W_S2_FOLD) {
+        uoff[u] = c_s2f_sub[u] * subA + (uint32_t)(c_s2f_dy[u] * a.PW + c_s2f_dx[u]) * xr16;
       } else {
         const int ky = u / 3, kx = u % 3;
         if (MODE == W_S1_TAPS) {
@@ -207,14 +217,18 @@ __device__ __forceinline__ void wgrad_ws_body(const CUtensorMap* mapx_p, const C
     else row = (lane < 16) ? warp * 16 + lane : -1;
     int kx = 0, ci = row;
     bool valid = row >= 0;
-    if (MODE == W_S1_FOLD) {
+    if (MODE == W_S1_FOLD || MODE == W_S2_FOLD) {
       kx = row / op.Ci; ci = row - kx * op.Ci;
-      valid = valid && kx < 3;
+      valid = valid && kx < ((MODE == W_S1_FOLD) ? 3 : 2);
     } else {
       valid = valid && row < op.Ci;
     }
+    const bool valid_row = valid;
     for (int u = 0; u < UNITS; ++u) {
-      const int tap = (MODE == W_S1_FOLD) ? u * 3 + kx : u;
+      int tap;
+      if (MODE == W_S1_FOLD) tap = u * 3 + kx;
+      else if (MODE == W_S2_FOLD) { tap = (kx == 0) ? c_s2f_tap0[u] : c_s2f_tap1[u]; valid = valid_row && tap >= 0; if (tap < 0) tap = 0; }
+      else tap = u;
       for (int nc = 0; nc < a.NT; nc += 16) {
         float v[16];
         tmem_ld16(tmem + lane_base + u * a.NT + nc, v);
@@ -267,8 +281,8 @@ bool plan_ww(const WgradOp& op, WwArgs& a) {
   if (s == 1) { if (op.Hin != op.Hout || op.Win != op.Wout) return false; }
   else if (s == 2) { if (op.Hin != 2 * op.Hout || op.Win != 2 * op.Wout) return false; }
   else return false;
-  const int mode = (s == 2) ? W_S2_TAPS : (3 * op.Ci <= 128 ? W_S1_FOLD : W_S1_TAPS);
-  const int units = (mode == W_S1_FOLD) ? 3 : 9;
+  const int mode = (s == 2) ? (op.Ci <= 32 ? W_S2_FOLD : W_S2_TAPS) : (3 * op.Ci <= 128 ? W_S1_FOLD : W_S1_TAPS);
+  const int units = (mode == W_S1_FOLD) ? 3 : (mode == W_S2_FOLD ? 6 : 9);
   int NT = 0;
   for (int cand : {64, 32, 16})
     if (op.Co % cand == 0 && units * cand <= 512) { NT = cand; break; }
@@ -315,14 +329,16 @@ bool plan_ww(const WgradOp& op, WwArgs& a) {
   a = b;
   a.op = op;
   a.mode = mode; a.units = units;
-  a.M = (mode == W_S1_FOLD) ? (3 * op.Ci <= 64 ? 64 : 128) : (op.Ci <= 64 ? 64 : 128);
+  a.M = (mode == W_S1_FOLD) ? (3 * op.Ci <= 64 ? 64 : 128) : (mode == W_S2_FOLD ? 64 : (op.Ci <= 64 ? 64 : 128));
   a.PW = PW; a.NT = NT; a.CoP = round_up(op.Co, 16);
   a.xrow = xrow; a.drow = drow; a.nblkx = nblkx; a.nsub = nsub;
   a.tiles_per_img = (op.Hout + a.TH - 1) / a.TH;
   a.tiles_total = a.tiles_per_img * op.B;
   a.nstage = (int)std::min<size_t>(WW_MAX_STAGE, ((size_t)WW_MAX_SMEM - 1024) / a.stage_bytes);
   // two CTAs per SM when their rings fit side by side (more loads in flight, two MMA issue streams)
-  if ((size_t)a.nstage * a.stage_bytes + 1024 > 112 * 1024 && 3 * (size_t)a.stage_bytes + 1024 <= 112 * 1024) a.nstage = 3;
+  if ((size_t)a.nstage * a.stage_bytes + 1024 > 112 * 1024) {
+    if (3 * (size_t)a.stage_bytes + 1024 <= 112 * 1024) a.nstage = 3;  // (two slots per CTA measured slower)
+  }
   int pc = 32;
   while (pc < units * NT) pc <<= 1;
   a.tmem_cols = pc;
@@ -413,6 +429,7 @@ int wgrad_ws(const WgradOp& op, cudaStream_t st) {
   } while (0)
   if (a.mode == W_S1_FOLD) WW_LAUNCH(W_S1_FOLD);
   else if (a.mode == W_S1_TAPS) WW_LAUNCH(W_S1_TAPS);
+  else if (a.mode == W_S2_FOLD) WW_LAUNCH(W_S2_FOLD);
   else WW_LAUNCH(W_S2_TAPS);
 #undef WW_LAUNCH
   }
@@ -434,8 +451,8 @@ int wgrad_ws_batched(const WgradOp* ops, int n, void* table_dev, std::vector<uns
   CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(tab.data());
   WwArgs* args = reinterpret_cast<WwArgs*>(tab.data() + maps_bytes);
   int* order = reinterpret_cast<int*>(tab.data() + maps_bytes + args_bytes);
-  unsigned smem[3] = {0, 0, 0}, gx[3] = {1, 1, 1};
-  int count[3] = {0, 0, 0};
+  unsigned smem[4] = {0, 0, 0, 0}, gx[4] = {1, 1, 1, 1};
+  int count[4] = {0, 0, 0, 0};
   double flops = 0, bytes = 0;
   for (int i = 0; i < n; ++i) {
     WwArgs a;
@@ -458,8 +475,8 @@ int wgrad_ws_batched(const WgradOp* ops, int n, void* table_dev, std::vector<uns
     flops += 2.0 * total * ops[i].Co * ops[i].Ci * 9.0;
     bytes += total * ops[i].Co * 2.0 + (double)ops[i].B * ops[i].Hin * ops[i].Win * ops[i].Ci * 2.0;
   }
-  int start[3], pos = 0;
-  for (int m = 0; m < 3; ++m) {
+  int start[4], pos = 0;
+  for (int m = 0; m < 4; ++m) {
     start[m] = pos;
     for (int i = 0; i < n; ++i)
       if (args[i].mode == m) order[pos++] = i;
@@ -490,6 +507,7 @@ int wgrad_ws_batched(const WgradOp* ops, int n, void* table_dev, std::vector<uns
   WWB_LAUNCH(W_S1_FOLD);
   WWB_LAUNCH(W_S1_TAPS);
   WWB_LAUNCH(W_S2_TAPS);
+  WWB_LAUNCH(W_S2_FOLD);
 #undef WWB_LAUNCH
   return 0;
 }
