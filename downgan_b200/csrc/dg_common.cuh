@@ -128,6 +128,7 @@ struct WgradOp {
   int stride = 1;
   float* dw = nullptr;   // packed [9][Ci][CoP] fp32, accumulated with atomics
   float* dbias = nullptr;  // [Co] accumulated, may be null
+  int dbias_B = 0;         // > 0: the bias gradient sums the first dbias_B samples only (0: all B)
   // channel-block ops (dg_umma_wgrad_ws.cu): this op covers input channels [dw_ci_off, dw_ci_off + Ci) of a layer with
   // dw_ci_total input channels; dw rows are tap * dw_ci_total + dw_ci_off + ci   (0 / 0: the op is the whole layer)
   int dw_ci_total = 0, dw_ci_off = 0;
@@ -166,6 +167,9 @@ int scale_add(TV dst, TV a, float sa, TV b, float sb, size_t pixels, int C, cuda
 int build_critic_input(const float* real_nchw, const float* fake, int fake_is_nchw, const float* alpha,
                        float* dst_nhwc, int B, int C, int H, int W, int with_interp, cudaStream_t st);
 int colsum(TV dy, size_t pixels, int C, float* out, cudaStream_t st);
+// Streams the library creates for overlapped work get their own column-sum scratch slot (1 or 2); every other
+// stream shares slot 0 (one caller stream at a time per process, include/downgan_b200.h threading note).
+void register_side_stream(cudaStream_t st, int slot);
 
 // linear layers (critic classifier)
 int fc_fwd(const void* x, int x_bf, const float* w, const float* bias, float* y, int NB, int K, int N,

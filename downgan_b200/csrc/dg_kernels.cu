@@ -272,13 +272,26 @@ int wgrad_direct(const WgradOp& op, cudaStream_t st) {
 // column sums over pixels (bias gradients).  Block partials are combined in fp64 by the last
 // block to finish: critic bias gradients are sums of cancelling real/fake halves, and an fp32
 // atomic chain loses ~1e-3 of the result there.  out[c] += sum.
-constexpr int COLSUM_MAX_BLOCKS = 1024, COLSUM_MAX_C = 256;
-__device__ float g_colsum_part[COLSUM_MAX_BLOCKS * COLSUM_MAX_C];
-__device__ unsigned int g_colsum_done = 0;
+// The partial buffer and the completion counter exist once per SLOT: launches on the library's side streams
+// (register_side_stream) use their own slot, so a column sum there may overlap one on the caller's stream.
+constexpr int COLSUM_MAX_BLOCKS = 1024, COLSUM_MAX_C = 256, COLSUM_SLOTS = 3;
+__device__ float g_colsum_parts[COLSUM_SLOTS][COLSUM_MAX_BLOCKS * COLSUM_MAX_C];
+__device__ unsigned int g_colsum_dones[COLSUM_SLOTS] = {0, 0, 0};
+static cudaStream_t g_side_streams[COLSUM_SLOTS] = {nullptr, nullptr, nullptr};
+void register_side_stream(cudaStream_t st, int slot) {
+  if (slot >= 1 && slot < COLSUM_SLOTS) g_side_streams[slot] = st;
+}
+static int colsum_slot(cudaStream_t st) {
+  for (int i = 1; i < COLSUM_SLOTS; ++i)
+    if (g_side_streams[i] && g_side_streams[i] == st) return i;
+  return 0;
+}
 
-__global__ void colsum_kernel(TV dy, size_t pixels, int C, float* out, size_t pix_per_block) {
+__global__ void colsum_kernel(TV dy, size_t pixels, int C, float* out, size_t pix_per_block, int slot) {
   __shared__ float sh[8][33];
   __shared__ bool last;
+  float* const g_colsum_part = g_colsum_parts[slot];
+  unsigned int& g_colsum_done = g_colsum_dones[slot];
   const size_t p0 = (size_t)blockIdx.x * pix_per_block;
   const size_t p1 = min(pixels, p0 + pix_per_block);
   for (int c0 = 0; c0 < C; c0 += 32) {
@@ -310,9 +323,11 @@ __global__ void colsum_kernel(TV dy, size_t pixels, int C, float* out, size_t pi
 }
 // bf16 rows with C in {16,32,64,128,256}: 16-byte loads (8 channels per thread), four pixels in flight per
 // thread; same fp64 last-block combine as colsum_kernel.
-__global__ void __launch_bounds__(256) colsum_vec_kernel(TV dy, size_t pixels, int C, float* out, size_t pix_per_block) {
+__global__ void __launch_bounds__(256) colsum_vec_kernel(TV dy, size_t pixels, int C, float* out, size_t pix_per_block, int slot) {
   __shared__ float sh[256 * 8];
   __shared__ bool last;
+  float* const g_colsum_part = g_colsum_parts[slot];
+  unsigned int& g_colsum_done = g_colsum_dones[slot];
   const int cpp = C >> 3;              // 16-byte chunks per pixel (a power of two <= 32)
   const int chunk = threadIdx.x & (cpp - 1), pl = threadIdx.x / cpp, npl = 256 / cpp;
   const size_t p0 = (size_t)blockIdx.x * pix_per_block;
@@ -368,14 +383,14 @@ int colsum(TV dy, size_t pixels, int C, float* out, cudaStream_t st) {
     size_t ppb = (pixels + 148 * 6 - 1) / (148 * 6);
     if (ppb < 256) ppb = 256;
     const unsigned grid = (unsigned)((pixels + ppb - 1) / ppb);
-    colsum_vec_kernel<<<grid, 256, 0, st>>>(dy, pixels, C, out, ppb);
+    colsum_vec_kernel<<<grid, 256, 0, st>>>(dy, pixels, C, out, ppb, colsum_slot(st));
     DG_LAUNCH_CHECK();
     return 0;
   }
   size_t ppb = (pixels + 148 * 4 - 1) / (148 * 4);
   if (ppb < 64) ppb = 64;
   unsigned grid = (unsigned)((pixels + ppb - 1) / ppb);
-  colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(dy, pixels, C, out, ppb);
+  colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(dy, pixels, C, out, ppb, colsum_slot(st));
   DG_LAUNCH_CHECK();
   return 0;
 }
@@ -776,7 +791,7 @@ __global__ void __launch_bounds__(256) fc_wgrad_kernel(const float* __restrict__
   }
 #pragma unroll
   for (int jj = 0; jj < FCW_BJ; ++jj)
-    if (j0 + jj < N) dw[(size_t)(j0 + jj) * K + k] += acc[jj];
+    if (j0 + jj < N) atomicAdd(&dw[(size_t)(j0 + jj) * K + k], acc[jj]);  // (two sample ranges may accumulate concurrently)
 }
 int fc_wgrad(const float* dz, const void* x, int x_bf, float* dw, int NB, int K, int N, cudaStream_t st) {
   DG_CHECK(NB <= FCW_MAXB, "fc_wgrad: batch %d > %d", NB, FCW_MAXB);
@@ -1057,7 +1072,7 @@ CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank,
   return fn(map, dt, rank, addr, dims, strides, box, estr, il, sw, l2, oob);
 }
 }  // namespace dg
-namespace dg { int g_tune[DG_TUNE_KEYS] = {1, 1, 1, 0, 1, 0, 1, 1}; }  // see include/downgan_b200.h: dg_set_tuning
+namespace dg { int g_tune[DG_TUNE_KEYS] = {1, 1, 1, 0, 1, 0, 1, 1, 1, 1}; }  // see include/downgan_b200.h: dg_set_tuning
 extern "C" int dg_set_tuning(int key, int value) {
   if (key < 0 || key >= DG_TUNE_KEYS) { dg::set_error("dg_set_tuning: unknown key %d", key); return DG_ERR_INVALID; }
   const int prev = dg::g_tune[key];

@@ -31,6 +31,45 @@ struct DevBuf {
   size_t bytes = 0;
 };
 
+// A library-owned stream for work that only has to be finished by the end of an API call (weight gradients and
+// their bias column sums): forked from / joined to the caller's stream with events, so the call keeps plain
+// stream-order semantics for the caller.  Non-blocking, so it also overlaps a caller on the legacy default stream.
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr, aux_ev = nullptr;
+  bool dirty = false;  // work has been enqueued on `s` since the last join
+  int create(int colsum_slot) {
+    DG_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    DG_CUDA(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+    DG_CUDA(cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming));
+    DG_CUDA(cudaEventCreateWithFlags(&aux_ev, cudaEventDisableTiming));
+    register_side_stream(s, colsum_slot);
+    return 0;
+  }
+  void destroy() {
+    if (fork_ev) cudaEventDestroy(fork_ev);
+    if (join_ev) cudaEventDestroy(join_ev);
+    if (aux_ev) cudaEventDestroy(aux_ev);
+    if (s) cudaStreamDestroy(s);
+    s = nullptr; fork_ev = join_ev = aux_ev = nullptr;
+  }
+  // everything enqueued on `st` so far happens before what is enqueued on the side stream next
+  int fork(cudaStream_t st) {
+    DG_CUDA(cudaEventRecord(fork_ev, st));
+    DG_CUDA(cudaStreamWaitEvent(s, fork_ev, 0));
+    dirty = true;
+    return 0;
+  }
+  // everything enqueued on the side stream so far happens before what is enqueued on `st` next
+  int join(cudaStream_t st) {
+    if (!dirty) return 0;
+    DG_CUDA(cudaEventRecord(join_ev, s));
+    DG_CUDA(cudaStreamWaitEvent(st, join_ev, 0));
+    dirty = false;
+    return 0;
+  }
+};
+
 int dev_alloc(std::vector<void*>& pool, void** out, size_t bytes) {
   if (bytes == 0) bytes = 16;
   void* p = nullptr;
@@ -49,8 +88,16 @@ int dev_alloc(std::vector<void*>& pool, void** out, size_t bytes) {
   return 0;
 }
 
-int run_wgrad(const WgradOp& w, cudaStream_t st) {
-  if (g_tune[2] && wgrad_ws_supported(w)) return wgrad_ws(w, st);
+int run_wgrad(const WgradOp& w0, cudaStream_t st) {
+  WgradOp w = w0;
+  // bias gradient over a leading part of the batch: only the first-layer tcgen05 kernel folds it in; elsewhere it is
+  // a column sum over those samples
+  const bool ws_path = g_tune[2] && wgrad_ws_supported(w);
+  if (w.dbias && w.dbias_B > 0 && w.dbias_B < w.B && (ws_path || !wgrad_im2col_supported(w))) {
+    DG_TRY(colsum(w.dy, (size_t)w.dbias_B * w.Hout * w.Wout, w.Co, w.dbias, st));
+    w.dbias = nullptr;
+  }
+  if (ws_path) return wgrad_ws(w, st);
   if (wgrad_im2col_supported(w)) return wgrad_im2col(w, st);
   if (wgrad_skinny_supported(w)) return wgrad_skinny(w, st);
   if (wgrad_umma_supported(w)) return wgrad_umma(w, st);
@@ -109,6 +156,9 @@ struct dg_generator {
   void* wgws_table_dev = nullptr; // same for the TMA-fed kernel (plans + tensor maps)
   std::vector<unsigned char> wgws_shadow;
   void *D = nullptr, *gR = nullptr, *gx0 = nullptr, *gx1 = nullptr, *gT1 = nullptr, *gA = nullptr, *gB = nullptr;
+  std::vector<void*> gU;   // gU[u]: dz of upsample stage u, (B, Hc<<u, Hc<<u, 4F); one buffer per stage (no ping-pong), so
+                           // weight gradients on the side stream never race a later data-gradient store; gU[U-1] == gB
+  SideStream side;
   float* dfake = nullptr;  // NHWC fp32
   float* fine_nhwc = nullptr;
   float* l1 = nullptr;
@@ -305,8 +355,14 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
   GA(g->gx0, B * pc * F * g->esz);
   GA(g->gx1, B * pc * F * g->esz);
   GA(g->gT1, B * pc * F * g->esz);
-  GA(g->gA, B * pf * F * g->esz);   // also holds 4F channels at quarter resolution
-  GA(g->gB, B * pf * F * g->esz);
+  GA(g->gA, B * pf * F * g->esz);
+  GA(g->gB, B * pf * F * g->esz);   // 4F channels at quarter resolution
+  g->gU.assign(std::max(g->U, 1), nullptr);
+  for (int u = 0; u < g->U; ++u) {
+    if (u == g->U - 1) g->gU[u] = g->gB;
+    else GA(g->gU[u], B * (pc << (2 * u)) * 4 * F * g->esz);
+  }
+  if ((s = g->side.create(2)) != 0) { dg_generator_destroy(g); return s; }
 #undef GA
   *out = g;
   return 0;
@@ -314,6 +370,7 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
 
 extern "C" int dg_generator_destroy(dg_generator* g) {
   if (!g) return 0;
+  g->side.destroy();
   for (void* p : g->pool) cudaFree(p);
   delete g;
   return 0;
@@ -427,12 +484,18 @@ static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_co
   const int B = g->saved_batch, F = g->F, Hc = g->Hc, Hf = g->Hf;
   if (B <= 0) { set_error("generator backward without a saved forward"); return DG_ERR_STATE; }
   DG_CUDA(cudaMemsetAsync(g->gpk, 0, sizeof(float) * g->pk_elems, st));
+  // Weight gradients only feed the final unpack: with the side stream on they are enqueued there (after everything
+  // enqueued on `st` so far, i.e. after the data-gradient that produced their dy) and joined before the unpack, so the
+  // tail layers' weight gradients overlap the data-gradient chain and the 64-CTA trunk kernel.
+  bool side_on = g_tune[9] && g->side.s != nullptr;
   auto wgrad = [&](int li, TV x, int H, TV dy) {
     const Layer& l = g->layers[li];
     WgradOp w;
     w.x = x; w.Hin = H; w.Win = H; w.Ci = l.Ci; w.dy = dy; w.Hout = H; w.Wout = H; w.Co = l.Co; w.B = B; w.stride = 1;
     w.dw = g->gpk + l.pk_off; w.dbias = g->gpk + l.pkb_off;
-    return run_wgrad(w, st);
+    if (!side_on) return run_wgrad(w, st);
+    DG_TRY(g->side.fork(st));
+    return run_wgrad(w, g->side.s);
   };
   auto dconv = [&](int li, TV dy, int H, TV dx) {  // data-gradient op of plain layer li: Ci_op = Co, Co_op = Ci
     const Layer& l = g->layers[li];
@@ -455,24 +518,22 @@ static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_co
   DG_TRY(wgrad(g->idx_c30(), g->act(last_up, F), Hf, g->act(g->gA, F)));
   void* gcur = nullptr;  // gradient w.r.t. the input of the layer just processed
   {
-    ConvOp op = dconv(g->idx_c30(), g->act(g->gA, F), Hf, g->U > 0 ? g->act(g->gB, 4 * F) : g->act(g->gT1, F));
+    ConvOp op = dconv(g->idx_c30(), g->act(g->gA, F), Hf, g->U > 0 ? g->act(g->gU[g->U - 1], 4 * F) : g->act(g->gT1, F));
     if (g->U > 0) {  // store un-shuffled and masked by the pre-shuffle LeakyReLU (sign taken from the shuffled copy)
       op.shuffle = SHUF_UNPIXEL; op.act = ACT_MASK; op.slope = G_SLOPE; op.mask = g->act(last_up, F);
     }
     DG_TRY(run_conv(op, st));
-    gcur = g->U > 0 ? g->gB : g->gT1;
+    gcur = g->U > 0 ? g->gU[g->U - 1] : g->gT1;
   }
-  // upsample stages, last to first; gcur holds dz of stage u as (B, H, H, 4F)
-  void* ping = g->gA;
+  // upsample stages, last to first; gcur = gU[u] holds dz of stage u as (B, H, H, 4F)
   for (int u = g->U - 1; u >= 0; --u) {
     const int H = Hc << u;
     void* xin = u > 0 ? g->up[u - 1] : g->t1;
     DG_TRY(wgrad(g->idx_up(u), g->act(xin, F), H, g->act(gcur, 4 * F)));
-    void* dst = u > 0 ? ping : g->gT1;
+    void* dst = u > 0 ? g->gU[u - 1] : g->gT1;
     ConvOp op = dconv(g->idx_up(u), g->act(gcur, 4 * F), H, u > 0 ? g->act(dst, 4 * F) : g->act(dst, F));
     if (u > 0) { op.shuffle = SHUF_UNPIXEL; op.act = ACT_MASK; op.slope = G_SLOPE; op.mask = g->act(xin, F); }
     DG_TRY(run_conv(op, st));
-    ping = gcur;
     gcur = dst;
   }
   // gT1 = dL/d(out1 + conv2(trunk))
@@ -489,6 +550,10 @@ static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_co
   if (batched_wgrad) wops.reserve((size_t)g->R * 15);
   void* const D0 = g->D;
   const bool fused_bwd = batched_wgrad && trunk_fused_supported(F, Hc, g->R, g->bf);
+  if (!fused_bwd && side_on) {  // the per-layer trunk path reuses its dz / gradient buffers block after block
+    DG_TRY(g->side.join(st));
+    side_on = false;
+  }
   if (fused_bwd) {
     // persistent tcgen05 kernel: the whole data-gradient chain of the trunk, dz slices saved per block
     DG_TRY(trunk_bwd_fused(g->gR, g->gR, (void* const*)g->db_ptrs_dev, (void* const*)g->d_ptrs_dev, g->pkd_trunk, g->R, B, st));
@@ -585,6 +650,7 @@ static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_co
     DG_TRY(run_conv(op, st));
     DG_TRY(nhwc_to_nchw(g->act(g->gx1, g->Cin), d_coarse, B, g->Cin, Hc, Hc, st));
   }
+  DG_TRY(g->side.join(st));
   DG_TRY(unpack_wgrads(g->gpk, grads_flat, g->tab_fwd, g->n_fwd, g->max_fwd, st));
   return 0;
 }
@@ -626,6 +692,7 @@ struct dg_critic {
   float *g = nullptr, *u = nullptr;        // (maxB,Hf,Hf,nc) fp32
   void *v0 = nullptr, *v1 = nullptr;       // JVP ping-pong
   float *sumsq = nullptr, *coef = nullptr, *norms = nullptr, *scal = nullptr;
+  SideStream side;
   int saved_batch = 0;
   TV act(void* p, int pitch, int coff = 0) const { return tv(p, bf, pitch, coff); }
   size_t pix(int l) const { return (size_t)Hout[l] * Hout[l]; }  // l = 0..7 -> a[l+1]
@@ -763,11 +830,13 @@ extern "C" int dg_critic_create(const dg_critic_config* cfg, dg_critic** out) {
   CA(c->norms, B * sizeof(float));
   CA(c->scal, 64);
 #undef CA
+  if ((s = c->side.create(1)) != 0) { dg_critic_destroy(c); return s; }
   *out = c;
   return 0;
 }
 extern "C" int dg_critic_destroy(dg_critic* c) {
   if (!c) return 0;
+  c->side.destroy();
   for (void* p : c->pool) cudaFree(p);
   delete c;
   return 0;
@@ -781,41 +850,68 @@ extern "C" int dg_critic_pack(dg_critic* c, const float* params, void* stream) {
   return 0;
 }
 
-// Critic.forward (critic.py:101-106) over samples [0, NB) of c->a0.
-static int critic_forward_internal(dg_critic* c, int NB, cudaStream_t st) {
-  TV x = tv(c->a0, 0, c->nc);
+// Critic.forward (critic.py:101-106) over samples [s0, s0 + NB) of c->a0.
+static int critic_forward_internal(dg_critic* c, int NB, cudaStream_t st, int s0 = 0) {
+  TV x = tv_batch(tv(c->a0, 0, c->nc), (size_t)c->Hf * c->Hf, s0);
   for (int i = 0; i < 8; ++i) {
     const Layer& l = c->L[i];
     ConvOp op;
     op.x = x; op.Hin = c->Hin[i]; op.Win = c->Hin[i]; op.Ci = l.Ci;
-    op.y = c->act(c->a[i + 1], l.Co); op.Hout = c->Hout[i]; op.Wout = c->Hout[i]; op.Co = l.Co;
+    op.y = tv_batch(c->act(c->a[i + 1], l.Co), c->pix(i), s0); op.Hout = c->Hout[i]; op.Wout = c->Hout[i]; op.Co = l.Co;
     op.B = NB; op.w = c->pk + l.pk_off; op.bias = (i == 0) ? c->pk + c->pk_b0 : nullptr;
     if (c->bf) op.w_umma = c->pk_u + l.pk_off;
     op.stride = l.stride; op.act = ACT_LRELU; op.slope = C_SLOPE;
     DG_TRY(run_conv(op, st));
     x = op.y;
   }
-  DG_TRY(fc_fwd(c->a[8], c->bf, c->pk + c->pk_fc1w, c->pk + c->pk_fc1b, c->a9, NB, c->fc_in, FC_HIDDEN, ACT_LRELU, C_SLOPE,
-                nullptr, st));
-  DG_TRY(fc2_fwd(c->a9, c->pk + c->pk_fc2w, c->pk + c->pk_fc2b, c->scores, NB, FC_HIDDEN, st));
+  float* a9 = c->a9 + (size_t)s0 * FC_HIDDEN;
+  DG_TRY(fc_fwd(x.p, c->bf, c->pk + c->pk_fc1w, c->pk + c->pk_fc1b, a9, NB, c->fc_in, FC_HIDDEN, ACT_LRELU, C_SLOPE, nullptr, st));
+  DG_TRY(fc2_fwd(a9, c->pk + c->pk_fc2w, c->pk + c->pk_fc2b, c->scores + s0, NB, FC_HIDDEN, st));
   return 0;
 }
 
-// Input-gradient chain for samples [0, NB) seeded by c->seed; layer-1 data
+// Weight gradient of conv layer i over samples [s0, s0 + n) of the saved activations / dz buffers (x = a[i], dy = dz[i+1]),
+// accumulated into c->gpk; `bias_n` > 0 adds the features.0 bias gradient over the first bias_n of those samples.
+// With `side` the launch goes to the critic's side stream, ordered after everything enqueued on `st` so far.
+static int critic_layer_wgrad(dg_critic* c, int i, int s0, int n, int bias_n, bool side, cudaStream_t st) {
+  const Layer& l = c->L[i];
+  WgradOp w;
+  const size_t pin = (size_t)c->Hin[i] * c->Hin[i];
+  w.x = tv_batch((i == 0) ? tv(c->a0, 0, c->nc) : c->act(c->a[i], l.Ci), pin, s0);
+  w.Hin = c->Hin[i]; w.Win = c->Hin[i]; w.Ci = l.Ci;
+  w.dy = tv_batch(c->act(c->dz[i + 1], l.Co), c->pix(i), s0); w.Hout = c->Hout[i]; w.Wout = c->Hout[i]; w.Co = l.Co;
+  w.B = n; w.stride = l.stride;
+  w.dw = c->gpk + l.pk_off;
+  if (i == 0 && bias_n > 0) { w.dbias = c->gpk + c->pk_b0; w.dbias_B = bias_n; }
+  if (!side) return run_wgrad(w, st);
+  DG_TRY(c->side.fork(st));
+  return run_wgrad(w, c->side.s);
+}
+
+// Input-gradient chain for samples [s0, s0 + NB) seeded by c->seed; layer-1 data
 // gradient only for samples [n0, n0+n1) into g_out (NHWC fp32) when n1 > 0.
-static int critic_backward_chain(dg_critic* c, int NB, int n0, int n1, float* g_out, cudaStream_t st) {
-  DG_TRY(fc2_seed(c->a9, c->pk + c->pk_fc2w, c->seed, c->dz9, NB, FC_HIDDEN, C_SLOPE, st));
-  DG_TRY(fc_dgrad(c->dz9, c->pk + c->pk_fc1w, c->dz[8], c->bf, NB, c->fc_in, FC_HIDDEN, c->a[8], c->bf, C_SLOPE, st));
+// early != 0: the weight gradient of every conv layer over the chain's samples is enqueued as soon as its dz exists
+// (c->gpk must already be zeroed): early == 1 on the side stream (forked from `st`), early == 2 on `st` itself (the
+// chain already runs on a stream of its own).
+static int critic_backward_chain(dg_critic* c, int NB, int n0, int n1, float* g_out, cudaStream_t st, int early = 0, int s0 = 0) {
+  float* dz9 = c->dz9 + (size_t)s0 * FC_HIDDEN;
+  const size_t e8 = (size_t)s0 * c->fc_in;
+  void* dz8 = c->bf ? (void*)((bf16*)c->dz[8] + e8) : (void*)((float*)c->dz[8] + e8);
+  const void* a8 = c->bf ? (const void*)((const bf16*)c->a[8] + e8) : (const void*)((const float*)c->a[8] + e8);
+  DG_TRY(fc2_seed(c->a9 + (size_t)s0 * FC_HIDDEN, c->pk + c->pk_fc2w, c->seed + s0, dz9, NB, FC_HIDDEN, C_SLOPE, st));
+  DG_TRY(fc_dgrad(dz9, c->pk + c->pk_fc1w, dz8, c->bf, NB, c->fc_in, FC_HIDDEN, a8, c->bf, C_SLOPE, st));
+  if (early) DG_TRY(critic_layer_wgrad(c, 7, s0, NB, 0, early == 1, st));
   for (int i = 7; i >= 1; --i) {  // dz[i] = dgrad_{i+1}(dz[i+1]) * lrelu'(a[i])
     const Layer& l = c->L[i];
     ConvOp op;
-    op.x = c->act(c->dz[i + 1], l.Co); op.Hin = c->Hout[i]; op.Win = c->Hout[i]; op.Ci = l.Co;
-    op.y = c->act(c->dz[i], l.Ci); op.Hout = c->Hin[i]; op.Wout = c->Hin[i]; op.Co = l.Ci;
+    op.x = tv_batch(c->act(c->dz[i + 1], l.Co), c->pix(i), s0); op.Hin = c->Hout[i]; op.Win = c->Hout[i]; op.Ci = l.Co;
+    op.y = tv_batch(c->act(c->dz[i], l.Ci), c->pix(i - 1), s0); op.Hout = c->Hin[i]; op.Wout = c->Hin[i]; op.Co = l.Ci;
     op.B = NB; op.w = c->pkd + l.pkd_off;
     if (c->bf) op.w_umma = c->pkd_u + l.pkd_off;
     op.transposed = (l.stride == 2);
-    op.act = ACT_MASK; op.slope = C_SLOPE; op.mask = c->act(c->a[i], l.Ci);
+    op.act = ACT_MASK; op.slope = C_SLOPE; op.mask = tv_batch(c->act(c->a[i], l.Ci), c->pix(i - 1), s0);
     DG_TRY(run_conv(op, st));
+    if (early) DG_TRY(critic_layer_wgrad(c, i - 1, s0, NB, NB, early == 1, st));
   }
   if (n1 > 0) {
     const Layer& l = c->L[0];
@@ -896,10 +992,22 @@ static int critic_gp_first_order(dg_critic* c, const dg_hyper* hp, int n0, int B
 // epilogue thread reads the mask element and overwrites the same element).  Afterwards
 // a[l] = [real acts ; fake acts ; v_l] and dz[l+1] = [dz real ; dz fake ; dz interpolates], so ONE
 // weight-gradient launch per layer over all 3B samples yields  d(E[C(fake)] - E[C(real)])/dW + dGP/dW.
-static int critic_second_order_and_wgrads(dg_critic* c, int B, cudaStream_t st) {
+static int critic_second_order_and_wgrads(dg_critic* c, int B, cudaStream_t st, bool two_chain) {
   const int n0 = 2 * B;
+  // The weight gradient of layer i reads a[i] = [real ; fake ; v_{i-1}] and dz[i+1]; nothing later in the call
+  // overwrites either, so with the side stream on it is enqueued there as soon as v_{i-1} exists and overlaps the
+  // rest of the JVP chain and the classifier kernels (joined here, before the caller's unpack).
+  // two_chain: the real + fake rows (forward, input-gradient chain, their weight-gradient rows, classifier rows) are
+  // running on the side stream; this stream only adds the interpolates' rows and joins at the end.
+  const bool side_on = !two_chain && g_tune[9] && c->side.s != nullptr;
+  auto layer_wgrad = [&](int i) {
+    // features.0.bias: real + fake samples only (the gradient penalty contributes exactly zero to biases)
+    if (two_chain) return critic_layer_wgrad(c, i, n0, B, 0, false, st);
+    return critic_layer_wgrad(c, i, 0, 3 * B, n0, side_on, st);
+  };
   TV v = tv_batch(tv(c->a0, 0, c->nc), (size_t)c->Hf * c->Hf, n0);  // u was written here by gp_scale
   for (int i = 0; i < 8; ++i) {
+    if (side_on) DG_TRY(layer_wgrad(i));
     const Layer& l = c->L[i];
     ConvOp op;
     op.x = v; op.Hin = c->Hin[i]; op.Win = c->Hin[i]; op.Ci = l.Ci;
@@ -910,25 +1018,23 @@ static int critic_second_order_and_wgrads(dg_critic* c, int B, cudaStream_t st) 
     DG_TRY(run_conv(op, st));
     v = op.y;
   }
-  // classifier: dW_fc1 over all 3B rows at once; v_fc and dW_fc2 as in critic_gp_second_order
-  DG_TRY(fc_wgrad(c->dz9, c->a[8], c->bf, c->gpk + c->pk_fc1w, 3 * B, c->fc_in, FC_HIDDEN, st));
+  // classifier: dW_fc1 over all 3B rows at once (two_chain: the interpolates' rows); v_fc and dW_fc2 as in critic_gp_second_order
+  if (two_chain) DG_TRY(fc_wgrad(c->dz9 + (size_t)n0 * FC_HIDDEN, v.p, c->bf, c->gpk + c->pk_fc1w, B, c->fc_in, FC_HIDDEN, st));
+  else DG_TRY(fc_wgrad(c->dz9, c->a[8], c->bf, c->gpk + c->pk_fc1w, 3 * B, c->fc_in, FC_HIDDEN, st));
   DG_TRY(fc_fwd(v.p, c->bf, c->pk + c->pk_fc1w, nullptr, c->vfc, B, c->fc_in, FC_HIDDEN, ACT_MASK, C_SLOPE,
                 c->a9 + (size_t)n0 * FC_HIDDEN, st));
+  if (two_chain) {
+    for (int i = 0; i < 8; ++i) DG_TRY(layer_wgrad(i));
+    DG_TRY(c->side.join(st));
+  }
   // classifier.0.bias, classifier.2.weight (incl. the GP term sum_b v_fc) and classifier.2.bias in one launch
   DG_TRY(critic_small_grads(c->dz9, c->seed, c->a9, c->vfc, n0, B, FC_HIDDEN, c->gpk + c->pk_fc1b, c->gpk + c->pk_fc2w,
                             c->gpk + c->pk_fc2b, st));
-  for (int i = 0; i < 8; ++i) {
-    const Layer& l = c->L[i];
-    WgradOp w;
-    w.x = (i == 0) ? tv(c->a0, 0, c->nc) : c->act(c->a[i], l.Ci);
-    w.Hin = c->Hin[i]; w.Win = c->Hin[i]; w.Ci = l.Ci;
-    w.dy = c->act(c->dz[i + 1], l.Co); w.Hout = c->Hout[i]; w.Wout = c->Hout[i]; w.Co = l.Co;
-    w.B = 3 * B; w.stride = l.stride;
-    w.dw = c->gpk + l.pk_off; w.dbias = nullptr;
-    DG_TRY(run_wgrad(w, st));
+  if (!two_chain) {
+    if (!side_on)
+      for (int i = 0; i < 8; ++i) DG_TRY(layer_wgrad(i));
+    DG_TRY(c->side.join(st));
   }
-  // features.0.bias: real + fake samples only (the gradient penalty contributes exactly zero to biases)
-  DG_TRY(colsum(c->act(c->dz[1], c->L[0].Co), (size_t)n0 * c->pix(0), c->L[0].Co, c->gpk + c->pk_b0, st));
   return 0;
 }
 
@@ -997,15 +1103,35 @@ static int critic_step_body(dg_generator* g, dg_critic* c, const dg_hyper* hp, c
                             const float* alpha, int B, float* c_grads_flat, float* scalars, cudaStream_t st) {
   // one 3B critic batch: [real ; fake ; alpha*real + (1-alpha)*fake]   (:37-38, :91-97)
   DG_TRY(build_critic_input(fine, fake_nhwc, 0, alpha, c->a0, B, c->nc, c->Hf, c->Hf, 0, st));
-  DG_TRY(critic_forward_internal(c, 3 * B, st));
-  DG_TRY(critic_means(c->scores, B, scalars, st));
   critic_seed_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(c->seed, B);
   DG_LAUNCH_CHECK();
-  DG_TRY(critic_backward_chain(c, 3 * B, 2 * B, B, c->g, st));
+  DG_CUDA(cudaMemsetAsync(c->gpk, 0, sizeof(float) * c->pk_elems, st));
+  // g_tune[9] == 2: two chains over disjoint sample ranges.  The real + fake rows [0, 2B) run forward, input-gradient
+  // chain (layers 8..2) and their weight-gradient rows on the side stream; the interpolates [2B, 3B) run forward,
+  // input-gradient chain down to the input, penalty, JVP chain and their weight-gradient rows on the caller's stream.
+  // The kernels are latency- rather than bandwidth-bound, so the two chains fill each other's ramp-up and tail.
+  const bool two_chain = g_tune[9] >= 2 && c->side.s != nullptr;
+  if (two_chain) {
+    cudaStream_t sa = c->side.s;
+    DG_TRY(c->side.fork(st));
+    DG_TRY(critic_forward_internal(c, 2 * B, sa, 0));
+    DG_TRY(critic_means(c->scores, B, scalars, sa));
+    DG_CUDA(cudaEventRecord(c->side.aux_ev, sa));
+    DG_TRY(critic_backward_chain(c, 2 * B, 0, 0, nullptr, sa, 2, 0));
+    {
+      DG_TRY(fc_wgrad(c->dz9, c->a[8], c->bf, c->gpk + c->pk_fc1w, 2 * B, c->fc_in, FC_HIDDEN, sa));
+    }
+    DG_TRY(critic_forward_internal(c, B, st, 2 * B));
+    DG_TRY(critic_backward_chain(c, B, 2 * B, B, c->g, st, 0, 2 * B));
+    DG_CUDA(cudaStreamWaitEvent(st, c->side.aux_ev, 0));  // the loss scalar needs the real / fake means
+  } else {
+    DG_TRY(critic_forward_internal(c, 3 * B, st));
+    DG_TRY(critic_means(c->scores, B, scalars, st));
+    DG_TRY(critic_backward_chain(c, 3 * B, 2 * B, B, c->g, st));
+  }
   DG_TRY(critic_gp_first_order(c, hp, 2 * B, B, scalars, 1, nullptr, st,
                                c->a0 + (size_t)2 * B * c->Hf * c->Hf * c->nc));  // u overwrites the interpolates
-  DG_CUDA(cudaMemsetAsync(c->gpk, 0, sizeof(float) * c->pk_elems, st));
-  DG_TRY(critic_second_order_and_wgrads(c, B, st));
+  DG_TRY(critic_second_order_and_wgrads(c, B, st, two_chain));
   DG_TRY(unpack_wgrads(c->gpk, c_grads_flat, c->tab_fwd, c->n_fwd, c->max_fwd, st));
   c->saved_batch = 0;
   (void)g;

@@ -29,6 +29,7 @@ struct IcArgs {
   int tiles_total, tiles_per_cta;
   unsigned a_off;  // byte offset of the dy tile (after the im2col planes)
   unsigned xs_bytes;  // staged fp32 input rows per ring slot (pipelined first-layer kernel)
+  int bias_n;         // staged first-layer kernel: > 0 = im2col column 9*Ci is 1 for samples < bias_n (fused bias gradient)
 };
 
 __device__ __forceinline__ float ldx(const void* p, int bf, size_t i) {
@@ -336,6 +337,8 @@ __global__ void __launch_bounds__(L1_THREADS) wgrad_l1_kernel(const IcArgs a) {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        // fused bias gradient: a column of ones makes D[co][9*CI] = sum_pos dy[pos][co] (tiles never straddle samples)
+        if (9 * CI < 32) v[9 * CI < 32 ? 9 * CI : 0] = ((t_begin + it) / tiles_per_img < a.bias_n) ? 1.f : 0.f;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const float* px = xs + ((r + tap / 3) * PWx + c + tap % 3) * CI;
@@ -406,8 +409,10 @@ __global__ void __launch_bounds__(L1_THREADS) wgrad_l1_kernel(const IcArgs a) {
       tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + nc, v);
       if (co >= 0 && co < op.Co) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
+        for (int j = 0; j < 16; ++j) {
           if (nc + j < 9 * CI) atomicAdd(op.dw + (size_t)(nc + j) * a.CoP + co, v[j]);
+          else if (STAGED && nc + j == 9 * CI && a.bias_n > 0) atomicAdd(op.dbias + co, v[j]);
+        }
       }
     }
   }
@@ -457,6 +462,9 @@ int wgrad_im2col(const WgradOp& op, cudaStream_t st) {
     attr_set = true;
   }
   const double total = (double)a.total_pos;
+  const int bias_B = (op.dbias_B > 0 && op.dbias_B < op.B) ? op.dbias_B : op.B;
+  bool fused_bias = false;
+  a.bias_n = 0;
   {
     Prof prof(PC_WGRAD_UMMA, 2.0 * total * op.Co * op.Ci * 9.0, total * op.Co * 2.0 + total * op.Ci * (op.x.bf ? 2.0 : 4.0), st);
     if (op.Ci <= 3 && op.Co <= 64 && a.total_pos < (1LL << 31)) {
@@ -465,6 +473,8 @@ int wgrad_im2col(const WgradOp& op, cudaStream_t st) {
       const bool staged = !op.x.bf && op.x.pitch == op.Ci && op.x.coff == 0 && op.stride == 1 && pow2 && op.Wout <= IC_TPOS &&
                           (op.Hout % (IC_TPOS / op.Wout)) == 0 && (op.Ci == 2 || op.Ci == 1 || op.Ci == 3);
       a.xs_bytes = staged ? (unsigned)(((IC_TPOS / op.Wout + 2) * (op.Wout + 2) * op.Ci * 4 + 127) & ~127) : 0u;
+      fused_bias = staged && op.dbias && g_tune[8];
+      a.bias_n = fused_bias ? bias_B : 0;
       const unsigned l1_smem = (unsigned)(L1_NSTAGE * ((L1_NPLB + a.nplA) * IC_PB + a.xs_bytes) + L1_NPLA * IC_PB);
       long long S = std::min<long long>(a.tiles_total, 148LL * 2);
       a.tiles_per_cta = (int)((a.tiles_total + S - 1) / S);
@@ -494,7 +504,7 @@ int wgrad_im2col(const WgradOp& op, cudaStream_t st) {
     }
   }
   DG_LAUNCH_CHECK();
-  if (op.dbias) DG_TRY(colsum(op.dy, (size_t)a.total_pos, op.Co, op.dbias, st));
+  if (op.dbias && !fused_bias) DG_TRY(colsum(op.dy, (size_t)bias_B * op.Hout * op.Wout, op.Co, op.dbias, st));
   return 0;
 }
 

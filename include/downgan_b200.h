@@ -198,8 +198,12 @@ int dg_profile_report(double* out, int n_classes);
  * gradients on the TMA-fed kernel as channel blocks (1) or the cp.async batched kernel (0); key 5: programmatic
  * dependent launch of the TMA-fed conv / weight-gradient kernels (1) or plain stream order (0); key 6: tcgen05 kernel
  * for the few-channel fp32 boundary conv (1) or the CUDA-core kernel (0); key 7: narrow-output convs (Co < 16) on the
- * TMA-fed kernel with zero pad columns (1) or the CUDA-core kernel (0).  Returns the previous value, or DG_ERR_INVALID for an unknown key. */
-#define DG_TUNE_KEYS 8
+ * TMA-fed kernel with zero pad columns (1) or the CUDA-core kernel (0); key 8: features.0 bias gradient folded into the
+ * first-layer weight-gradient kernel as an im2col column of ones (1) or a separate column-sum launch (0); key 9: weight
+ * gradients (and their bias column sums) of the fused iterations on a library-owned side stream, forked and joined with
+ * events inside the call, so they overlap the data-gradient / JVP chain (1) or everything in stream order (0).
+ * Returns the previous value, or DG_ERR_INVALID for an unknown key. */
+#define DG_TUNE_KEYS 10
 int dg_set_tuning(int key, int value);
 
 #ifdef __cplusplus

@@ -63,13 +63,17 @@ def test_conv_primitives(case, precision):
     y_ref = F.leaky_relu(F.conv2d(x, wt, bias, stride=s, padding=1), 0.2)
     y = pu.conv_fwd(x, wt, bias, s, 0.2, precision)
     assert pu.rel(y, y_ref) < tol
-    dy = torch.randn_like(y_ref)
+    dy = torch.randn(y_ref.shape, generator=g)
     dx_ref = torch.nn.grad.conv2d_input(x.shape, wt, dy, stride=s, padding=1)
     assert pu.rel(pu.conv_dgrad(dy, wt, h, w, s, precision), dx_ref) < tol
     dw_ref = torch.nn.grad.conv2d_weight(x, wt.shape, dy, stride=s, padding=1)
     dw, db = pu.conv_wgrad(x, dy, s, precision)
     assert pu.rel(dw, dw_ref) < tol
-    assert pu.rel(db, dy.sum((0, 2, 3))) < tol
+    # the bias gradient is a cancelling sum: judge it against the sum of the values the kernel is given
+    # (bf16 mode rounds dy on entry), on the scale of the summed magnitudes
+    dy_in = dy.bfloat16().float() if precision == "bf16" else dy
+    db_ref = dy_in.double().sum((0, 2, 3))
+    assert float((db.double().cpu() - db_ref).abs().max() / dy_in.abs().sum((0, 2, 3)).max()) < 1e-5
 
 
 # ---------------------------------------------------------------- forward passes
