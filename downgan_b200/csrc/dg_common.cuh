@@ -183,6 +183,11 @@ int fc2_fwd(const float* a, const float* w, const float* bias, float* s, int NB,
 int fc2_seed(const float* a9, const float* w2, const float* seed, float* dz9, int NB, int K, float slope, cudaStream_t st);
 
 int critic_means(const float* scores, int B, float* scalars, cudaStream_t st);
+bool fc_fwd_raw_supported(int K, int N);
+int fc_fwd_raw(const void* x, int x_bf, const float* w, float* y, int NB, int K, int N, cudaStream_t st);  // y = x w^T
+bool critic_head_supported(int B);
+int critic_head(float* a9, const float* b1, const float* w2, const float* b2, float* scores, float* seed, float* dz9,
+                float* scalars, int B, int K, float slope, cudaStream_t st);
 int gp_norms(const float* g, int B, size_t per_sample, float* sumsq, cudaStream_t st);
 int gp_finish(const float* sumsq, int B, float gp_lambda, float* norms, float* coef, float* scalars, int write_loss, cudaStream_t st);
 int gp_scale(const float* g, const float* coef, float* u, int B, size_t per_sample, cudaStream_t st);

@@ -688,6 +688,81 @@ __global__ void fc_fwd_kernel(const void* __restrict__ x, int x_bf, const float*
     y[(size_t)b * N + j] = s;
   }
 }
+// y = x w^T without bias / activation (the caller's next kernel applies them); false: shape not covered by the tiled kernel
+bool fc_fwd_raw_supported(int K, int N) { return N <= FCF_BN && K % 8 == 0; }
+int fc_fwd_raw(const void* x, int x_bf, const float* w, float* y, int NB, int K, int N, cudaStream_t st) {
+  DG_CHECK(fc_fwd_raw_supported(K, N), "fc_fwd_raw: unsupported shape K=%d N=%d", K, N);
+  Prof prof(PC_FC, 2.0 * NB * N * K, (double)N * K * 4.0 + (double)NB * K * (x_bf ? 2 : 4), st);
+  const int nbt = (NB + FCF_BM - 1) / FCF_BM;
+  int splits = (296 + nbt - 1) / nbt;
+  splits = std::max(1, std::min(splits, (K + 63) / 64));
+  const int kchunk = ((K + splits - 1) / splits + FCF_BK - 1) / FCF_BK * FCF_BK;
+  splits = (K + kchunk - 1) / kchunk;
+  DG_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)NB * N, st));
+  if (x_bf) fc_fwd_tiled_kernel<true><<<dim3(nbt, splits), 256, 0, st>>>(x, w, y, NB, K, N, kchunk);
+  else fc_fwd_tiled_kernel<false><<<dim3(nbt, splits), 256, 0, st>>>(x, w, y, NB, K, N, kchunk);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+// Classifier head of the fused critic iteration in ONE launch (single CTA, deterministic), for the 3B batch
+// [real ; fake ; interpolates]: a9 = lrelu(y + b1) in place (classifier.1), scores = a9 w2 + b2 (classifier.2), the score
+// means of the real / fake rows (wasserstein.py:46-47), the per-row loss seeds (-1/B, +1/B, 1 for the penalty's ones
+// seed) and dz9 = seed * w2 * lrelu'(a9).  Replaces fc_finish + fc2_fwd + critic_means + critic_seed + fc2_seed.
+__global__ void __launch_bounds__(1024) critic_head_kernel(float* __restrict__ a9, const float* __restrict__ b1,
+                                                           const float* __restrict__ w2, const float* __restrict__ b2,
+                                                           float* __restrict__ scores, float* __restrict__ seed,
+                                                           float* __restrict__ dz9, float* __restrict__ scalars, int B, int K,
+                                                           float slope) {
+  __shared__ float ssc[1024];
+  __shared__ float part[2][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = warp; b < 3 * B; b += 32) {
+    const float sd = b < B ? -1.f / B : (b < 2 * B ? 1.f / B : 1.f);
+    float v = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const size_t i = (size_t)b * K + k;
+      float s = a9[i] + b1[k];
+      s = s > 0.f ? s : s * slope;
+      a9[i] = s;
+      const float w = w2[k];
+      v = fmaf(s, w, v);
+      dz9[i] = sd * w * lrelu_d(s, slope);
+    }
+    v = warp_sum(v);
+    if (lane == 0) {
+      v += b2[0];
+      scores[b] = v;
+      ssc[b] = v;
+      seed[b] = sd;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 256) {
+    float r = 0.f, f = 0.f;
+    for (int i = threadIdx.x; i < B; i += 256) { r += ssc[i]; f += ssc[B + i]; }
+    r = warp_sum(r);
+    f = warp_sum(f);
+    if (lane == 0) { part[0][warp] = r; part[1][warp] = f; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = 0.f, f = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { r += part[0][k]; f += part[1][k]; }
+    scalars[1] = r / B;
+    scalars[2] = f / B;
+  }
+}
+bool critic_head_supported(int B) { return 3 * B <= 1024; }
+int critic_head(float* a9, const float* b1, const float* w2, const float* b2, float* scores, float* seed, float* dz9,
+                float* scalars, int B, int K, float slope, cudaStream_t st) {
+  DG_CHECK(critic_head_supported(B), "critic_head: batch %d too large", B);
+  critic_head_kernel<<<1, 1024, 0, st>>>(a9, b1, w2, b2, scores, seed, dz9, scalars, B, K, slope);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
 int fc_fwd(const void* x, int x_bf, const float* w, const float* bias, float* y, int NB, int K, int N, int act,
            float slope, const float* mask, cudaStream_t st) {
   Prof prof(PC_FC, 2.0 * NB * N * K, (double)N * K * 4.0 + (double)NB * K * (x_bf ? 2 : 4), st);
@@ -728,6 +803,7 @@ __global__ void __launch_bounds__(256) fc_dgrad_kernel(const float* __restrict__
   float acc[FCD_BB];
 #pragma unroll
   for (int i = 0; i < FCD_BB; ++i) acc[i] = 0.f;
+#pragma unroll 5
   for (int j = 0; j < N; ++j) {
     const float wv = w[(size_t)j * K + k];
     const float4* p = reinterpret_cast<const float4*>(sdz + j * FCD_BB);
@@ -1072,7 +1148,7 @@ CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank,
   return fn(map, dt, rank, addr, dims, strides, box, estr, il, sw, l2, oob);
 }
 }  // namespace dg
-namespace dg { int g_tune[DG_TUNE_KEYS] = {1, 1, 1, 0, 1, 0, 1, 1, 1, 1}; }  // see include/downgan_b200.h: dg_set_tuning
+namespace dg { int g_tune[DG_TUNE_KEYS] = {1, 1, 1, 0, 1, 0, 1, 1, 1, 1, 4, 1}; }  // see include/downgan_b200.h: dg_set_tuning
 extern "C" int dg_set_tuning(int key, int value) {
   if (key < 0 || key >= DG_TUNE_KEYS) { dg::set_error("dg_set_tuning: unknown key %d", key); return DG_ERR_INVALID; }
   const int prev = dg::g_tune[key];

@@ -393,9 +393,13 @@ extern "C" int dg_generator_pack(dg_generator* g, const float* params, void* str
 // Generator.forward, networks/generator.py:83-90 (dense block :36-41, RRDB :52-53).
 // Input already in g->x0 (NHWC); output in g->fake (NHWC fp32).
 // `save_count` leading samples keep their activations for a later backward (0: inference / critic iterations).
-static int gen_forward_internal(dg_generator* g, int B, int save_count, cudaStream_t st) {
+// Generator.forward (generator.py:83-90) over samples [s0, s0 + B) of g->x0; the first save_count samples keep their
+// dense-block activations (only meaningful for s0 == 0).
+static int gen_forward_range(dg_generator* g, int s0, int B, int save_count, cudaStream_t st) {
   const bool save = save_count > 0;
   const int F = g->F, Hc = g->Hc;
+  const size_t pc = (size_t)Hc * Hc;
+  auto V = [&](void* p, int pitch, int coff, size_t pixels) { return tv_batch(g->act(p, pitch, coff), pixels, s0); };
   auto conv = [&](int li, TV x, int H, TV y) {
     const Layer& l = g->layers[li];
     ConvOp op;
@@ -408,60 +412,80 @@ static int gen_forward_internal(dg_generator* g, int B, int save_count, cudaStre
   void* first = g->R > 0 ? g->db[0] : g->trunk_out;
   const int first_pitch = g->R > 0 ? 5 * F : F;
   {
-    ConvOp op = conv(g->idx_conv1(), g->act(g->x0, g->Cin), Hc, g->act(first, first_pitch));
+    ConvOp op = conv(g->idx_conv1(), V(g->x0, g->Cin, 0, pc), Hc, V(first, first_pitch, 0, pc));
     DG_TRY(run_conv(op, st));
   }
   const bool fused_trunk = trunk_fused_supported(F, Hc, g->R, g->bf);
   if (fused_trunk) {
     // persistent tcgen05 kernel: the whole RRDB trunk with the concat buffer resident in shared memory
     const Layer& l0 = g->layers[g->idx_db(0, 0, 1)];
-    DG_TRY(trunk_fwd_fused(g->db[0], 5 * F, 0, g->trunk_out, F, save ? (void* const*)g->db_ptrs_dev : nullptr,
-                           g->pk_trunk, g->pk + l0.pkb_off, g->R, B, save_count, st));
+    DG_TRY(trunk_fwd_fused(V(g->db[0], 5 * F, 0, pc).p, 5 * F, 0, V(g->trunk_out, F, 0, pc).p, F,
+                           (save && s0 == 0) ? (void* const*)g->db_ptrs_dev : nullptr, g->pk_trunk, g->pk + l0.pkb_off, g->R, B,
+                           s0 == 0 ? save_count : 0, st));
   }
   for (int r = 0; r < (fused_trunk ? 0 : g->R); ++r)
     for (int d = 0; d < 3; ++d) {
       void* buf = g->db[r * 3 + d];
       for (int k = 1; k <= 4; ++k) {
-        ConvOp op = conv(g->idx_db(r, d, k), g->act(buf, 5 * F), Hc, g->act(buf, 5 * F, k * F));
+        ConvOp op = conv(g->idx_db(r, d, k), V(buf, 5 * F, 0, pc), Hc, V(buf, 5 * F, k * F, pc));
         op.act = ACT_LRELU; op.slope = G_SLOPE;
         DG_TRY(run_conv(op, st));
       }
       const bool last_db = (r == g->R - 1 && d == 2);
       void* nxt = last_db ? g->trunk_out : g->db[r * 3 + d + 1];
       const int npitch = last_db ? F : 5 * F;
-      ConvOp op = conv(g->idx_db(r, d, 5), g->act(buf, 5 * F), Hc, g->act(nxt, npitch));
+      ConvOp op = conv(g->idx_db(r, d, 5), V(buf, 5 * F, 0, pc), Hc, V(nxt, npitch, 0, pc));
       if (d < 2) {  // 0.2*o5 + x
-        op.s_acc = RES_SCALE; op.r1 = g->act(buf, 5 * F); op.s1 = 1.f;
+        op.s_acc = RES_SCALE; op.r1 = V(buf, 5 * F, 0, pc); op.s1 = 1.f;
       } else {      // 0.2*(0.2*o5 + x_db) + x_rrdb
-        op.s_acc = RES_SCALE * RES_SCALE; op.r1 = g->act(buf, 5 * F); op.s1 = RES_SCALE;
-        op.r2 = g->act(g->db[r * 3], 5 * F); op.s2 = 1.f;
+        op.s_acc = RES_SCALE * RES_SCALE; op.r1 = V(buf, 5 * F, 0, pc); op.s1 = RES_SCALE;
+        op.r2 = V(g->db[r * 3], 5 * F, 0, pc); op.s2 = 1.f;
       }
       DG_TRY(run_conv(op, st));
     }
   {  // out1 + conv2(trunk)
-    ConvOp op = conv(g->idx_conv2(), g->act(g->trunk_out, F), Hc, g->act(g->t1, F));
-    if (g->R > 0) { op.r1 = g->act(g->db[0], 5 * F); op.s1 = 1.f; }
-    else { op.s_acc = 1.f; op.r1 = g->act(g->trunk_out, F); op.s1 = 1.f; }
+    ConvOp op = conv(g->idx_conv2(), V(g->trunk_out, F, 0, pc), Hc, V(g->t1, F, 0, pc));
+    if (g->R > 0) { op.r1 = V(g->db[0], 5 * F, 0, pc); op.s1 = 1.f; }
+    else { op.s_acc = 1.f; op.r1 = V(g->trunk_out, F, 0, pc); op.s1 = 1.f; }
     DG_TRY(run_conv(op, st));
   }
   void* cur = g->t1;
   int H = Hc;
   for (int u = 0; u < g->U; ++u) {  // conv -> LeakyReLU -> PixelShuffle(2)
-    ConvOp op = conv(g->idx_up(u), g->act(cur, F), H, g->act(g->up[u], F));
+    ConvOp op = conv(g->idx_up(u), V(cur, F, 0, (size_t)H * H), H, V(g->up[u], F, 0, (size_t)4 * H * H));
     op.act = ACT_LRELU; op.slope = G_SLOPE; op.shuffle = SHUF_PIXEL;
     DG_TRY(run_conv(op, st));
     cur = g->up[u];
     H *= 2;
   }
   {
-    ConvOp op = conv(g->idx_c30(), g->act(cur, F), H, g->act(g->c30, F));
+    ConvOp op = conv(g->idx_c30(), V(cur, F, 0, (size_t)H * H), H, V(g->c30, F, 0, (size_t)H * H));
     op.act = ACT_LRELU; op.slope = G_SLOPE;
     DG_TRY(run_conv(op, st));
   }
   {
-    ConvOp op = conv(g->idx_c32(), g->act(g->c30, F), H, tv(g->fake, 0, g->Cout));
+    ConvOp op = conv(g->idx_c32(), V(g->c30, F, 0, (size_t)H * H), H,
+                     tv_batch(tv(g->fake, 0, g->Cout), (size_t)H * H, s0));
     op.narrow_ok = g->bf && umma_img_ok(F, g->Cout);
     DG_TRY(run_conv(op, st));
+  }
+  return 0;
+}
+
+// g_tune[10] = k > 0: when the batch is larger than one wave of the persistent trunk kernel (2 CTAs x 148 SMs), the last
+// 32k samples run as a second chain on the side stream, so the tail convolutions of the first chain overlap the trunk
+// kernel's partial second wave instead of waiting for it.
+static int gen_forward_internal(dg_generator* g, int B, int save_count, cudaStream_t st) {
+  const int nb = 32 * g_tune[10];
+  const bool split = nb > 0 && g->side.s != nullptr && B > 2 * 148 && B - nb >= save_count && B - nb >= nb &&
+                     trunk_fused_supported(g->F, g->Hc, g->R, g->bf);
+  if (split) {
+    DG_TRY(g->side.fork(st));
+    DG_TRY(gen_forward_range(g, 0, B - nb, save_count, st));
+    DG_TRY(gen_forward_range(g, B - nb, nb, 0, g->side.s));
+    DG_TRY(g->side.join(st));
+  } else {
+    DG_TRY(gen_forward_range(g, 0, B, save_count, st));
   }
   g->saved_batch = save_count;
   return 0;
@@ -851,7 +875,7 @@ extern "C" int dg_critic_pack(dg_critic* c, const float* params, void* stream) {
 }
 
 // Critic.forward (critic.py:101-106) over samples [s0, s0 + NB) of c->a0.
-static int critic_forward_internal(dg_critic* c, int NB, cudaStream_t st, int s0 = 0) {
+static int critic_forward_internal(dg_critic* c, int NB, cudaStream_t st, int s0 = 0, bool raw_head = false) {
   TV x = tv_batch(tv(c->a0, 0, c->nc), (size_t)c->Hf * c->Hf, s0);
   for (int i = 0; i < 8; ++i) {
     const Layer& l = c->L[i];
@@ -865,6 +889,7 @@ static int critic_forward_internal(dg_critic* c, int NB, cudaStream_t st, int s0
     x = op.y;
   }
   float* a9 = c->a9 + (size_t)s0 * FC_HIDDEN;
+  if (raw_head) return fc_fwd_raw(x.p, c->bf, c->pk + c->pk_fc1w, a9, NB, c->fc_in, FC_HIDDEN, st);  // critic_head finishes
   DG_TRY(fc_fwd(x.p, c->bf, c->pk + c->pk_fc1w, c->pk + c->pk_fc1b, a9, NB, c->fc_in, FC_HIDDEN, ACT_LRELU, C_SLOPE, nullptr, st));
   DG_TRY(fc2_fwd(a9, c->pk + c->pk_fc2w, c->pk + c->pk_fc2b, c->scores + s0, NB, FC_HIDDEN, st));
   return 0;
@@ -893,12 +918,13 @@ static int critic_layer_wgrad(dg_critic* c, int i, int s0, int n, int bias_n, bo
 // early != 0: the weight gradient of every conv layer over the chain's samples is enqueued as soon as its dz exists
 // (c->gpk must already be zeroed): early == 1 on the side stream (forked from `st`), early == 2 on `st` itself (the
 // chain already runs on a stream of its own).
-static int critic_backward_chain(dg_critic* c, int NB, int n0, int n1, float* g_out, cudaStream_t st, int early = 0, int s0 = 0) {
+static int critic_backward_chain(dg_critic* c, int NB, int n0, int n1, float* g_out, cudaStream_t st, int early = 0, int s0 = 0,
+                                 bool seeded = false) {
   float* dz9 = c->dz9 + (size_t)s0 * FC_HIDDEN;
   const size_t e8 = (size_t)s0 * c->fc_in;
   void* dz8 = c->bf ? (void*)((bf16*)c->dz[8] + e8) : (void*)((float*)c->dz[8] + e8);
   const void* a8 = c->bf ? (const void*)((const bf16*)c->a[8] + e8) : (const void*)((const float*)c->a[8] + e8);
-  DG_TRY(fc2_seed(c->a9 + (size_t)s0 * FC_HIDDEN, c->pk + c->pk_fc2w, c->seed + s0, dz9, NB, FC_HIDDEN, C_SLOPE, st));
+  if (!seeded) DG_TRY(fc2_seed(c->a9 + (size_t)s0 * FC_HIDDEN, c->pk + c->pk_fc2w, c->seed + s0, dz9, NB, FC_HIDDEN, C_SLOPE, st));
   DG_TRY(fc_dgrad(dz9, c->pk + c->pk_fc1w, dz8, c->bf, NB, c->fc_in, FC_HIDDEN, a8, c->bf, C_SLOPE, st));
   if (early) DG_TRY(critic_layer_wgrad(c, 7, s0, NB, 0, early == 1, st));
   for (int i = 7; i >= 1; --i) {  // dz[i] = dgrad_{i+1}(dz[i+1]) * lrelu'(a[i])
@@ -1103,14 +1129,17 @@ static int critic_step_body(dg_generator* g, dg_critic* c, const dg_hyper* hp, c
                             const float* alpha, int B, float* c_grads_flat, float* scalars, cudaStream_t st) {
   // one 3B critic batch: [real ; fake ; alpha*real + (1-alpha)*fake]   (:37-38, :91-97)
   DG_TRY(build_critic_input(fine, fake_nhwc, 0, alpha, c->a0, B, c->nc, c->Hf, c->Hf, 0, st));
-  critic_seed_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(c->seed, B);
-  DG_LAUNCH_CHECK();
+  const bool two_chain = g_tune[9] >= 2 && c->side.s != nullptr;
+  const bool head = !two_chain && g_tune[11] && critic_head_supported(B) && fc_fwd_raw_supported(c->fc_in, FC_HIDDEN);
+  if (!head) {
+    critic_seed_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(c->seed, B);
+    DG_LAUNCH_CHECK();
+  }
   DG_CUDA(cudaMemsetAsync(c->gpk, 0, sizeof(float) * c->pk_elems, st));
   // g_tune[9] == 2: two chains over disjoint sample ranges.  The real + fake rows [0, 2B) run forward, input-gradient
   // chain (layers 8..2) and their weight-gradient rows on the side stream; the interpolates [2B, 3B) run forward,
   // input-gradient chain down to the input, penalty, JVP chain and their weight-gradient rows on the caller's stream.
   // The kernels are latency- rather than bandwidth-bound, so the two chains fill each other's ramp-up and tail.
-  const bool two_chain = g_tune[9] >= 2 && c->side.s != nullptr;
   if (two_chain) {
     cudaStream_t sa = c->side.s;
     DG_TRY(c->side.fork(st));
@@ -1124,6 +1153,11 @@ static int critic_step_body(dg_generator* g, dg_critic* c, const dg_hyper* hp, c
     DG_TRY(critic_forward_internal(c, B, st, 2 * B));
     DG_TRY(critic_backward_chain(c, B, 2 * B, B, c->g, st, 0, 2 * B));
     DG_CUDA(cudaStreamWaitEvent(st, c->side.aux_ev, 0));  // the loss scalar needs the real / fake means
+  } else if (head) {
+    DG_TRY(critic_forward_internal(c, 3 * B, st, 0, true));
+    DG_TRY(critic_head(c->a9, c->pk + c->pk_fc1b, c->pk + c->pk_fc2w, c->pk + c->pk_fc2b, c->scores, c->seed, c->dz9, scalars, B,
+                       FC_HIDDEN, C_SLOPE, st));
+    DG_TRY(critic_backward_chain(c, 3 * B, 2 * B, B, c->g, st, 0, 0, true));
   } else {
     DG_TRY(critic_forward_internal(c, 3 * B, st));
     DG_TRY(critic_means(c->scores, B, scalars, st));

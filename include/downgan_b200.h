@@ -202,8 +202,12 @@ int dg_profile_report(double* out, int n_classes);
  * first-layer weight-gradient kernel as an im2col column of ones (1) or a separate column-sum launch (0); key 9: weight
  * gradients (and their bias column sums) of the fused iterations on a library-owned side stream, forked and joined with
  * events inside the call, so they overlap the data-gradient / JVP chain (1) or everything in stream order (0).
+ * key 9 == 2: the critic iteration as two chains over disjoint sample ranges (measured slower than 1).  key 10 = k > 0:
+ * generator forward of more than 296 samples (look-ahead pass) split so that its last 32k samples run as a second
+ * chain on the side stream (0: one chain).  key 11: classifier head of the fused critic iteration (bias + LeakyReLU,
+ * classifier.2, score means, loss seeds, dz of the hidden layer) in one launch (1) or five (0).
  * Returns the previous value, or DG_ERR_INVALID for an unknown key. */
-#define DG_TUNE_KEYS 10
+#define DG_TUNE_KEYS 12
 int dg_set_tuning(int key, int value);
 
 #ifdef __cplusplus
