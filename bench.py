@@ -61,7 +61,11 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []   # (host time the line arrived, line)
+        self.windows = []  # (t0, t1) host times of the timed regions
+
+    def mark(self, t0: float, t1: float):
+        self.windows.append((t0, t1))
 
     def start(self):
         try:
@@ -75,7 +79,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -88,7 +92,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        # the sampler is started before the warm-up (its start-up cost stays out of the timed regions); only samples
+        # that arrived inside a timed region (+100 ms: one sampling period) count, all of them if none did
+        inside = [ln for t, ln in self.lines if any(a <= t <= b + 0.1 for a, b in self.windows)]
+        scope = "timed regions" if inside else "whole run (timed regions shorter than the sampling period)"
+        for ln in (inside or [ln for _, ln in self.lines]):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -101,7 +109,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
 # ------------------------------------------------------------------------------------------
@@ -164,8 +172,8 @@ def config_dict(args, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("DOWNGAN_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -252,15 +260,17 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), lib.dg_launch_count() - l0
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     # warm-up (also creates the native handles and workspaces)
     run(args.warmup, devb, False)
     tr.num_steps = 0
     tr._train_epoch([devb[s % NBATCH] for s in range(max(args.warmup, 6))])
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    t_w0 = time.time()
     ms, launches = timed(args.steps, devb, False)
+    sampler.mark(t_w0, time.time())
 
     # ---- e2e: the public trainer API on HOST batches (wasserstein.py:120-147 `_train_epoch`):
     # every batch is copied host->device inside the timed region (pinned memory, side stream) and the
@@ -273,10 +283,12 @@ def main():
     tr.num_steps = 0
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_w0 = time.time()
     e0.record()
     logs = tr._train_epoch(epoch_batches(args.steps, 0))
     e1.record()
     barrier()
+    sampler.mark(t_w0, time.time())
     assert logs.shape == (args.steps, 8) and bool(torch.isfinite(logs).all())
     t_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
