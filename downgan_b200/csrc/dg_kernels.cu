@@ -709,15 +709,17 @@ int fc_fwd_raw(const void* x, int x_bf, const float* w, float* y, int NB, int K,
 // [real ; fake ; interpolates]: a9 = lrelu(y + b1) in place (classifier.1), scores = a9 w2 + b2 (classifier.2), the score
 // means of the real / fake rows (wasserstein.py:46-47), the per-row loss seeds (-1/B, +1/B, 1 for the penalty's ones
 // seed) and dz9 = seed * w2 * lrelu'(a9).  Replaces fc_finish + fc2_fwd + critic_means + critic_seed + fc2_seed.
-__global__ void __launch_bounds__(1024) critic_head_kernel(float* __restrict__ a9, const float* __restrict__ b1,
-                                                           const float* __restrict__ w2, const float* __restrict__ b2,
-                                                           float* __restrict__ scores, float* __restrict__ seed,
-                                                           float* __restrict__ dz9, float* __restrict__ scalars, int B, int K,
-                                                           float slope) {
-  __shared__ float ssc[1024];
+__device__ unsigned int g_head_done = 0;  // completion counter (the fused iteration runs on one stream at a time)
+__global__ void __launch_bounds__(256) critic_head_kernel(float* __restrict__ a9, const float* __restrict__ b1,
+                                                          const float* __restrict__ w2, const float* __restrict__ b2,
+                                                          float* __restrict__ scores, float* __restrict__ seed,
+                                                          float* __restrict__ dz9, float* __restrict__ scalars, int B, int K,
+                                                          float slope) {
   __shared__ float part[2][8];
+  __shared__ bool last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int b = warp; b < 3 * B; b += 32) {
+  const int b = blockIdx.x * 8 + warp;  // one sample per warp
+  if (b < 3 * B) {
     const float sd = b < B ? -1.f / B : (b < 2 * B ? 1.f / B : 1.f);
     float v = 0.f;
     for (int k = lane; k < K; k += 32) {
@@ -731,34 +733,36 @@ __global__ void __launch_bounds__(1024) critic_head_kernel(float* __restrict__ a
     }
     v = warp_sum(v);
     if (lane == 0) {
-      v += b2[0];
-      scores[b] = v;
-      ssc[b] = v;
+      scores[b] = v + b2[0];
       seed[b] = sd;
     }
   }
+  // the last block to finish sums the real / fake scores in a fixed order (deterministic means)
+  __threadfence();
   __syncthreads();
-  if (threadIdx.x < 256) {
-    float r = 0.f, f = 0.f;
-    for (int i = threadIdx.x; i < B; i += 256) { r += ssc[i]; f += ssc[B + i]; }
-    r = warp_sum(r);
-    f = warp_sum(f);
-    if (lane == 0) { part[0][warp] = r; part[1][warp] = f; }
-  }
+  if (threadIdx.x == 0) last = (atomicAdd(&g_head_done, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float r = 0.f, f = 0.f;
+  for (int i = threadIdx.x; i < B; i += 256) { r += __ldcg(scores + i); f += __ldcg(scores + B + i); }
+  r = warp_sum(r);
+  f = warp_sum(f);
+  if (lane == 0) { part[0][warp] = r; part[1][warp] = f; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float r = 0.f, f = 0.f;
+    r = 0.f; f = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) { r += part[0][k]; f += part[1][k]; }
     scalars[1] = r / B;
     scalars[2] = f / B;
+    g_head_done = 0;
   }
 }
-bool critic_head_supported(int B) { return 3 * B <= 1024; }
+bool critic_head_supported(int B) { return B >= 1; }
 int critic_head(float* a9, const float* b1, const float* w2, const float* b2, float* scores, float* seed, float* dz9,
                 float* scalars, int B, int K, float slope, cudaStream_t st) {
-  DG_CHECK(critic_head_supported(B), "critic_head: batch %d too large", B);
-  critic_head_kernel<<<1, 1024, 0, st>>>(a9, b1, w2, b2, scores, seed, dz9, scalars, B, K, slope);
+  critic_head_kernel<<<(3 * B + 7) / 8, 256, 0, st>>>(a9, b1, w2, b2, scores, seed, dz9, scalars, B, K, slope);
   DG_LAUNCH_CHECK();
   return 0;
 }

@@ -12,7 +12,11 @@
  *   - every function returns 0 on success, a negative dg_status otherwise;
  *     dg_last_error() returns a thread-local message for the last failure.
  *   - no exceptions cross the ABI, no hidden device synchronisation, every
- *     call enqueues on the cudaStream_t passed as `void* stream`.
+ *     call enqueues on the cudaStream_t passed as `void* stream`.  A handle
+ *     also owns one non-blocking side stream: the fused iterations fork
+ *     work onto it (weight gradients, the second chain of a look-ahead
+ *     forward) and join it back with events before returning, so towards
+ *     the caller a call is still plain work in order on `stream`.
  *   - the caller owns all tensors handed in (device pointers unless stated);
  *     handles own only packed weights and activation workspaces.
  *   - user-facing tensors are contiguous NCHW fp32 (the reference layout);
