@@ -299,16 +299,16 @@ def main():
     # ---- per-kernel-class CUDA-event pass (same steps, events around every launch) ---------
     prof = None
     if not args.no_profile:
-        # kernels timed one at a time: the side-stream overlap (dg_set_tuning keys 9, 10) is switched off for this pass,
+        # kernels timed one at a time: the side-stream overlap (dg_set_tuning keys 9, 10, 12) is switched off for this pass,
         # otherwise an event pair around a launch also spans whatever runs concurrently on the other stream
-        prev9, prev10 = lib.dg_set_tuning(9, 0), lib.dg_set_tuning(10, 0)
+        prev9, prev10, prev12 = lib.dg_set_tuning(9, 0), lib.dg_set_tuning(10, 0), lib.dg_set_tuning(12, 0)
         lib.dg_profile(1)
         tr.num_steps = 0
         tr._train_epoch([devb[s % NBATCH] for s in range(args.steps)])
         buf = (C.c_double * (4 * len(_lib.PROFILE_CLASSES)))()
         _lib.check(lib.dg_profile_report(buf, len(_lib.PROFILE_CLASSES)))
         lib.dg_profile(0)
-        lib.dg_set_tuning(9, prev9); lib.dg_set_tuning(10, prev10)
+        lib.dg_set_tuning(9, prev9); lib.dg_set_tuning(10, prev10); lib.dg_set_tuning(12, prev12)
         prof = {n: {"launches": int(buf[4 * i]), "ms": buf[4 * i + 1], "flops": buf[4 * i + 2], "bytes": buf[4 * i + 3]}
                 for i, n in enumerate(_lib.PROFILE_CLASSES) if buf[4 * i] > 0}
 

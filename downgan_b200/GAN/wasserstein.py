@@ -150,7 +150,7 @@ class WassersteinGAN:
             self._c_adam.step(grads, scale)
         self.last_critic = self._c_scal
 
-    def _generator_lookahead(self, coarse_all: torch.Tensor, save_first: int = 0) -> None:
+    def _generator_lookahead(self, coarse_all: torch.Tensor, save_first: int = 0, first: Optional[tuple] = None) -> None:
         """fake = G(coarse) for several upcoming critic batches in one pass (same generator weights: the
         generator is only updated every `critic_iterations` steps, wasserstein.py:136-137).  The first
         `save_first` samples keep their activations for the generator iteration on that batch."""
@@ -159,8 +159,13 @@ class WassersteinGAN:
         with torch.cuda.device(self.device):
             g = self.G.native(h, total)
             self.G.ensure_packed(g)
-            _lib.check(_lib.load().dg_generator_lookahead(g, coarse_all.data_ptr(), total, int(save_first),
-                                                          _lib.stream_ptr()))
+            if first is not None and save_first <= first[0]:
+                # only the next critic iteration's batch in stream order, the rest overlaps that iteration
+                _lib.check(_lib.load().dg_generator_lookahead_first(g, coarse_all.data_ptr(), total, int(save_first),
+                                                                    int(first[0]), int(first[1]), _lib.stream_ptr()))
+            else:
+                _lib.check(_lib.load().dg_generator_lookahead(g, coarse_all.data_ptr(), total, int(save_first),
+                                                              _lib.stream_ptr()))
 
     def _generator_train_iteration(self, coarse, fine, _saved_forward: bool = False):
         """One generator update (wasserstein.py:58-83).  `_saved_forward` (set by `_train_epoch`'s look-ahead):
@@ -277,12 +282,13 @@ class WassersteinGAN:
                         order = [len(group) - 1] + list(range(len(group) - 1)) if full else list(range(len(group)))
                         coarse_all = torch.cat([group[i][0]["bufs"][0] for i in order], dim=0)
                         save_first = group[-1][0]["bufs"][0].shape[0] if full else 0
-                        self._generator_lookahead(coarse_all, save_first)
                         offs = [0] * len(group)
                         off = 0
                         for i in order:
                             offs[i] = off
                             off += group[i][0]["bufs"][0].shape[0]
+                        self._generator_lookahead(coarse_all, save_first,
+                                                  first=(offs[0], group[0][0]["bufs"][0].shape[0]))
                         offsets.extend(offs)
                         saved_steps = {s + len(group) - 1} if full else set()
                 slot, ev = pending.pop(0)

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "dg_critic_step": (C.c_int, [_P, _P, C.POINTER(Hyper), _P, _P, _P, C.c_int, _P, _P, _P]),
     "dg_generator_step": (C.c_int, [_P, _P, C.POINTER(Hyper), _P, _P, C.c_int, _P, _P, _P]),
     "dg_generator_lookahead": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    "dg_generator_lookahead_first": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "dg_generator_step_saved": (C.c_int, [_P, _P, C.POINTER(Hyper), _P, C.c_int, _P, _P, _P]),
     "dg_critic_step_fake": (C.c_int, [_P, _P, C.POINTER(Hyper), C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     "dg_conv3x3_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -47,6 +47,7 @@ struct SideStream {
     return 0;
   }
   void destroy() {
+    if (s) cudaStreamSynchronize(s);  // a deferred chain may still be using the handle's buffers
     if (fork_ev) cudaEventDestroy(fork_ev);
     if (join_ev) cudaEventDestroy(join_ev);
     if (aux_ev) cudaEventDestroy(aux_ev);
@@ -164,6 +165,7 @@ struct dg_generator {
   float* l1 = nullptr;
   int saved_batch = 0;
   int lookahead = 0;  // samples of g->fake produced by the last dg_generator_lookahead (0: none / overwritten)
+  int ready_lo = 0, ready_hi = 0;  // dg_generator_lookahead_first: samples already final in stream order while side.dirty
 
   int idx_conv1() const { return 0; }
   int idx_db(int r, int d, int k) const { return 1 + (r * 3 + d) * 5 + (k - 1); }
@@ -379,6 +381,7 @@ extern "C" int dg_generator_destroy(dg_generator* g) {
 extern "C" int dg_generator_pack(dg_generator* g, const float* params, void* stream) {
   DG_CHECK(g && params, "dg_generator_pack: null argument");
   cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(g->side.join(st));  // a deferred look-ahead chain (dg_generator_lookahead_first) may still be running
   DG_TRY(pack_weights(params, g->pk, g->pk_u, g->tab_fwd, g->n_fwd, g->max_fwd, st));
   DG_TRY(pack_weights(params, g->pkd, g->pkd_u, g->tab_dgrad, g->n_dgrad, g->max_dgrad, st));
   if (trunk_fused_supported(g->F, g->Hc, g->R, g->bf))
@@ -496,6 +499,7 @@ extern "C" int dg_generator_fwd(dg_generator* g, const float* coarse, int batch,
   DG_CHECK(batch >= 1 && batch <= g->maxB, "dg_generator_fwd: batch %d outside [1,%d]", batch, g->maxB);
   if (!g->packed) { set_error("dg_generator_fwd: dg_generator_pack has not been called"); return DG_ERR_STATE; }
   cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(g->side.join(st));  // a deferred look-ahead chain (dg_generator_lookahead_first) may still be running
   DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), batch, g->Cin, g->Hc, g->Hc, st));
   g->lookahead = 0;
   DG_TRY(gen_forward_internal(g, batch, save ? batch : 0, st));
@@ -682,6 +686,7 @@ static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_co
 extern "C" int dg_generator_bwd(dg_generator* g, const float* d_fake, float* grads_flat, float* d_coarse, void* stream) {
   DG_CHECK(g && d_fake && grads_flat, "dg_generator_bwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(g->side.join(st));  // a deferred look-ahead chain (dg_generator_lookahead_first) may still be running
   if (g->saved_batch <= 0) { set_error("dg_generator_bwd: no saved forward"); return DG_ERR_STATE; }
   DG_TRY(nchw_to_nhwc(d_fake, tv(g->dfake, 0, g->Cout), g->saved_batch, g->Cout, g->Hf, g->Hf, st));
   return gen_backward_internal(g, grads_flat, d_coarse, st);
@@ -1179,6 +1184,7 @@ extern "C" int dg_critic_step(dg_generator* g, dg_critic* c, const dg_hyper* hp,
   DG_CHECK(g->Hf == c->Hf && g->Cout == c->nc, "dg_critic_step: generator output does not match critic input");
   if (!g->packed || !c->packed) { set_error("dg_critic_step: weights not packed"); return DG_ERR_STATE; }
   cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(g->side.join(st));  // a deferred look-ahead chain (dg_generator_lookahead_first) may still be running
   const int B = batch;
   DG_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(float), st));
   // fake = G(coarse): the reference keeps the graph (:35) but discards the generator gradients (:65)
@@ -1200,10 +1206,38 @@ extern "C" int dg_generator_lookahead(dg_generator* g, const float* coarse, int 
   DG_CHECK(save_first >= 0 && save_first <= total, "dg_generator_lookahead: save_first %d outside [0,%d]", save_first, total);
   if (!g->packed) { set_error("dg_generator_lookahead: dg_generator_pack has not been called"); return DG_ERR_STATE; }
   cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(g->side.join(st));  // a deferred look-ahead chain (dg_generator_lookahead_first) may still be running
   DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), total, g->Cin, g->Hc, g->Hc, st));
   DG_TRY(gen_forward_internal(g, total, save_first, st));  // sets saved_batch = save_first
   g->lookahead = total;
   return 0;
+}
+
+extern "C" int dg_generator_lookahead_first(dg_generator* g, const float* coarse, int total, int save_first, int first_offset,
+                                            int first_count, void* stream) {
+  DG_CHECK(g && coarse, "dg_generator_lookahead_first: null argument");
+  DG_CHECK(total >= 1 && total <= g->maxB, "dg_generator_lookahead_first: %d samples outside [1,%d]", total, g->maxB);
+  DG_CHECK(first_offset >= 0 && first_count >= 1 && first_offset + first_count <= total,
+           "dg_generator_lookahead_first: first range [%d,%d) outside [0,%d)", first_offset, first_offset + first_count, total);
+  DG_CHECK(save_first >= 0 && save_first <= first_offset, "dg_generator_lookahead_first: save_first %d > first_offset %d", save_first,
+           first_offset);
+  if (!g_tune[12] || g->side.s == nullptr || first_count == total)
+    return dg_generator_lookahead(g, coarse, total, save_first, stream);
+  if (!g->packed) { set_error("dg_generator_lookahead_first: dg_generator_pack has not been called"); return DG_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(g->side.join(st));
+  DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), total, g->Cin, g->Hc, g->Hc, st));
+  DG_TRY(g->side.fork(st));
+  // the next critic iteration's fakes in stream order ...
+  DG_TRY(gen_forward_range(g, first_offset, first_count, 0, st));
+  // ... everything else (the generator iteration's batch with its saved activations first) behind it on the side stream
+  if (first_offset > 0) DG_TRY(gen_forward_range(g, 0, first_offset, save_first, g->side.s));
+  if (first_offset + first_count < total)
+    DG_TRY(gen_forward_range(g, first_offset + first_count, total - first_offset - first_count, 0, g->side.s));
+  g->saved_batch = save_first;
+  g->lookahead = total;
+  g->ready_lo = first_offset; g->ready_hi = first_offset + first_count;
+  return 0;  // side.dirty stays set: consumers join
 }
 
 extern "C" int dg_critic_step_fake(dg_generator* g, dg_critic* c, const dg_hyper* hp, int fake_offset, const float* fine,
@@ -1218,6 +1252,8 @@ extern "C" int dg_critic_step_fake(dg_generator* g, dg_critic* c, const dg_hyper
   }
   if (!c->packed) { set_error("dg_critic_step_fake: weights not packed"); return DG_ERR_STATE; }
   cudaStream_t st = (cudaStream_t)stream;
+  // fakes outside the range dg_generator_lookahead_first computed in stream order: wait for the deferred chain
+  if (g->side.dirty && !(fake_offset >= g->ready_lo && fake_offset + batch <= g->ready_hi)) DG_TRY(g->side.join(st));
   DG_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(float), st));
   const float* fake = g->fake + (size_t)fake_offset * g->Hf * g->Hf * g->Cout;
   return critic_step_body(g, c, hp, fake, fine, alpha, batch, c_grads_flat, scalars, st);
@@ -1250,6 +1286,7 @@ extern "C" int dg_generator_step(dg_generator* g, dg_critic* c, const dg_hyper* 
   DG_CHECK(g->Hf == c->Hf && g->Cout == c->nc, "dg_generator_step: generator output does not match critic input");
   if (!g->packed || !c->packed) { set_error("dg_generator_step: weights not packed"); return DG_ERR_STATE; }
   cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(g->side.join(st));  // a deferred look-ahead chain (dg_generator_lookahead_first) may still be running
   const int B = batch;
   DG_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(float), st));
   DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), B, g->Cin, g->Hc, g->Hc, st));
@@ -1272,6 +1309,7 @@ extern "C" int dg_generator_step_saved(dg_generator* g, dg_critic* c, const dg_h
     return DG_ERR_STATE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(g->side.join(st));  // a deferred look-ahead chain (dg_generator_lookahead_first) may still be running
   DG_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(float), st));
   return generator_step_body(g, c, hp, fine, batch, g_grads_flat, scalars, st);
 }

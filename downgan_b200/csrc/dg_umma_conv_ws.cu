@@ -510,16 +510,22 @@ bool plan_ws(const ConvOp& op, WsArgs& a, int& ctas_per_sm) {
   int bestTH = 0, best_mt = 0, best_stage = 0, best_cps = 1, NT = 0;
   size_t best_over = 0;
   const int CoE = narrow ? 16 : op.Co;  // MMA columns
+  // DG_WS_FORCE="NT:cps:TH" (0 = free) restricts the search (tools/ws_sweep.py); read on every call
+  int f_nt = 0, f_cps = 0, f_th = 0;
+  if (const char* f = getenv("DG_WS_FORCE")) sscanf(f, "%d:%d:%d", &f_nt, &f_cps, &f_th);
   for (int cand : {256, 128, 64, 32, 16}) {
     if (cand > CoE || CoE % cand) continue;
     if (ncls * cand > 256) continue;
+    if (f_nt && cand != f_nt) continue;
     const size_t wbytes = (size_t)9 * op.Ci * cand * 2;
     if (wbytes > 112 * 1024) continue;
     const int n_chunks = CoE / cand;
     for (int cps = 2; cps >= 1; --cps) {
+      if (f_cps && cps != f_cps) continue;
       const size_t budget = ((cps == 2) ? (size_t)(113 * 1024 - 2048) : (size_t)WS_MAX_SMEM) - 1024;
       const int acc_max = (cps == 2) ? 128 : 256;
       for (int TH = 1; TH <= Ht; ++TH) {
+        if (f_th && TH != f_th) { if (TH > f_th) break; continue; }
         const int span = TH * PW - (PW - Wt);
         const int n_mt = (span + 127) / 128;
         if (n_mt > 8 || n_mt * ncls * cand > acc_max) break;

@@ -164,6 +164,13 @@ int dg_generator_step(dg_generator* g, dg_critic* c, const dg_hyper* hp,
  * `save_first` samples also keep their activations, so that the generator iteration on that batch
  * (dg_generator_step_saved = dg_generator_step without the forward) needs no second forward. */
 int dg_generator_lookahead(dg_generator* g, const float* coarse, int total, int save_first, void* stream);
+/* Same pass, but only samples [first_offset, first_offset + first_count) - the batch of the NEXT critic iteration - are
+ * computed in stream order; the rest of the pass is enqueued on the handle's side stream and overlaps that critic
+ * iteration.  Every later call that touches the generator handle (dg_critic_step_fake for samples outside the first range,
+ * dg_generator_step_saved, any other generator entry point) first joins the side stream, so callers need no extra
+ * synchronisation.  Requires save_first <= first_offset; dg_set_tuning(12, 0) makes it identical to dg_generator_lookahead. */
+int dg_generator_lookahead_first(dg_generator* g, const float* coarse, int total, int save_first, int first_offset,
+                                 int first_count, void* stream);
 int dg_critic_step_fake(dg_generator* g, dg_critic* c, const dg_hyper* hp, int fake_offset,
                         const float* fine, const float* alpha, int batch,
                         float* c_grads_flat, float* scalars, void* stream);
@@ -210,8 +217,10 @@ int dg_profile_report(double* out, int n_classes);
  * generator forward of more than 296 samples (look-ahead pass) split so that its last 32k samples run as a second
  * chain on the side stream (0: one chain).  key 11: classifier head of the fused critic iteration (bias + LeakyReLU,
  * classifier.2, score means, loss seeds, dz of the hidden layer) in one launch (1) or five (0).
+ * key 12: dg_generator_lookahead_first defers everything but the first range to the side stream (1) or computes the whole
+ * pass in stream order (0).
  * Returns the previous value, or DG_ERR_INVALID for an unknown key. */
-#define DG_TUNE_KEYS 12
+#define DG_TUNE_KEYS 13
 int dg_set_tuning(int key, int value);
 
 #ifdef __cplusplus
