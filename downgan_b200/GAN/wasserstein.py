@@ -21,6 +21,7 @@ Differences from the reference that do not change results:
 """
 from __future__ import annotations
 
+import time
 from typing import Optional
 
 import torch
@@ -252,6 +253,7 @@ class WassersteinGAN:
 
             it = iter(dataloader)
             pending = []  # staged batches, oldest first
+            t_enqueue0 = time.perf_counter()
 
             def fill(n):
                 while len(pending) < n:
@@ -314,6 +316,7 @@ class WassersteinGAN:
                     self._log_host = grown
                 self._log_host[k].copy_(self.last_critic, non_blocking=True)
                 logs.append(k)
+            self.last_enqueue_seconds = time.perf_counter() - t_enqueue0  # host time to enqueue the epoch (diagnostic)
             main.synchronize()
         return self._log_host[:len(logs)].clone() if logs else torch.zeros(0, 8)
 

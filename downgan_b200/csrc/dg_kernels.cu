@@ -441,9 +441,47 @@ int colsum_dense_blocks(void* const* d_bufs_dev, int n_blocks, size_t rows, floa
 // ---------------------------------------------------------------------------
 // One pass per table entry: OIHW fp32 -> packed fp32 [tap][row][CoP] and (d.umma) the bf16 tcgen05 B-operand
 // image [(tap*R/8 + row/8)][CoP][8] at the same element offset of `udst`.  32-bit index arithmetic.
+// A launch may carry TWO tables (forward and data-gradient images of one network): rows [0, n1) of the grid's y dimension
+// use (dst, udst, tab), rows [n1, ..) use (dst2, udst2, tab2).
 __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src, float* __restrict__ dst, bf16* __restrict__ udst,
-                                                   const PackDesc* __restrict__ tab, int unpack) {
+                                                   const PackDesc* __restrict__ tab, int unpack, int n1,
+                                                   float* __restrict__ dst2, bf16* __restrict__ udst2,
+                                                   const PackDesc* __restrict__ tab2) {
+  if ((int)blockIdx.y >= n1) { dst = dst2; udst = udst2; tab = tab2 - n1; }
   const PackDesc d = tab[blockIdx.y];
+  if (d.mode == 4) {
+    // linear weight (Co = N rows, Ci = K cols) with the NCHW -> NHWC column permutation (K = C*HW, C = slice_off): per row a
+    // (C x HW) -> (HW x C) transpose through a 32 x 33 shared tile, so both the reads and the writes are coalesced
+    __shared__ float tile[32][33];
+    const unsigned C = (unsigned)d.slice_off, K = (unsigned)d.Ci, HW = K / C;
+    const unsigned tc = (C + 31) / 32, th = (HW + 31) / 32, per_row = tc * th, total = (unsigned)d.Co * per_row;
+    const float* s_base = src + (unpack ? d.dst_off : d.src_off);
+    float* d_base = dst + (unpack ? d.src_off : d.dst_off);
+    const unsigned tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
+    for (unsigned t = blockIdx.x; t < total; t += gridDim.x) {
+      const unsigned j = t / per_row, r = t - j * per_row, c0 = (r / th) * 32, h0 = (r - (r / th) * th) * 32;
+      // flat (reference) layout: [j][c][hw]; packed layout: [j][hw][c]
+      if (!unpack) {
+#pragma unroll
+        for (unsigned i = ty; i < 32; i += 8)
+          if (c0 + i < C && h0 + tx < HW) tile[i][tx] = s_base[(size_t)j * K + (c0 + i) * HW + h0 + tx];
+        __syncthreads();
+#pragma unroll
+        for (unsigned i = ty; i < 32; i += 8)
+          if (h0 + i < HW && c0 + tx < C) d_base[(size_t)j * K + (h0 + i) * C + c0 + tx] = tile[tx][i];
+      } else {
+#pragma unroll
+        for (unsigned i = ty; i < 32; i += 8)
+          if (h0 + i < HW && c0 + tx < C) tile[i][tx] = s_base[(size_t)j * K + (h0 + i) * C + c0 + tx];
+        __syncthreads();
+#pragma unroll
+        for (unsigned i = ty; i < 32; i += 8)
+          if (c0 + i < C && h0 + tx < HW) d_base[(size_t)j * K + (c0 + i) * HW + h0 + tx] = tile[tx][i];
+      }
+      __syncthreads();
+    }
+    return;
+  }
   unsigned n;
   if (d.mode == 5) n = (unsigned)d.Co;
   else if (d.mode == 4) n = (unsigned)d.Co * (unsigned)d.Ci;
@@ -453,16 +491,6 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src
   for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     if (d.mode == 5) {  // bias copy
       d_base[e] = s_base[e];
-      continue;
-    }
-    if (d.mode == 4) {
-      // linear weight (Co=N rows, Ci=K cols) with NCHW->NHWC column permutation: K = C*HW, C = slice_off
-      const unsigned C = (unsigned)d.slice_off, HW = (unsigned)d.Ci / C;
-      const unsigned j = e / (unsigned)d.Ci, k = e - j * (unsigned)d.Ci;  // k in NCHW order: c*HW + hw
-      const unsigned c = k / HW, hw = k - c * HW;
-      const unsigned pk = j * (unsigned)d.Ci + hw * C + c;
-      if (unpack) d_base[e] = s_base[pk];
-      else d_base[pk] = s_base[e];
       continue;
     }
     const unsigned r = e / 9u, tap = e - 9u * r;
@@ -495,13 +523,25 @@ static inline int pack_blocks(int max_elems) {
 }
 int pack_weights(const float* params, float* packed, void* packed_umma, const PackDesc* tab, int n, int max_elems, cudaStream_t st) {
   if (n == 0) return 0;
-  pack_kernel<<<dim3(pack_blocks(max_elems), n), 256, 0, st>>>(params, packed, (bf16*)packed_umma, tab, 0);
+  pack_kernel<<<dim3(pack_blocks(max_elems), n), 256, 0, st>>>(params, packed, (bf16*)packed_umma, tab, 0, n, nullptr, nullptr, nullptr);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+// forward and data-gradient tables of one network in ONE launch
+int pack_weights2(const float* params, float* packed, void* packed_umma, const PackDesc* tab, int n, int max_elems, float* packed2,
+                  void* packed_umma2, const PackDesc* tab2, int n2, int max_elems2, cudaStream_t st) {
+  if (n == 0 || n2 == 0) {
+    DG_TRY(pack_weights(params, packed, packed_umma, tab, n, max_elems, st));
+    return pack_weights(params, packed2, packed_umma2, tab2, n2, max_elems2, st);
+  }
+  pack_kernel<<<dim3(pack_blocks(std::max(max_elems, max_elems2)), n + n2), 256, 0, st>>>(params, packed, (bf16*)packed_umma, tab, 0, n,
+                                                                                       packed2, (bf16*)packed_umma2, tab2);
   DG_LAUNCH_CHECK();
   return 0;
 }
 int unpack_wgrads(const float* packed, float* grads, const PackDesc* tab, int n, int max_elems, cudaStream_t st) {
   if (n == 0) return 0;
-  pack_kernel<<<dim3(pack_blocks(max_elems), n), 256, 0, st>>>(packed, grads, nullptr, tab, 1);
+  pack_kernel<<<dim3(pack_blocks(max_elems), n), 256, 0, st>>>(packed, grads, nullptr, tab, 1, n, nullptr, nullptr, nullptr);
   DG_LAUNCH_CHECK();
   return 0;
 }

@@ -382,8 +382,8 @@ extern "C" int dg_generator_pack(dg_generator* g, const float* params, void* str
   DG_CHECK(g && params, "dg_generator_pack: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   DG_TRY(g->side.join(st));  // a deferred look-ahead chain (dg_generator_lookahead_first) may still be running
-  DG_TRY(pack_weights(params, g->pk, g->pk_u, g->tab_fwd, g->n_fwd, g->max_fwd, st));
-  DG_TRY(pack_weights(params, g->pkd, g->pkd_u, g->tab_dgrad, g->n_dgrad, g->max_dgrad, st));
+  DG_TRY(pack_weights2(params, g->pk, g->pk_u, g->tab_fwd, g->n_fwd, g->max_fwd, g->pkd, g->pkd_u, g->tab_dgrad, g->n_dgrad,
+                       g->max_dgrad, st));
   if (trunk_fused_supported(g->F, g->Hc, g->R, g->bf))
   {
     DG_TRY(pack_trunk_slices(g->pk + g->layers[g->idx_db(0, 0, 1)].pk_off, g->pk_trunk, g->R * 3, 0, st));
@@ -873,8 +873,8 @@ extern "C" int dg_critic_destroy(dg_critic* c) {
 extern "C" int dg_critic_pack(dg_critic* c, const float* params, void* stream) {
   DG_CHECK(c && params, "dg_critic_pack: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  DG_TRY(pack_weights(params, c->pk, c->pk_u, c->tab_fwd, c->n_fwd, c->max_fwd, st));
-  DG_TRY(pack_weights(params, c->pkd, c->pkd_u, c->tab_dgrad, c->n_dgrad, c->max_dgrad, st));
+  DG_TRY(pack_weights2(params, c->pk, c->pk_u, c->tab_fwd, c->n_fwd, c->max_fwd, c->pkd, c->pkd_u, c->tab_dgrad, c->n_dgrad,
+                       c->max_dgrad, st));
   c->packed = true;
   return 0;
 }

@@ -400,7 +400,8 @@ int wgrad_ws(const WgradOp& op, cudaStream_t st) {
   const int cps = (2 * (smem + 1024) <= 227 * 1024) ? 2 : 1;
   // position split: enough CTAs to fill the chip, bounded so that the cross-CTA fp32 reductions stay small
   long long S = (148 * cps + n_chunks - 1) / n_chunks;
-  const long long cap = 3000000LL / (9LL * op.Ci * op.Co) + 1;
+  static const long long cap_elems = getenv("DG_WW_CAP") ? atoll(getenv("DG_WW_CAP")) : 6000000LL;  // (bench sweep: 3 M -> 6 M = -5 % on the class, flat beyond)
+  const long long cap = cap_elems / (9LL * op.Ci * op.Co) + 1;
   if (S > cap) S = cap;
   if (S > a.tiles_total) S = a.tiles_total;
   if (S < 1) S = 1;

@@ -18,7 +18,8 @@ def run(batches, k, label):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); tr._train_epoch([batches[i % 8] for i in range(k)]); e1.record(); torch.cuda.synchronize()
     t1 = time.perf_counter()
-    print(f"{label}: events {e0.elapsed_time(e1)/k:.3f} ms/step, wall {(t1-t0)*1e3/k:.3f} ms/step", flush=True)
+    print(f"{label}: events {e0.elapsed_time(e1)/k:.3f} ms/step, wall {(t1-t0)*1e3/k:.3f} ms/step, "
+          f"host enqueue {tr.last_enqueue_seconds*1e3/k:.3f} ms/step", flush=True)
 def run_plain(k, label):
     tr.num_steps = 0
     torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -30,5 +31,5 @@ def run_plain(k, label):
     torch.cuda.synchronize(); t1 = time.perf_counter()
     print(f"{label}: wall {(t1-t0)*1e3/k:.3f} ms/step, cpu-enqueue {(t_cpu-t0)*1e3/k:.3f} ms/step", flush=True)
 for _ in range(2):
-    run(devb, 20, "epoch(device)"); run(host, 20, "epoch(host)"); run_plain(20, "plain(device)")
+    run(devb, 200, "epoch(device)"); run(host, 200, "epoch(host)"); run_plain(20, "plain(device)")
 os._exit(0)
