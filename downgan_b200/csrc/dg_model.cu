@@ -923,15 +923,18 @@ static int critic_layer_wgrad(dg_critic* c, int i, int s0, int n, int bias_n, bo
 // early != 0: the weight gradient of every conv layer over the chain's samples is enqueued as soon as its dz exists
 // (c->gpk must already be zeroed): early == 1 on the side stream (forked from `st`), early == 2 on `st` itself (the
 // chain already runs on a stream of its own).
+// early_rows > 0 (with early == 1): only rows [s0, s0 + early_rows) and only layers <= early_max_layer go early (the
+// interpolates' rows of the fused 3B batch need the JVP chain first).
 static int critic_backward_chain(dg_critic* c, int NB, int n0, int n1, float* g_out, cudaStream_t st, int early = 0, int s0 = 0,
-                                 bool seeded = false) {
+                                 bool seeded = false, int early_rows = 0, int early_max_layer = 7) {
+  const int en = early_rows > 0 ? early_rows : NB;
   float* dz9 = c->dz9 + (size_t)s0 * FC_HIDDEN;
   const size_t e8 = (size_t)s0 * c->fc_in;
   void* dz8 = c->bf ? (void*)((bf16*)c->dz[8] + e8) : (void*)((float*)c->dz[8] + e8);
   const void* a8 = c->bf ? (const void*)((const bf16*)c->a[8] + e8) : (const void*)((const float*)c->a[8] + e8);
   if (!seeded) DG_TRY(fc2_seed(c->a9 + (size_t)s0 * FC_HIDDEN, c->pk + c->pk_fc2w, c->seed + s0, dz9, NB, FC_HIDDEN, C_SLOPE, st));
   DG_TRY(fc_dgrad(dz9, c->pk + c->pk_fc1w, dz8, c->bf, NB, c->fc_in, FC_HIDDEN, a8, c->bf, C_SLOPE, st));
-  if (early) DG_TRY(critic_layer_wgrad(c, 7, s0, NB, 0, early == 1, st));
+  if (early && early_max_layer >= 7) DG_TRY(critic_layer_wgrad(c, 7, s0, en, 0, early == 1, st));
   for (int i = 7; i >= 1; --i) {  // dz[i] = dgrad_{i+1}(dz[i+1]) * lrelu'(a[i])
     const Layer& l = c->L[i];
     ConvOp op;
@@ -942,7 +945,7 @@ static int critic_backward_chain(dg_critic* c, int NB, int n0, int n1, float* g_
     op.transposed = (l.stride == 2);
     op.act = ACT_MASK; op.slope = C_SLOPE; op.mask = tv_batch(c->act(c->a[i], l.Ci), c->pix(i - 1), s0);
     DG_TRY(run_conv(op, st));
-    if (early) DG_TRY(critic_layer_wgrad(c, i - 1, s0, NB, NB, early == 1, st));
+    if (early && i - 1 <= early_max_layer) DG_TRY(critic_layer_wgrad(c, i - 1, s0, en, en, early == 1, st));
   }
   if (n1 > 0) {
     const Layer& l = c->L[0];
@@ -1023,7 +1026,7 @@ static int critic_gp_first_order(dg_critic* c, const dg_hyper* hp, int n0, int B
 // epilogue thread reads the mask element and overwrites the same element).  Afterwards
 // a[l] = [real acts ; fake acts ; v_l] and dz[l+1] = [dz real ; dz fake ; dz interpolates], so ONE
 // weight-gradient launch per layer over all 3B samples yields  d(E[C(fake)] - E[C(real)])/dW + dGP/dW.
-static int critic_second_order_and_wgrads(dg_critic* c, int B, cudaStream_t st, bool two_chain) {
+static int critic_second_order_and_wgrads(dg_critic* c, int B, cudaStream_t st, bool two_chain, int early_max_layer = -1) {
   const int n0 = 2 * B;
   // The weight gradient of layer i reads a[i] = [real ; fake ; v_{i-1}] and dz[i+1]; nothing later in the call
   // overwrites either, so with the side stream on it is enqueued there as soon as v_{i-1} exists and overlaps the
@@ -1034,6 +1037,8 @@ static int critic_second_order_and_wgrads(dg_critic* c, int B, cudaStream_t st, 
   auto layer_wgrad = [&](int i) {
     // features.0.bias: real + fake samples only (the gradient penalty contributes exactly zero to biases)
     if (two_chain) return critic_layer_wgrad(c, i, n0, B, 0, false, st);
+    // layers whose real + fake rows already went early (during the input-gradient chain): the interpolates' rows remain
+    if (i <= early_max_layer) return critic_layer_wgrad(c, i, n0, B, 0, side_on, st);
     return critic_layer_wgrad(c, i, 0, 3 * B, n0, side_on, st);
   };
   TV v = tv_batch(tv(c->a0, 0, c->nc), (size_t)c->Hf * c->Hf, n0);  // u was written here by gp_scale
@@ -1136,6 +1141,9 @@ static int critic_step_body(dg_generator* g, dg_critic* c, const dg_hyper* hp, c
   DG_TRY(build_critic_input(fine, fake_nhwc, 0, alpha, c->a0, B, c->nc, c->Hf, c->Hf, 0, st));
   const bool two_chain = g_tune[9] >= 2 && c->side.s != nullptr;
   const bool head = !two_chain && g_tune[11] && critic_head_supported(B) && fc_fwd_raw_supported(c->fc_in, FC_HIDDEN);
+  // g_tune[13] = k > 0: the real + fake rows of the weight gradients of layers 0 .. k-1 (the HBM-bound ones, which scale with
+  // the rows) run on the side stream during the input-gradient chain, where that stream is otherwise idle
+  const int early_ml = (!two_chain && g_tune[9] == 1 && c->side.s != nullptr) ? g_tune[13] - 1 : -1;
   if (!head) {
     critic_seed_kernel<<<(3 * B + 255) / 256, 256, 0, st>>>(c->seed, B);
     DG_LAUNCH_CHECK();
@@ -1162,15 +1170,15 @@ static int critic_step_body(dg_generator* g, dg_critic* c, const dg_hyper* hp, c
     DG_TRY(critic_forward_internal(c, 3 * B, st, 0, true));
     DG_TRY(critic_head(c->a9, c->pk + c->pk_fc1b, c->pk + c->pk_fc2w, c->pk + c->pk_fc2b, c->scores, c->seed, c->dz9, scalars, B,
                        FC_HIDDEN, C_SLOPE, st));
-    DG_TRY(critic_backward_chain(c, 3 * B, 2 * B, B, c->g, st, 0, 0, true));
+    DG_TRY(critic_backward_chain(c, 3 * B, 2 * B, B, c->g, st, early_ml >= 0 ? 1 : 0, 0, true, 2 * B, early_ml));
   } else {
     DG_TRY(critic_forward_internal(c, 3 * B, st));
     DG_TRY(critic_means(c->scores, B, scalars, st));
-    DG_TRY(critic_backward_chain(c, 3 * B, 2 * B, B, c->g, st));
+    DG_TRY(critic_backward_chain(c, 3 * B, 2 * B, B, c->g, st, early_ml >= 0 ? 1 : 0, 0, false, 2 * B, early_ml));
   }
   DG_TRY(critic_gp_first_order(c, hp, 2 * B, B, scalars, 1, nullptr, st,
                                c->a0 + (size_t)2 * B * c->Hf * c->Hf * c->nc));  // u overwrites the interpolates
-  DG_TRY(critic_second_order_and_wgrads(c, B, st, two_chain));
+  DG_TRY(critic_second_order_and_wgrads(c, B, st, two_chain, early_ml));
   DG_TRY(unpack_wgrads(c->gpk, c_grads_flat, c->tab_fwd, c->n_fwd, c->max_fwd, st));
   c->saved_batch = 0;
   (void)g;

@@ -219,8 +219,10 @@ int dg_profile_report(double* out, int n_classes);
  * classifier.2, score means, loss seeds, dz of the hidden layer) in one launch (1) or five (0).
  * key 12: dg_generator_lookahead_first defers everything but the first range to the side stream (1) or computes the whole
  * pass in stream order (0).
+ * key 13 = k > 0 (with key 9 == 1): the real + fake rows of the weight gradients of critic layers 0 .. k-1 are enqueued on
+ * the side stream during the input-gradient chain, their interpolates' rows during the JVP chain (0: one 3B launch per layer).
  * Returns the previous value, or DG_ERR_INVALID for an unknown key. */
-#define DG_TUNE_KEYS 13
+#define DG_TUNE_KEYS 14
 int dg_set_tuning(int key, int value);
 
 #ifdef __cplusplus
