@@ -66,6 +66,8 @@ _SIGNATURES = {
                                C.c_int, C.c_float, _P]),
     "dg_critic_step": (C.c_int, [_P, _P, C.POINTER(Hyper), _P, _P, _P, C.c_int, _P, _P, _P]),
     "dg_generator_step": (C.c_int, [_P, _P, C.POINTER(Hyper), _P, _P, C.c_int, _P, _P, _P]),
+    "dg_critic_defer_conv_grads": (C.c_int, [_P, C.c_int]),
+    "dg_critic_step_finish": (C.c_int, [_P, _P, _P]),
     "dg_generator_lookahead": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     "dg_generator_lookahead_first": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "dg_generator_step_saved": (C.c_int, [_P, _P, C.POINTER(Hyper), _P, C.c_int, _P, _P, _P]),

@@ -722,6 +722,9 @@ struct dg_critic {
   void *v0 = nullptr, *v1 = nullptr;       // JVP ping-pong
   float *sumsq = nullptr, *coef = nullptr, *norms = nullptr, *scal = nullptr;
   SideStream side;
+  int defer_conv = 0;           // dg_critic_defer_conv_grads: the fused iteration returns before its conv weight gradients are final
+  bool pending_finish = false;  // ... and dg_critic_step_finish has not been called yet
+  static constexpr int N_CONV_ENTRIES = 9;  // tab_fwd order: 8 conv weights, features.0.bias, then the 4 classifier tensors
   int saved_batch = 0;
   TV act(void* p, int pitch, int coff = 0) const { return tv(p, bf, pitch, coff); }
   size_t pix(int l) const { return (size_t)Hout[l] * Hout[l]; }  // l = 0..7 -> a[l+1]
@@ -871,6 +874,7 @@ extern "C" int dg_critic_destroy(dg_critic* c) {
   return 0;
 }
 extern "C" int dg_critic_pack(dg_critic* c, const float* params, void* stream) {
+  if (c && c->pending_finish) { set_error("dg_critic_pack: dg_critic_step_finish has not been called"); return DG_ERR_STATE; }
   DG_CHECK(c && params, "dg_critic_pack: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   DG_TRY(pack_weights2(params, c->pk, c->pk_u, c->tab_fwd, c->n_fwd, c->max_fwd, c->pkd, c->pkd_u, c->tab_dgrad, c->n_dgrad,
@@ -1026,7 +1030,8 @@ static int critic_gp_first_order(dg_critic* c, const dg_hyper* hp, int n0, int B
 // epilogue thread reads the mask element and overwrites the same element).  Afterwards
 // a[l] = [real acts ; fake acts ; v_l] and dz[l+1] = [dz real ; dz fake ; dz interpolates], so ONE
 // weight-gradient launch per layer over all 3B samples yields  d(E[C(fake)] - E[C(real)])/dW + dGP/dW.
-static int critic_second_order_and_wgrads(dg_critic* c, int B, cudaStream_t st, bool two_chain, int early_max_layer = -1) {
+static int critic_second_order_and_wgrads(dg_critic* c, int B, cudaStream_t st, bool two_chain, int early_max_layer = -1,
+                                          bool defer_join = false) {
   const int n0 = 2 * B;
   // The weight gradient of layer i reads a[i] = [real ; fake ; v_{i-1}] and dz[i+1]; nothing later in the call
   // overwrites either, so with the side stream on it is enqueued there as soon as v_{i-1} exists and overlaps the
@@ -1069,12 +1074,13 @@ static int critic_second_order_and_wgrads(dg_critic* c, int B, cudaStream_t st, 
   if (!two_chain) {
     if (!side_on)
       for (int i = 0; i < 8; ++i) DG_TRY(layer_wgrad(i));
-    DG_TRY(c->side.join(st));
+    if (!defer_join) DG_TRY(c->side.join(st));  // deferred: dg_critic_step_finish joins
   }
   return 0;
 }
 
 extern "C" int dg_critic_fwd(dg_critic* c, const float* x, int batch, float* scores, void* stream) {
+  if (c && c->pending_finish) { set_error("dg_critic_fwd: dg_critic_step_finish has not been called"); return DG_ERR_STATE; }
   DG_CHECK(c && x && scores, "dg_critic_fwd: null argument");
   DG_CHECK(batch >= 1 && batch <= c->NBmax, "dg_critic_fwd: batch %d outside [1,%d]", batch, c->NBmax);
   if (!c->packed) { set_error("dg_critic_fwd: dg_critic_pack has not been called"); return DG_ERR_STATE; }
@@ -1087,6 +1093,7 @@ extern "C" int dg_critic_fwd(dg_critic* c, const float* x, int batch, float* sco
 }
 
 extern "C" int dg_critic_bwd(dg_critic* c, const float* d_scores, float* grads_flat, float* d_x, void* stream) {
+  if (c && c->pending_finish) { set_error("dg_critic_bwd: dg_critic_step_finish has not been called"); return DG_ERR_STATE; }
   DG_CHECK(c && d_scores, "dg_critic_bwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int B = c->saved_batch;
@@ -1106,6 +1113,7 @@ extern "C" int dg_critic_bwd(dg_critic* c, const float* d_scores, float* grads_f
 // WassersteinGAN._gp (wasserstein.py:87-117).
 extern "C" int dg_gp(dg_critic* c, const dg_hyper* hp, const float* real, const float* fake, const float* alpha, int batch,
                      float* gp_out, float* norms, float* grads_flat, void* stream) {
+  if (c && c->pending_finish) { set_error("dg_gp: dg_critic_step_finish has not been called"); return DG_ERR_STATE; }
   DG_CHECK(c && hp && real && fake && alpha && gp_out, "dg_gp: null argument");
   DG_CHECK(batch >= 1 && batch <= c->maxB, "dg_gp: batch %d outside [1,%d]", batch, c->maxB);
   if (!c->packed) { set_error("dg_gp: dg_critic_pack has not been called"); return DG_ERR_STATE; }
@@ -1178,8 +1186,16 @@ static int critic_step_body(dg_generator* g, dg_critic* c, const dg_hyper* hp, c
   }
   DG_TRY(critic_gp_first_order(c, hp, 2 * B, B, scalars, 1, nullptr, st,
                                c->a0 + (size_t)2 * B * c->Hf * c->Hf * c->nc));  // u overwrites the interpolates
-  DG_TRY(critic_second_order_and_wgrads(c, B, st, two_chain, early_ml));
-  DG_TRY(unpack_wgrads(c->gpk, c_grads_flat, c->tab_fwd, c->n_fwd, c->max_fwd, st));
+  const bool defer = c->defer_conv && !two_chain && c->n_fwd > dg_critic::N_CONV_ENTRIES;
+  DG_TRY(critic_second_order_and_wgrads(c, B, st, two_chain, early_ml, defer));
+  if (defer) {
+    // the classifier gradients (74 % of the bucket) are final on this stream: unpack them now so that the caller can start
+    // their all-reduce while the conv weight gradients are still running on the side stream
+    DG_TRY(unpack_wgrads(c->gpk, c_grads_flat, c->tab_fwd + dg_critic::N_CONV_ENTRIES, c->n_fwd - dg_critic::N_CONV_ENTRIES, c->max_fwd, st));
+    c->pending_finish = true;
+  } else {
+    DG_TRY(unpack_wgrads(c->gpk, c_grads_flat, c->tab_fwd, c->n_fwd, c->max_fwd, st));
+  }
   c->saved_batch = 0;
   (void)g;
   return 0;
@@ -1187,6 +1203,7 @@ static int critic_step_body(dg_generator* g, dg_critic* c, const dg_hyper* hp, c
 
 extern "C" int dg_critic_step(dg_generator* g, dg_critic* c, const dg_hyper* hp, const float* coarse, const float* fine,
                               const float* alpha, int batch, float* c_grads_flat, float* scalars, void* stream) {
+  if (c && c->pending_finish) { set_error("dg_critic_step: dg_critic_step_finish has not been called"); return DG_ERR_STATE; }
   DG_CHECK(g && c && hp && coarse && fine && alpha && c_grads_flat && scalars, "dg_critic_step: null argument");
   DG_CHECK(batch >= 1 && batch <= g->maxB && batch <= c->maxB, "dg_critic_step: batch %d too large", batch);
   DG_CHECK(g->Hf == c->Hf && g->Cout == c->nc, "dg_critic_step: generator output does not match critic input");
@@ -1201,6 +1218,26 @@ extern "C" int dg_critic_step(dg_generator* g, dg_critic* c, const dg_hyper* hp,
   g->saved_batch = 0;
   g->lookahead = 0;
   return critic_step_body(g, c, hp, g->fake, fine, alpha, B, c_grads_flat, scalars, st);
+}
+
+// Data-parallel overlap: with the switch on, dg_critic_step / dg_critic_step_fake return once the classifier gradients are
+// unpacked (the conv weight gradients still run on the side stream); the caller starts the all-reduce of
+// c_grads_flat[dg_critic_param_offset(cfg, 9) ..] and then calls dg_critic_step_finish, which joins the side stream and
+// unpacks the conv gradients c_grads_flat[.. offset).
+extern "C" int dg_critic_defer_conv_grads(dg_critic* c, int on) {
+  DG_CHECK(c, "dg_critic_defer_conv_grads: null argument");
+  if (c->pending_finish) { set_error("dg_critic_defer_conv_grads: dg_critic_step_finish has not been called"); return DG_ERR_STATE; }
+  c->defer_conv = on ? 1 : 0;
+  return 0;
+}
+extern "C" int dg_critic_step_finish(dg_critic* c, float* c_grads_flat, void* stream) {
+  DG_CHECK(c && c_grads_flat, "dg_critic_step_finish: null argument");
+  if (!c->pending_finish) { set_error("dg_critic_step_finish: no deferred critic iteration"); return DG_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(c->side.join(st));
+  DG_TRY(unpack_wgrads(c->gpk, c_grads_flat, c->tab_fwd, dg_critic::N_CONV_ENTRIES, c->max_fwd, st));
+  c->pending_finish = false;
+  return 0;
 }
 
 // Look-ahead generator forward: the critic iterations between two generator updates all see the SAME generator
@@ -1250,6 +1287,7 @@ extern "C" int dg_generator_lookahead_first(dg_generator* g, const float* coarse
 
 extern "C" int dg_critic_step_fake(dg_generator* g, dg_critic* c, const dg_hyper* hp, int fake_offset, const float* fine,
                                    const float* alpha, int batch, float* c_grads_flat, float* scalars, void* stream) {
+  if (c && c->pending_finish) { set_error("dg_critic_step_fake: dg_critic_step_finish has not been called"); return DG_ERR_STATE; }
   DG_CHECK(g && c && hp && fine && alpha && c_grads_flat && scalars, "dg_critic_step_fake: null argument");
   DG_CHECK(batch >= 1 && batch <= c->maxB, "dg_critic_step_fake: batch %d too large", batch);
   DG_CHECK(g->Hf == c->Hf && g->Cout == c->nc, "dg_critic_step_fake: generator output does not match critic input");
@@ -1289,6 +1327,7 @@ static int generator_step_body(dg_generator* g, dg_critic* c, const dg_hyper* hp
 
 extern "C" int dg_generator_step(dg_generator* g, dg_critic* c, const dg_hyper* hp, const float* coarse, const float* fine,
                                  int batch, float* g_grads_flat, float* scalars, void* stream) {
+  if (c && c->pending_finish) { set_error("dg_generator_step: dg_critic_step_finish has not been called"); return DG_ERR_STATE; }
   DG_CHECK(g && c && hp && coarse && fine && g_grads_flat && scalars, "dg_generator_step: null argument");
   DG_CHECK(batch >= 1 && batch <= g->maxB && batch <= c->maxB, "dg_generator_step: batch %d too large", batch);
   DG_CHECK(g->Hf == c->Hf && g->Cout == c->nc, "dg_generator_step: generator output does not match critic input");
@@ -1307,6 +1346,7 @@ extern "C" int dg_generator_step(dg_generator* g, dg_critic* c, const dg_hyper* 
 // save_first == batch) is still resident: the generator weights have not changed since, so G(coarse) is not recomputed.
 extern "C" int dg_generator_step_saved(dg_generator* g, dg_critic* c, const dg_hyper* hp, const float* fine, int batch,
                                        float* g_grads_flat, float* scalars, void* stream) {
+  if (c && c->pending_finish) { set_error("dg_generator_step_saved: dg_critic_step_finish has not been called"); return DG_ERR_STATE; }
   DG_CHECK(g && c && hp && fine && g_grads_flat && scalars, "dg_generator_step_saved: null argument");
   DG_CHECK(batch >= 1 && batch <= c->maxB, "dg_generator_step_saved: batch %d too large", batch);
   DG_CHECK(g->Hf == c->Hf && g->Cout == c->nc, "dg_generator_step_saved: generator output does not match critic input");

@@ -40,3 +40,10 @@ def allreduce_sum_(flat: torch.Tensor) -> float:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         return 1.0 / w
     return 1.0
+
+
+def allreduce_sum_async_(flat: torch.Tensor):
+    """Asynchronous in-place sum-all-reduce (world > 1): the collective is ordered after the work already enqueued on the
+    current stream and runs on the backend's own stream; ``.wait()`` on the returned handle orders the current stream
+    after it.  Used to overlap the classifier-gradient bucket with the conv weight gradients still in flight."""
+    return dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)

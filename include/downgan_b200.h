@@ -177,6 +177,15 @@ int dg_critic_step_fake(dg_generator* g, dg_critic* c, const dg_hyper* hp, int f
 int dg_generator_step_saved(dg_generator* g, dg_critic* c, const dg_hyper* hp, const float* fine, int batch,
                             float* g_grads_flat, float* scalars_out, void* stream);
 
+/* Data-parallel overlap of the gradient all-reduce with the backward (the one exchange step of the path).
+ * After dg_critic_defer_conv_grads(c, 1), dg_critic_step / dg_critic_step_fake return as soon as the classifier gradients
+ * c_grads_flat[dg_critic_param_offset(cfg, 9) ..) are final in stream order, while the conv weight gradients still run on
+ * the handle's side stream; the caller starts the all-reduce of that slice and calls dg_critic_step_finish, which joins the
+ * side stream and writes the conv gradients c_grads_flat[0 .. offset).  Until then every other critic entry point
+ * returns DG_ERR_STATE. */
+int dg_critic_defer_conv_grads(dg_critic* c, int on);
+int dg_critic_step_finish(dg_critic* c, float* c_grads_flat, void* stream);
+
 /* ---- unit-testable conv primitives (NCHW fp32 in/out, OIHW fp32 weights)
  * 3x3, padding 1, stride 1 or 2.  `precision` selects the kernel family.
  * Replaces the cudnn_convolution / convolution_backward calls behind
