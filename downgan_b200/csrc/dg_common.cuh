@@ -172,6 +172,7 @@ int colsum(TV dy, size_t pixels, int C, float* out, cudaStream_t st);
 // Streams the library creates for overlapped work get their own column-sum scratch slot (1 or 2); every other
 // stream shares slot 0 (one caller stream at a time per process, include/downgan_b200.h threading note).
 void register_side_stream(cudaStream_t st, int slot);
+void unregister_side_stream(cudaStream_t st);
 
 // linear layers (critic classifier)
 int fc_fwd(const void* x, int x_bf, const float* w, const float* bias, float* y, int NB, int K, int N,

@@ -6,6 +6,8 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <utility>
+#include <vector>
 
 #include "dg_common.cuh"
 
@@ -277,13 +279,21 @@ int wgrad_direct(const WgradOp& op, cudaStream_t st) {
 constexpr int COLSUM_MAX_BLOCKS = 1024, COLSUM_MAX_C = 256, COLSUM_SLOTS = 3;
 __device__ float g_colsum_parts[COLSUM_SLOTS][COLSUM_MAX_BLOCKS * COLSUM_MAX_C];
 __device__ unsigned int g_colsum_dones[COLSUM_SLOTS] = {0, 0, 0};
-static cudaStream_t g_side_streams[COLSUM_SLOTS] = {nullptr, nullptr, nullptr};
+// every handle's side stream is registered (several handles may share a slot: their side streams never carry column
+// sums at the same time - a call joins its side stream before it returns, and the deferred look-ahead chain has none)
+static std::vector<std::pair<cudaStream_t, int>> g_side_streams;
 void register_side_stream(cudaStream_t st, int slot) {
-  if (slot >= 1 && slot < COLSUM_SLOTS) g_side_streams[slot] = st;
+  unregister_side_stream(st);
+  if (st && slot >= 1 && slot < COLSUM_SLOTS) g_side_streams.emplace_back(st, slot);
+}
+void unregister_side_stream(cudaStream_t st) {
+  for (size_t i = 0; i < g_side_streams.size();)
+    if (g_side_streams[i].first == st) g_side_streams.erase(g_side_streams.begin() + i);
+    else ++i;
 }
 static int colsum_slot(cudaStream_t st) {
-  for (int i = 1; i < COLSUM_SLOTS; ++i)
-    if (g_side_streams[i] && g_side_streams[i] == st) return i;
+  for (const auto& e : g_side_streams)
+    if (e.first == st) return e.second;
   return 0;
 }
 

@@ -48,6 +48,7 @@ struct SideStream {
   }
   void destroy() {
     if (s) cudaStreamSynchronize(s);  // a deferred chain may still be using the handle's buffers
+    if (s) unregister_side_stream(s);
     if (fork_ev) cudaEventDestroy(fork_ev);
     if (join_ev) cudaEventDestroy(join_ev);
     if (aux_ev) cudaEventDestroy(aux_ev);
