@@ -160,3 +160,38 @@ def test_lookahead_epoch_equals_plain_iterations():
     # would instead show up in the critic scalars at O(1).
     assert pu.rel(logs[True], logs[False]) < 1e-3
     assert pu.rel(logs[(True, "p")], logs[(False, "p")]) < 2e-2
+
+
+def test_deferred_conv_gradients_equal_plain_step():
+    """Data-parallel overlap hook: with dg_critic_defer_conv_grads the critic iteration returns with the classifier gradients
+    final and the conv gradients pending; after dg_critic_step_finish the bucket must equal the plain iteration's (same kernels;
+    fp32 atomics -> tolerance).  Until the finish call every other critic entry point refuses to run."""
+    G, C, _, _ = pu.build_pair(CFG2_G, CFG2_C, "bf16", seed=1, critic_scale=1.9)
+    coarse, fine, alpha = synth_batch(8, 2, 16, seed=5, aseed=6)
+    tr = pu.WassersteinGAN(G, C, None, None)
+    lib = _lib.load()
+    b = coarse.shape[0]
+    cd, fd, ad = coarse.cuda(), fine.cuda(), alpha.reshape(b).cuda().contiguous()
+    g, c = tr._handles(cd)
+    off = C.param_offsets()[9]
+
+    def step(defer):
+        sc = torch.zeros(8, device="cuda")
+        cg = torch.full_like(C.flat_params(), float("nan"))
+        _lib.check(lib.dg_critic_defer_conv_grads(c, 1 if defer else 0))
+        _lib.check(lib.dg_critic_step(g, c, tr._hyper(), cd.data_ptr(), fd.data_ptr(), ad.data_ptr(), b, cg.data_ptr(),
+                                      sc.data_ptr(), _lib.stream_ptr()))
+        if defer:
+            torch.cuda.synchronize()
+            assert torch.isfinite(cg[off:]).all(), "classifier gradients must be final before the finish call"
+            assert lib.dg_critic_pack(c, C.flat_params().data_ptr(), _lib.stream_ptr()) != 0, "pending finish must be refused"
+            _lib.check(lib.dg_critic_step_finish(c, cg.data_ptr(), _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        return sc.cpu(), cg.cpu()
+
+    sc0, g0 = step(False)
+    sc1, g1 = step(True)
+    _lib.check(lib.dg_critic_defer_conv_grads(c, 0))
+    assert torch.isfinite(g1).all()
+    assert pu.rel(sc1, sc0) < 1e-5
+    assert pu.rel(g1[off:], g0[off:]) < 1e-4 and pu.rel(g1[:off], g0[:off]) < 1e-4
