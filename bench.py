@@ -355,7 +355,7 @@ def main():
                     "hbm_peak_gbs": hbm}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported at N=1 only (the reference arm covers every N)
         secs, smp = cpu_oracle_steps(5, 1, 16)
         cores = os.cpu_count() or 1
         cpu = {"value": smp / secs, "unit": "samples/s", "cores": cores, "kind": "port",
