@@ -186,6 +186,11 @@ int fc2_fwd(const float* a, const float* w, const float* bias, float* s, int NB,
 int fc2_seed(const float* a9, const float* w2, const float* seed, float* dz9, int NB, int K, float slope, cudaStream_t st);
 
 int critic_means(const float* scores, int B, float* scalars, cudaStream_t st);
+// tcgen05 classifier kernels (dg_umma_fc.cu): behind dg_set_tuning(14, 1), not yet validated on hardware
+bool fc_umma_supported(int NB, int K, int N, int x_bf);
+int fc_fwd_umma(const void* x, const float* w, float* y, int NB, int K, int N, cudaStream_t st);  // y (zeroed) += x w^T
+int fc_dgrad_umma(const float* dz, const float* w, void* dx, int NB, int K, int N, const void* mask, float slope, cudaStream_t st);
+int fc_wgrad_umma(const float* dz, const void* x, float* dw, int NB, int K, int N, cudaStream_t st);  // dw += dz^T x
 bool fc_fwd_raw_supported(int K, int N);
 int fc_fwd_raw(const void* x, int x_bf, const float* w, float* y, int NB, int K, int N, cudaStream_t st);  // y = x w^T
 bool critic_head_supported(int B);

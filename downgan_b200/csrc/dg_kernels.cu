@@ -749,6 +749,7 @@ int fc_fwd_raw(const void* x, int x_bf, const float* w, float* y, int NB, int K,
   const int kchunk = ((K + splits - 1) / splits + FCF_BK - 1) / FCF_BK * FCF_BK;
   splits = (K + kchunk - 1) / kchunk;
   DG_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)NB * N, st));
+  if (fc_umma_supported(NB, K, N, x_bf)) return fc_fwd_umma(x, w, y, NB, K, N, st);
   if (x_bf) fc_fwd_tiled_kernel<true><<<dim3(nbt, splits), 256, 0, st>>>(x, w, y, NB, K, N, kchunk);
   else fc_fwd_tiled_kernel<false><<<dim3(nbt, splits), 256, 0, st>>>(x, w, y, NB, K, N, kchunk);
   DG_LAUNCH_CHECK();
@@ -832,9 +833,12 @@ int fc_fwd(const void* x, int x_bf, const float* w, const float* bias, float* y,
   const int kchunk = ((K + splits - 1) / splits + FCF_BK - 1) / FCF_BK * FCF_BK;
   splits = (K + kchunk - 1) / kchunk;
   DG_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)NB * N, st));
-  if (x_bf) fc_fwd_tiled_kernel<true><<<dim3(nbt, splits), 256, 0, st>>>(x, w, y, NB, K, N, kchunk);
-  else fc_fwd_tiled_kernel<false><<<dim3(nbt, splits), 256, 0, st>>>(x, w, y, NB, K, N, kchunk);
-  DG_LAUNCH_CHECK();
+  if (fc_umma_supported(NB, K, N, x_bf)) DG_TRY(fc_fwd_umma(x, w, y, NB, K, N, st));
+  else {
+    if (x_bf) fc_fwd_tiled_kernel<true><<<dim3(nbt, splits), 256, 0, st>>>(x, w, y, NB, K, N, kchunk);
+    else fc_fwd_tiled_kernel<false><<<dim3(nbt, splits), 256, 0, st>>>(x, w, y, NB, K, N, kchunk);
+    DG_LAUNCH_CHECK();
+  }
   fc_finish_kernel<<<(NB * N + 255) / 256, 256, 0, st>>>(y, bias, NB, N, act, slope, mask);
   DG_LAUNCH_CHECK();
   return 0;
@@ -882,6 +886,7 @@ __global__ void __launch_bounds__(256) fc_dgrad_kernel(const float* __restrict__
 int fc_dgrad(const float* dz, const float* w, void* dx, int dx_bf, int NB, int K, int N, const void* mask, int mask_bf,
              float slope, cudaStream_t st) {
   Prof prof(PC_FC, 2.0 * NB * N * K, (double)N * K * 4.0 + (double)NB * K * (dx_bf ? 2 : 4), st);
+  if (mask && mask_bf && fc_umma_supported(NB, K, N, dx_bf)) return fc_dgrad_umma(dz, w, dx, NB, K, N, mask, slope, st);
   fc_dgrad_kernel<<<dim3((K + 255) / 256, (NB + FCD_BB - 1) / FCD_BB), 256, N * FCD_BB * sizeof(float), st>>>(
       dz, w, dx, dx_bf, NB, K, N, mask, mask_bf, slope);
   DG_LAUNCH_CHECK();
@@ -926,6 +931,7 @@ __global__ void __launch_bounds__(256) fc_wgrad_kernel(const float* __restrict__
 int fc_wgrad(const float* dz, const void* x, int x_bf, float* dw, int NB, int K, int N, cudaStream_t st) {
   DG_CHECK(NB <= FCW_MAXB, "fc_wgrad: batch %d > %d", NB, FCW_MAXB);
   Prof prof(PC_FC, 2.0 * NB * N * K, (double)N * K * 8.0 + (double)NB * K * (x_bf ? 2 : 4), st);
+  if (fc_umma_supported(NB, K, N, x_bf)) return fc_wgrad_umma(dz, x, dw, NB, K, N, st);
   fc_wgrad_kernel<<<dim3((K + 255) / 256, (N + FCW_BJ - 1) / FCW_BJ), 256, (size_t)NB * FCW_BJ * sizeof(float), st>>>(dz, x, x_bf, dw,
                                                                                                                    NB, K, N);
   DG_LAUNCH_CHECK();
@@ -1202,7 +1208,7 @@ CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank,
   return fn(map, dt, rank, addr, dims, strides, box, estr, il, sw, l2, oob);
 }
 }  // namespace dg
-namespace dg { int g_tune[DG_TUNE_KEYS] = {1, 1, 1, 0, 1, 0, 1, 1, 1, 1, 4, 1, 1, 3}; }  // see include/downgan_b200.h: dg_set_tuning
+namespace dg { int g_tune[DG_TUNE_KEYS] = {1, 1, 1, 0, 1, 0, 1, 1, 1, 1, 4, 1, 1, 3, 0}; }  // see include/downgan_b200.h: dg_set_tuning
 extern "C" int dg_set_tuning(int key, int value) {
   if (key < 0 || key >= DG_TUNE_KEYS) { dg::set_error("dg_set_tuning: unknown key %d", key); return DG_ERR_INVALID; }
   const int prev = dg::g_tune[key];

@@ -230,8 +230,10 @@ int dg_profile_report(double* out, int n_classes);
  * pass in stream order (0).
  * key 13 = k > 0 (with key 9 == 1): the real + fake rows of the weight gradients of critic layers 0 .. k-1 are enqueued on
  * the side stream during the input-gradient chain, their interpolates' rows during the JVP chain (0: one 3B launch per layer).
+ * key 14: classifier.0 products (forward, input gradient, weight gradient) on the tcgen05 kernels of csrc/dg_umma_fc.cu (1)
+ * or on the CUDA-core kernels (0, default: the tcgen05 variants have not been validated on hardware yet).
  * Returns the previous value, or DG_ERR_INVALID for an unknown key. */
-#define DG_TUNE_KEYS 14
+#define DG_TUNE_KEYS 15
 int dg_set_tuning(int key, int value);
 
 #ifdef __cplusplus
