@@ -226,6 +226,34 @@ class WassersteinGAN:
         self.last_gp_norms = norms
         return (out[0], grads) if want_grads else out[0]
 
+    def prepare(self, coarse_shape, fine_shape, with_alpha: bool = True) -> None:
+        """Allocate everything `_train_epoch` needs for host batches of these shapes (staging slots, the look-ahead
+        buffer, the pinned scalar ring, native handles sized for the look-ahead pass) so that the first epoch neither
+        allocates nor synchronises inside its loop.  Optional: `_train_epoch` allocates lazily without it."""
+        dev = self.device
+        n_critic = int(hp.critic_iterations)
+        b = int(coarse_shape[0])
+        with torch.cuda.device(dev):
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            shapes = [tuple(coarse_shape), tuple(fine_shape)] + ([(b, 1, 1, 1)] if with_alpha else [])
+            self._slots = [{"bufs": [torch.empty(sh, device=dev, dtype=torch.float32) for sh in shapes], "done": None}
+                           for _ in range(n_critic + 3)]
+            self._slot_i = 0
+            self._la_buf = torch.empty(((n_critic + 1) * b,) + tuple(coarse_shape[1:]), device=dev, dtype=torch.float32)
+            if getattr(self, "_log_host", None) is None:
+                self._log_host = torch.empty(1024, 8, dtype=torch.float32, pin_memory=True)
+            la = (n_critic + 1) * b if getattr(self, "lookahead", True) and n_critic > 1 else b
+            g = self.G.native(int(coarse_shape[2]), la)
+            c = self.C.native(b)
+            self.G.ensure_packed(g)
+            self.C.ensure_packed(c)
+            if self._c_scal is None or self._c_scal.device != dev:
+                self._c_scal = torch.zeros(8, device=dev)
+            if self._g_scal is None or self._g_scal.device != dev:
+                self._g_scal = torch.zeros(8, device=dev)
+            torch.cuda.synchronize(dev)
+
     # ---- epoch loop (wasserstein.py:120-189, logging/plotting out of scope) ----
     def _train_epoch(self, dataloader, testdataloader=None, epoch: int = 0):
         """One pass over `dataloader` with the reference schedule (wasserstein.py:131-147): a critic
@@ -255,10 +283,15 @@ class WassersteinGAN:
                 slot = self._slots[self._slot_i % len(self._slots)]
                 self._slot_i += 1
                 shapes = [tuple(t.shape) for t in src]
-                if slot["bufs"] is None or [tuple(b.shape) for b in slot["bufs"]] != shapes:
-                    slot["bufs"] = [torch.empty(s, device=dev, dtype=torch.float32) for s in shapes]
-                    slot["done"] = None
                 with torch.cuda.stream(self._copy_stream):
+                    if slot["bufs"] is None or [tuple(b.shape) for b in slot["bufs"]] != shapes:
+                        # (re)allocated ON the copy stream: the caching allocator may hand back a block whose last user is
+                        # still queued on the main stream (a freed look-ahead or alpha temporary), so the first write into a
+                        # fresh block is also ordered after everything the main stream has enqueued so far
+                        slot["bufs"] = [torch.empty(sh, device=dev, dtype=torch.float32) for sh in shapes]
+                        fresh = torch.cuda.Event()
+                        fresh.record(main)
+                        self._copy_stream.wait_event(fresh)
                     if slot["done"] is not None:
                         self._copy_stream.wait_event(slot["done"])
                     for b, t in zip(slot["bufs"], src):
@@ -298,13 +331,23 @@ class WassersteinGAN:
                         # it goes first in the pass and keeps its activations, so that iteration needs no forward
                         full = len(group) == want
                         order = [len(group) - 1] + list(range(len(group) - 1)) if full else list(range(len(group)))
-                        coarse_all = torch.cat([group[i][0]["bufs"][0] for i in order], dim=0)
                         save_first = group[-1][0]["bufs"][0].shape[0] if full else 0
                         offs = [0] * len(group)
                         off = 0
                         for i in order:
                             offs[i] = off
                             off += group[i][0]["bufs"][0].shape[0]
+                        # the group's coarse fields side by side in a fixed buffer (no allocation in the steady state)
+                        c0 = group[0][0]["bufs"][0]
+                        la = getattr(self, "_la_buf", None)
+                        if la is None or la.shape[0] < off or la.shape[1:] != c0.shape[1:] or la.device != c0.device:
+                            la = torch.empty((max(off, (n_critic + 1) * c0.shape[0]),) + tuple(c0.shape[1:]), device=dev,
+                                             dtype=torch.float32)
+                            self._la_buf = la
+                        for i in order:
+                            t = group[i][0]["bufs"][0]
+                            la[offs[i]:offs[i] + t.shape[0]].copy_(t)
+                        coarse_all = la[:off]
                         self._generator_lookahead(coarse_all, save_first,
                                                   first=(offs[0], group[0][0]["bufs"][0].shape[0]))
                         offsets.extend(offs)

@@ -72,6 +72,10 @@ _SIGNATURES = {
     "dg_generator_lookahead_first": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "dg_generator_step_saved": (C.c_int, [_P, _P, C.POINTER(Hyper), _P, C.c_int, _P, _P, _P]),
     "dg_critic_step_fake": (C.c_int, [_P, _P, C.POINTER(Hyper), C.c_int, _P, _P, C.c_int, _P, _P, _P]),
+    "dg_generator_activation": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
+    "dg_critic_activation": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "dg_generator_trunk_fwd": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "dg_generator_trunk_bwd": (C.c_int, [_P, _P, _P, _P, _P]),
     "dg_conv3x3_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_float, C.c_int, _P]),
     "dg_conv3x3_dgrad": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

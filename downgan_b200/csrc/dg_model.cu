@@ -394,12 +394,9 @@ extern "C" int dg_generator_pack(dg_generator* g, const float* params, void* str
   return 0;
 }
 
-// Generator.forward, networks/generator.py:83-90 (dense block :36-41, RRDB :52-53).
-// Input already in g->x0 (NHWC); output in g->fake (NHWC fp32).
-// `save_count` leading samples keep their activations for a later backward (0: inference / critic iterations).
-// Generator.forward (generator.py:83-90) over samples [s0, s0 + B) of g->x0; the first save_count samples keep their
-// dense-block activations (only meaningful for s0 == 0).
-static int gen_forward_range(dg_generator* g, int s0, int B, int save_count, cudaStream_t st) {
+// The RRDB trunk (generator.py:36-53; `self.res_blocks(out1)` at :85) over samples [s0, s0 + B): reads slice 0 of g->db[0],
+// writes g->trunk_out.  Fused persistent tcgen05 kernel where the shape allows, per-layer convs otherwise.
+static int gen_trunk_forward(dg_generator* g, int s0, int B, int save_count, cudaStream_t st) {
   const bool save = save_count > 0;
   const int F = g->F, Hc = g->Hc;
   const size_t pc = (size_t)Hc * Hc;
@@ -413,12 +410,6 @@ static int gen_forward_range(dg_generator* g, int s0, int B, int save_count, cud
     if (g->bf) op.w_umma = g->pk_u + l.pk_off;
     return op;
   };
-  void* first = g->R > 0 ? g->db[0] : g->trunk_out;
-  const int first_pitch = g->R > 0 ? 5 * F : F;
-  {
-    ConvOp op = conv(g->idx_conv1(), V(g->x0, g->Cin, 0, pc), Hc, V(first, first_pitch, 0, pc));
-    DG_TRY(run_conv(op, st));
-  }
   const bool fused_trunk = trunk_fused_supported(F, Hc, g->R, g->bf);
   if (fused_trunk) {
     // persistent tcgen05 kernel: the whole RRDB trunk with the concat buffer resident in shared memory
@@ -447,6 +438,34 @@ static int gen_forward_range(dg_generator* g, int s0, int B, int save_count, cud
       }
       DG_TRY(run_conv(op, st));
     }
+  return 0;
+}
+
+// Generator.forward, networks/generator.py:83-90 (dense block :36-41, RRDB :52-53).
+// Input already in g->x0 (NHWC); output in g->fake (NHWC fp32).
+// `save_count` leading samples keep their activations for a later backward (0: inference / critic iterations).
+// Generator.forward (generator.py:83-90) over samples [s0, s0 + B) of g->x0; the first save_count samples keep their
+// dense-block activations (only meaningful for s0 == 0).
+static int gen_forward_range(dg_generator* g, int s0, int B, int save_count, cudaStream_t st) {
+  const int F = g->F, Hc = g->Hc;
+  const size_t pc = (size_t)Hc * Hc;
+  auto V = [&](void* p, int pitch, int coff, size_t pixels) { return tv_batch(g->act(p, pitch, coff), pixels, s0); };
+  auto conv = [&](int li, TV x, int H, TV y) {
+    const Layer& l = g->layers[li];
+    ConvOp op;
+    op.x = x; op.Hin = H; op.Win = H; op.Ci = l.Ci;
+    op.y = y; op.Hout = H; op.Wout = H; op.Co = l.Co;
+    op.B = B; op.w = g->pk + l.pk_off; op.bias = g->pk + l.pkb_off;
+    if (g->bf) op.w_umma = g->pk_u + l.pk_off;
+    return op;
+  };
+  void* first = g->R > 0 ? g->db[0] : g->trunk_out;
+  const int first_pitch = g->R > 0 ? 5 * F : F;
+  {
+    ConvOp op = conv(g->idx_conv1(), V(g->x0, g->Cin, 0, pc), Hc, V(first, first_pitch, 0, pc));
+    DG_TRY(run_conv(op, st));
+  }
+  DG_TRY(gen_trunk_forward(g, s0, B, save_count, st));
   {  // out1 + conv2(trunk)
     ConvOp op = conv(g->idx_conv2(), V(g->trunk_out, F, 0, pc), Hc, V(g->t1, F, 0, pc));
     if (g->R > 0) { op.r1 = V(g->db[0], 5 * F, 0, pc); op.s1 = 1.f; }
@@ -508,15 +527,11 @@ extern "C" int dg_generator_fwd(dg_generator* g, const float* coarse, int batch,
   return 0;
 }
 
-// Backward of Generator.forward given g->dfake (NHWC fp32); fills g->gpk and unpacks into grads_flat.
-static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_coarse, cudaStream_t st) {
-  const int B = g->saved_batch, F = g->F, Hc = g->Hc, Hf = g->Hf;
-  if (B <= 0) { set_error("generator backward without a saved forward"); return DG_ERR_STATE; }
-  DG_CUDA(cudaMemsetAsync(g->gpk, 0, sizeof(float) * g->pk_elems, st));
-  // Weight gradients only feed the final unpack: with the side stream on they are enqueued there (after everything
-  // enqueued on `st` so far, i.e. after the data-gradient that produced their dy) and joined before the unpack, so the
-  // tail layers' weight gradients overlap the data-gradient chain and the 64-CTA trunk kernel.
-  bool side_on = g_tune[9] && g->side.s != nullptr;
+// Backward of the RRDB trunk: g->gR holds dL/d(trunk output) on entry and dL/d(trunk input) (through the trunk only) on exit;
+// the dense convs' weight / bias gradients are accumulated into g->gpk.  `side_on` is cleared when the per-layer path had to
+// join the side stream (it reuses its dz buffers block after block).
+static int gen_trunk_backward(dg_generator* g, int B, bool& side_on, cudaStream_t st) {
+  const int F = g->F, Hc = g->Hc;
   auto wgrad = [&](int li, TV x, int H, TV dy) {
     const Layer& l = g->layers[li];
     WgradOp w;
@@ -526,51 +541,6 @@ static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_co
     DG_TRY(g->side.fork(st));
     return run_wgrad(w, g->side.s);
   };
-  auto dconv = [&](int li, TV dy, int H, TV dx) {  // data-gradient op of plain layer li: Ci_op = Co, Co_op = Ci
-    const Layer& l = g->layers[li];
-    ConvOp op;
-    op.x = dy; op.Hin = H; op.Win = H; op.Ci = l.Co;
-    op.y = dx; op.Hout = H; op.Wout = H; op.Co = l.Ci;
-    op.B = B; op.w = g->pkd + l.pkd_off;
-    if (g->bf) op.w_umma = g->pkd_u + l.pkd_off;
-    return op;
-  };
-  void* last_up = g->U > 0 ? g->up[g->U - 1] : g->t1;
-  // conv3.2
-  DG_TRY(wgrad(g->idx_c32(), g->act(g->c30, F), Hf, tv(g->dfake, 0, g->Cout)));
-  {
-    ConvOp op = dconv(g->idx_c32(), tv(g->dfake, 0, g->Cout), Hf, g->act(g->gA, F));
-    op.act = ACT_MASK; op.slope = G_SLOPE; op.mask = g->act(g->c30, F);
-    DG_TRY(run_conv(op, st));
-  }
-  // conv3.0
-  DG_TRY(wgrad(g->idx_c30(), g->act(last_up, F), Hf, g->act(g->gA, F)));
-  void* gcur = nullptr;  // gradient w.r.t. the input of the layer just processed
-  {
-    ConvOp op = dconv(g->idx_c30(), g->act(g->gA, F), Hf, g->U > 0 ? g->act(g->gU[g->U - 1], 4 * F) : g->act(g->gT1, F));
-    if (g->U > 0) {  // store un-shuffled and masked by the pre-shuffle LeakyReLU (sign taken from the shuffled copy)
-      op.shuffle = SHUF_UNPIXEL; op.act = ACT_MASK; op.slope = G_SLOPE; op.mask = g->act(last_up, F);
-    }
-    DG_TRY(run_conv(op, st));
-    gcur = g->U > 0 ? g->gU[g->U - 1] : g->gT1;
-  }
-  // upsample stages, last to first; gcur = gU[u] holds dz of stage u as (B, H, H, 4F)
-  for (int u = g->U - 1; u >= 0; --u) {
-    const int H = Hc << u;
-    void* xin = u > 0 ? g->up[u - 1] : g->t1;
-    DG_TRY(wgrad(g->idx_up(u), g->act(xin, F), H, g->act(gcur, 4 * F)));
-    void* dst = u > 0 ? g->gU[u - 1] : g->gT1;
-    ConvOp op = dconv(g->idx_up(u), g->act(gcur, 4 * F), H, u > 0 ? g->act(dst, 4 * F) : g->act(dst, F));
-    if (u > 0) { op.shuffle = SHUF_UNPIXEL; op.act = ACT_MASK; op.slope = G_SLOPE; op.mask = g->act(xin, F); }
-    DG_TRY(run_conv(op, st));
-    gcur = dst;
-  }
-  // gT1 = dL/d(out1 + conv2(trunk))
-  DG_TRY(wgrad(g->idx_conv2(), g->act(g->trunk_out, F), Hc, g->act(g->gT1, F)));
-  {
-    ConvOp op = dconv(g->idx_conv2(), g->act(g->gT1, F), Hc, g->act(g->gR, F));
-    DG_TRY(run_conv(op, st));
-  }
   const size_t pix = (size_t)B * Hc * Hc;
   // trunk, RRDB by RRDB
   void* gxs[2] = {g->gx0, g->gx1};
@@ -671,6 +641,74 @@ static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_co
       DG_TRY(wgrad_umma_batched(wops.data(), (int)wops.size(), g->wg_table_dev, g->wg_shadow, 2, st));
     }
   }
+  return 0;
+}
+
+// Backward of Generator.forward given g->dfake (NHWC fp32); fills g->gpk and unpacks into grads_flat.
+static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_coarse, cudaStream_t st) {
+  const int B = g->saved_batch, F = g->F, Hc = g->Hc, Hf = g->Hf;
+  if (B <= 0) { set_error("generator backward without a saved forward"); return DG_ERR_STATE; }
+  DG_CUDA(cudaMemsetAsync(g->gpk, 0, sizeof(float) * g->pk_elems, st));
+  // Weight gradients only feed the final unpack: with the side stream on they are enqueued there (after everything
+  // enqueued on `st` so far, i.e. after the data-gradient that produced their dy) and joined before the unpack, so the
+  // tail layers' weight gradients overlap the data-gradient chain and the 64-CTA trunk kernel.
+  bool side_on = g_tune[9] && g->side.s != nullptr;
+  auto wgrad = [&](int li, TV x, int H, TV dy) {
+    const Layer& l = g->layers[li];
+    WgradOp w;
+    w.x = x; w.Hin = H; w.Win = H; w.Ci = l.Ci; w.dy = dy; w.Hout = H; w.Wout = H; w.Co = l.Co; w.B = B; w.stride = 1;
+    w.dw = g->gpk + l.pk_off; w.dbias = g->gpk + l.pkb_off;
+    if (!side_on) return run_wgrad(w, st);
+    DG_TRY(g->side.fork(st));
+    return run_wgrad(w, g->side.s);
+  };
+  auto dconv = [&](int li, TV dy, int H, TV dx) {  // data-gradient op of plain layer li: Ci_op = Co, Co_op = Ci
+    const Layer& l = g->layers[li];
+    ConvOp op;
+    op.x = dy; op.Hin = H; op.Win = H; op.Ci = l.Co;
+    op.y = dx; op.Hout = H; op.Wout = H; op.Co = l.Ci;
+    op.B = B; op.w = g->pkd + l.pkd_off;
+    if (g->bf) op.w_umma = g->pkd_u + l.pkd_off;
+    return op;
+  };
+  void* last_up = g->U > 0 ? g->up[g->U - 1] : g->t1;
+  // conv3.2
+  DG_TRY(wgrad(g->idx_c32(), g->act(g->c30, F), Hf, tv(g->dfake, 0, g->Cout)));
+  {
+    ConvOp op = dconv(g->idx_c32(), tv(g->dfake, 0, g->Cout), Hf, g->act(g->gA, F));
+    op.act = ACT_MASK; op.slope = G_SLOPE; op.mask = g->act(g->c30, F);
+    DG_TRY(run_conv(op, st));
+  }
+  // conv3.0
+  DG_TRY(wgrad(g->idx_c30(), g->act(last_up, F), Hf, g->act(g->gA, F)));
+  void* gcur = nullptr;  // gradient w.r.t. the input of the layer just processed
+  {
+    ConvOp op = dconv(g->idx_c30(), g->act(g->gA, F), Hf, g->U > 0 ? g->act(g->gU[g->U - 1], 4 * F) : g->act(g->gT1, F));
+    if (g->U > 0) {  // store un-shuffled and masked by the pre-shuffle LeakyReLU (sign taken from the shuffled copy)
+      op.shuffle = SHUF_UNPIXEL; op.act = ACT_MASK; op.slope = G_SLOPE; op.mask = g->act(last_up, F);
+    }
+    DG_TRY(run_conv(op, st));
+    gcur = g->U > 0 ? g->gU[g->U - 1] : g->gT1;
+  }
+  // upsample stages, last to first; gcur = gU[u] holds dz of stage u as (B, H, H, 4F)
+  for (int u = g->U - 1; u >= 0; --u) {
+    const int H = Hc << u;
+    void* xin = u > 0 ? g->up[u - 1] : g->t1;
+    DG_TRY(wgrad(g->idx_up(u), g->act(xin, F), H, g->act(gcur, 4 * F)));
+    void* dst = u > 0 ? g->gU[u - 1] : g->gT1;
+    ConvOp op = dconv(g->idx_up(u), g->act(gcur, 4 * F), H, u > 0 ? g->act(dst, 4 * F) : g->act(dst, F));
+    if (u > 0) { op.shuffle = SHUF_UNPIXEL; op.act = ACT_MASK; op.slope = G_SLOPE; op.mask = g->act(xin, F); }
+    DG_TRY(run_conv(op, st));
+    gcur = dst;
+  }
+  // gT1 = dL/d(out1 + conv2(trunk))
+  DG_TRY(wgrad(g->idx_conv2(), g->act(g->trunk_out, F), Hc, g->act(g->gT1, F)));
+  {
+    ConvOp op = dconv(g->idx_conv2(), g->act(g->gT1, F), Hc, g->act(g->gR, F));
+    DG_TRY(run_conv(op, st));
+  }
+  const size_t pix = (size_t)B * Hc * Hc;
+  DG_TRY(gen_trunk_backward(g, B, side_on, st));
   // dL/d(out1) = gR (through the trunk / conv2) + gT1 (long skip)
   DG_TRY(scale_add(g->act(g->gx0, F), g->act(g->gR, F), 1.f, g->act(g->gT1, F), 1.f, pix, F, st));
   DG_TRY(wgrad(g->idx_conv1(), g->act(g->x0, g->Cin), Hc, g->act(g->gx0, F)));
@@ -691,6 +729,57 @@ extern "C" int dg_generator_bwd(dg_generator* g, const float* d_fake, float* gra
   if (g->saved_batch <= 0) { set_error("dg_generator_bwd: no saved forward"); return DG_ERR_STATE; }
   DG_TRY(nchw_to_nhwc(d_fake, tv(g->dfake, 0, g->Cout), g->saved_batch, g->Cout, g->Hf, g->Hf, st));
   return gen_backward_internal(g, grads_flat, d_coarse, st);
+}
+
+// ---- parity instrumentation / unit-test entry points (include/downgan_b200.h) ---------------------------------------
+extern "C" int dg_generator_activation(dg_generator* g, int which, int batch, float* out, void* stream) {
+  DG_CHECK(g && out, "dg_generator_activation: null argument");
+  DG_CHECK(batch >= 1 && batch <= g->saved_batch, "dg_generator_activation: batch %d outside the saved forward (%d samples)", batch,
+           g->saved_batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(g->side.join(st));
+  const int F = g->F, Hc = g->Hc;
+  if (which >= 0 && which < g->R * 3) return nhwc_to_nchw(g->act(g->db[which], 5 * F), out, batch, 5 * F, Hc, Hc, st);
+  if (which == 1000) return nhwc_to_nchw(g->act(g->trunk_out, F), out, batch, F, Hc, Hc, st);
+  if (which == 1001) return nhwc_to_nchw(g->act(g->t1, F), out, batch, F, Hc, Hc, st);
+  if (which >= 1100 && which < 1100 + g->U) {
+    const int H = Hc << (which - 1100 + 1);
+    return nhwc_to_nchw(g->act(g->up[which - 1100], F), out, batch, F, H, H, st);
+  }
+  if (which == 1200) return nhwc_to_nchw(g->act(g->c30, F), out, batch, F, g->Hf, g->Hf, st);
+  set_error("dg_generator_activation: unknown activation %d", which);
+  return DG_ERR_INVALID;
+}
+
+extern "C" int dg_generator_trunk_fwd(dg_generator* g, const float* x, int batch, float* y, void* stream) {
+  DG_CHECK(g && x && y, "dg_generator_trunk_fwd: null argument");
+  DG_CHECK(batch >= 1 && batch <= g->maxB, "dg_generator_trunk_fwd: batch %d outside [1,%d]", batch, g->maxB);
+  DG_CHECK(g->R > 0, "dg_generator_trunk_fwd: the generator has no residual blocks");
+  if (!g->packed) { set_error("dg_generator_trunk_fwd: dg_generator_pack has not been called"); return DG_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(g->side.join(st));
+  DG_TRY(nchw_to_nhwc(x, g->act(g->db[0], 5 * g->F, 0), batch, g->F, g->Hc, g->Hc, st));
+  g->lookahead = 0;
+  DG_TRY(gen_trunk_forward(g, 0, batch, batch, st));
+  g->saved_batch = batch;
+  return nhwc_to_nchw(g->act(g->trunk_out, g->F), y, batch, g->F, g->Hc, g->Hc, st);
+}
+
+extern "C" int dg_generator_trunk_bwd(dg_generator* g, const float* d_y, float* d_x, float* grads_flat, void* stream) {
+  DG_CHECK(g && d_y && grads_flat, "dg_generator_trunk_bwd: null argument");
+  DG_CHECK(g->R > 0, "dg_generator_trunk_bwd: the generator has no residual blocks");
+  if (g->saved_batch <= 0) { set_error("dg_generator_trunk_bwd: no saved forward"); return DG_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(g->side.join(st));
+  const int B = g->saved_batch;
+  DG_TRY(nchw_to_nhwc(d_y, g->act(g->gR, g->F), B, g->F, g->Hc, g->Hc, st));
+  DG_CUDA(cudaMemsetAsync(g->gpk, 0, sizeof(float) * g->pk_elems, st));
+  bool side_on = g_tune[9] && g->side.s != nullptr;
+  DG_TRY(gen_trunk_backward(g, B, side_on, st));
+  DG_TRY(g->side.join(st));
+  DG_TRY(unpack_wgrads(g->gpk, grads_flat, g->tab_fwd, g->n_fwd, g->max_fwd, st));
+  if (d_x) DG_TRY(nhwc_to_nchw(g->act(g->gR, g->F), d_x, B, g->F, g->Hc, g->Hc, st));
+  return 0;
 }
 
 // ===========================================================================
@@ -721,6 +810,8 @@ struct dg_critic {
   void* dz[9] = {nullptr};   // dz[1..8]
   float *g = nullptr, *u = nullptr;        // (maxB,Hf,Hf,nc) fp32
   void *v0 = nullptr, *v1 = nullptr;       // JVP ping-pong
+  void* keep[9] = {nullptr};               // parity instrumentation (dg_set_tuning(15, 1)): the interpolates' activations a[1..8]
+  int keep_batch = 0;
   float *sumsq = nullptr, *coef = nullptr, *norms = nullptr, *scal = nullptr;
   SideStream side;
   int defer_conv = 0;           // dg_critic_defer_conv_grads: the fused iteration returns before its conv weight gradients are final
@@ -1048,6 +1139,15 @@ static int critic_second_order_and_wgrads(dg_critic* c, int B, cudaStream_t st, 
     return critic_layer_wgrad(c, i, 0, 3 * B, n0, side_on, st);
   };
   TV v = tv_batch(tv(c->a0, 0, c->nc), (size_t)c->Hf * c->Hf, n0);  // u was written here by gp_scale
+  c->keep_batch = 0;
+  if (g_tune[15]) {  // parity instrumentation: the JVP chain below overwrites the interpolates' activations in place
+    for (int i = 0; i < 8; ++i) {
+      const size_t e = c->pix(i) * c->L[i].Co * c->esz;
+      if (!c->keep[i + 1]) DG_TRY(dev_alloc(c->pool, &c->keep[i + 1], (size_t)c->maxB * e));
+      DG_CUDA(cudaMemcpyAsync(c->keep[i + 1], (const char*)c->a[i + 1] + (size_t)n0 * e, (size_t)B * e, cudaMemcpyDeviceToDevice, st));
+    }
+    c->keep_batch = B;
+  }
   for (int i = 0; i < 8; ++i) {
     if (side_on) DG_TRY(layer_wgrad(i));
     const Layer& l = c->L[i];
@@ -1091,6 +1191,31 @@ extern "C" int dg_critic_fwd(dg_critic* c, const float* x, int batch, float* sco
   DG_CUDA(cudaMemcpyAsync(scores, c->scores, sizeof(float) * batch, cudaMemcpyDeviceToDevice, st));
   c->saved_batch = batch;
   return 0;
+}
+
+extern "C" int dg_critic_activation(dg_critic* c, int which, int s0, int batch, float* out, void* stream) {
+  DG_CHECK(c && out, "dg_critic_activation: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(c->side.join(st));
+  if (which >= 101 && which <= 108) {
+    const int i = which - 101;
+    DG_CHECK(s0 >= 0 && batch >= 1 && s0 + batch <= c->keep_batch,
+             "dg_critic_activation: samples [%d,%d) outside the %d interpolates kept (dg_set_tuning(15, 1) before the iteration)", s0,
+             s0 + batch, c->keep_batch);
+    return nhwc_to_nchw(tv_batch(c->act(c->keep[i + 1], c->L[i].Co), c->pix(i), s0), out, batch, c->L[i].Co, c->Hout[i], c->Hout[i], st);
+  }
+  DG_CHECK(s0 >= 0 && batch >= 1 && s0 + batch <= c->NBmax, "dg_critic_activation: samples [%d,%d) outside [0,%d)", s0, s0 + batch,
+           c->NBmax);
+  if (which >= 1 && which <= 8) {
+    const int i = which - 1;
+    return nhwc_to_nchw(tv_batch(c->act(c->a[i + 1], c->L[i].Co), c->pix(i), s0), out, batch, c->L[i].Co, c->Hout[i], c->Hout[i], st);
+  }
+  if (which == 9) {
+    DG_CUDA(cudaMemcpyAsync(out, c->a9 + (size_t)s0 * FC_HIDDEN, sizeof(float) * batch * FC_HIDDEN, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  set_error("dg_critic_activation: unknown activation %d", which);
+  return DG_ERR_INVALID;
 }
 
 extern "C" int dg_critic_bwd(dg_critic* c, const float* d_scores, float* grads_flat, float* d_x, void* stream) {

@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include <cuda.h>
@@ -590,11 +591,13 @@ struct MapKey {
   }
 };
 static std::vector<std::pair<MapKey, CUtensorMap>> g_maps;
+static std::mutex g_maps_mu;  // two handles may be driven from two host threads (one handle per thread)
 
 static int get_map(const ConvOp& op, const WsArgs& a, CUtensorMap* out) {
   const int es = (a.mode == S2_FWD) ? 2 : 1;
   const int trows = a.TH + ((a.mode == S1) ? 2 : 1);
   MapKey k{(const bf16*)op.x.p + op.x.coff, op.Ci, op.Win, op.Hin, op.B, op.x.pitch, a.PW * es, trows * es, es};
+  std::lock_guard<std::mutex> lock(g_maps_mu);
   for (auto& e : g_maps)
     if (e.first == k) { *out = e.second; return 0; }
   cuuint64_t dims[4] = {(cuuint64_t)op.Ci, (cuuint64_t)op.Win, (cuuint64_t)op.Hin, (cuuint64_t)op.B};

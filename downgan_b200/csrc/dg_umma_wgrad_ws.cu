@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "dg_umma.cuh"
@@ -355,10 +356,12 @@ struct MapKeyW {
   }
 };
 std::vector<std::pair<MapKeyW, CUtensorMap>> g_maps_w;
+std::mutex g_maps_w_mu;
 
 // NHWC view {C, W, H, B} (bf16); box = bc channels x bw x bh (traversal extents) with element stride es on W and H
 int get_map_w(const TV& t, int C, int W, int H, int B, int bc, int bw, int bh, int es, CUtensorMap* out) {
   MapKeyW k{(const bf16*)t.p + t.coff, C, W, H, B, t.pitch, bc, bw, bh, es};
+  std::lock_guard<std::mutex> lock(g_maps_w_mu);
   for (auto& e : g_maps_w)
     if (e.first == k) { *out = e.second; return 0; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};

@@ -11,7 +11,9 @@
  * Conventions
  *   - every function returns 0 on success, a negative dg_status otherwise;
  *     dg_last_error() returns a thread-local message for the last failure.
- *   - no exceptions cross the ABI, no hidden device synchronisation, every
+ *   - no exceptions cross the ABI, no hidden device synchronisation (the
+ *     unit-test primitives dg_conv3x3_* are the exception: they allocate
+ *     scratch and synchronise the stream before returning), every
  *     call enqueues on the cudaStream_t passed as `void* stream`.  A handle
  *     also owns one non-blocking side stream: the fused iterations fork
  *     work onto it (weight gradients, the second chain of a look-ahead
@@ -198,6 +200,32 @@ int dg_conv3x3_dgrad(const float* dy, const float* w, float* dx,
 int dg_conv3x3_wgrad(const float* x, const float* dy, float* dw, float* dbias,
                      int batch, int ci, int co, int hin, int win, int stride, int precision, void* stream);
 
+/* ---- parity instrumentation (tests/ and tools/parity_report.py; no reference counterpart) ----------------
+ * Copies an activation the handle still holds out as NCHW fp32 (`out` is a device pointer), so that a test can
+ * take the LeakyReLU sign masks the CUDA path actually used (sign of the stored post-activation) and replay
+ * them in the CPU oracle: with the masks pinned, every parameter gradient must meet north_star's tolerance;
+ * without, bf16 rounding flips masks of near-zero pre-activations (profiles/parity_r02.md).
+ * dg_generator_activation, after a forward that saved (dg_generator_fwd save=1 / dg_generator_step):
+ *   which 0 .. 3R-1   dense-block concat buffer (batch, 5F, Hc, Hc): slices [x, o1, o2, o3, o4]
+ *   which 1000        trunk output (batch, F, Hc, Hc)        1001  out1 + conv2(trunk) (batch, F, Hc, Hc)
+ *   which 1100 + u    upsample stage u AFTER PixelShuffle (batch, F, Hc << (u+1), Hc << (u+1))
+ *   which 1200        conv3.0 output (batch, F, Hf, Hf)
+ * dg_critic_activation, samples [s0, s0 + batch) of the critic's last batch:
+ *   which 1 .. 8      output of features.{2(which-1)} after LeakyReLU (batch, Co, H, H)
+ *   which 9           classifier.0 output after LeakyReLU (batch, 100)
+ *   which 101 .. 108  the interpolates' activations of the last fused critic iteration, samples [s0, s0+batch)
+ *                     of its B interpolates (the iteration overwrites them in place with the JVP chain; they are
+ *                     kept aside only while dg_set_tuning(15, 1) is on). */
+int dg_generator_activation(dg_generator* g, int which, int batch, float* out, void* stream);
+int dg_critic_activation(dg_critic* c, int which, int s0, int batch, float* out, void* stream);
+
+/* The RRDB trunk alone (networks/generator.py:36-53, the res_blocks Sequential at :85): x (batch, F, Hc, Hc) NCHW
+ * fp32 -> y same shape, on the handle's packed weights; activations are saved.  dg_generator_trunk_bwd is its
+ * autograd: d_y -> d_x (may be NULL) and grads_flat (whole generator layout, overwritten; only the res_blocks
+ * tensors are non-zero).  Unit-test entry points for the fused persistent trunk kernels. */
+int dg_generator_trunk_fwd(dg_generator* g, const float* x, int batch, float* y, void* stream);
+int dg_generator_trunk_bwd(dg_generator* g, const float* d_y, float* d_x, float* grads_flat, void* stream);
+
 /* Number of kernel launches this library has enqueued since load (for bench.py's gpu_launches). */
 int64_t dg_launch_count(void);
 
@@ -232,8 +260,10 @@ int dg_profile_report(double* out, int n_classes);
  * the side stream during the input-gradient chain, their interpolates' rows during the JVP chain (0: one 3B launch per layer).
  * key 14: classifier.0 products (forward, input gradient, weight gradient) on the tcgen05 kernels of csrc/dg_umma_fc.cu (1)
  * or on the CUDA-core kernels (0, default: the tcgen05 variants have not been validated on hardware yet).
+ * key 15: parity instrumentation - the fused critic iteration keeps a copy of the interpolates' activations for
+ * dg_critic_activation(101..108) (0, default: off, no copy).
  * Returns the previous value, or DG_ERR_INVALID for an unknown key. */
-#define DG_TUNE_KEYS 15
+#define DG_TUNE_KEYS 16
 int dg_set_tuning(int key, int value);
 
 #ifdef __cplusplus

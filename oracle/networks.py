@@ -141,53 +141,108 @@ def init_critic_state(spec: CriticSpec, seed: int | None = None,
 
 
 # --------------------------------------------------------------------------
+# LeakyReLU mask tape (parity diagnostics, tests/test_gpu_masks.py)
+# --------------------------------------------------------------------------
+class MaskTape:
+    """Records, or replays, the LeakyReLU sign masks of a forward pass in call order.
+
+    ``MaskTape()`` records the pre-activations ``z`` of every LeakyReLU the pass executes
+    (``tape.z``; the mask is ``z > 0``).  ``MaskTape(masks)`` replays: the k-th LeakyReLU becomes
+    ``z * where(masks[k], 1, slope)`` — the same piecewise-linear function with the branch chosen
+    by the caller instead of by sign(z).  With the masks of the CUDA path replayed, the oracle
+    differentiates exactly the linear map the CUDA path differentiated, so the remaining
+    disagreement is arithmetic rounding only; without, bf16 storage flips the branch wherever
+    |z| is below its own rounding error (the reference's nn.LeakyReLU: generator.py:26,72,79,
+    critic.py:24..97 — the derivative at the flipped positions jumps between 1 and the slope).
+    ``bf16=True`` additionally rounds every conv / linear input and weight to bf16 (straight-through
+    gradient): the emulated storage precision of the CUDA path's bf16 mode."""
+
+    def __init__(self, masks=None, bf16: bool = False):
+        self.replay = masks is not None
+        self.masks = list(masks) if masks is not None else []
+        self.z: List[torch.Tensor] = []
+        self.i = 0
+        self.bf16 = bf16
+
+    def q(self, t: torch.Tensor) -> torch.Tensor:
+        if not self.bf16:
+            return t
+        return t + (t.detach().to(torch.bfloat16).to(t.dtype) - t.detach())
+
+
+def _lrelu(z: torch.Tensor, slope: float, tape: "MaskTape | None") -> torch.Tensor:
+    if tape is None:
+        return F.leaky_relu(z, slope)
+    if tape.replay:
+        m = tape.masks[tape.i]
+        tape.i += 1
+        if m.shape != z.shape:
+            raise ValueError(f"mask {tape.i - 1}: shape {tuple(m.shape)} != activation {tuple(z.shape)}")
+        return z * torch.where(m, torch.ones((), dtype=z.dtype), torch.full((), slope, dtype=z.dtype))
+    tape.z.append(z.detach())
+    return F.leaky_relu(z, slope)
+
+
+# --------------------------------------------------------------------------
 # forward passes
 # --------------------------------------------------------------------------
-def _conv(sd: Mapping[str, torch.Tensor], name: str, x: torch.Tensor, stride: int = 1) -> torch.Tensor:
-    return F.conv2d(x, sd[f"{name}.weight"], sd.get(f"{name}.bias"), stride=stride, padding=1)
+def _conv(sd: Mapping[str, torch.Tensor], name: str, x: torch.Tensor, stride: int = 1, tape=None) -> torch.Tensor:
+    w = sd[f"{name}.weight"]
+    if tape is not None and tape.bf16:
+        x, w = tape.q(x), tape.q(w)
+    return F.conv2d(x, w, sd.get(f"{name}.bias"), stride=stride, padding=1)
 
 
-def dense_block_forward(sd, prefix: str, x: torch.Tensor) -> torch.Tensor:
+def dense_block_forward(sd, prefix: str, x: torch.Tensor, tape=None) -> torch.Tensor:
     """generator.py:36-41 — concat order [x, o1, o2, o3, o4]; b5 has no activation."""
     feats = x
     o = x
     for k in range(1, 6):
-        o = _conv(sd, f"{prefix}.b{k}.0", feats)
+        o = _conv(sd, f"{prefix}.b{k}.0", feats, tape=tape)
         if k < 5:
-            o = F.leaky_relu(o, G_SLOPE)
+            o = _lrelu(o, G_SLOPE, tape)
             feats = torch.cat((feats, o), dim=1)
     return o * RES_SCALE + x
 
 
-def rrdb_forward(sd, prefix: str, x: torch.Tensor) -> torch.Tensor:
+def rrdb_forward(sd, prefix: str, x: torch.Tensor, tape=None) -> torch.Tensor:
     """generator.py:52-53."""
     y = x
     for d in range(3):
-        y = dense_block_forward(sd, f"{prefix}.dense_blocks.{d}", y)
+        y = dense_block_forward(sd, f"{prefix}.dense_blocks.{d}", y, tape)
     return y * RES_SCALE + x
 
 
-def generator_forward(sd: Mapping[str, torch.Tensor], spec: GeneratorSpec, x: torch.Tensor) -> torch.Tensor:
-    """generator.py:83-90.  x: (B, channels, H, W) -> (B, n_predictands, H*2^u, W*2^u)."""
-    first = _conv(sd, "conv1", x)
-    y = first
+def trunk_forward(sd, spec: GeneratorSpec, x: torch.Tensor, tape=None) -> torch.Tensor:
+    """``self.res_blocks(out1)`` of generator.py:85: the RRDB Sequential alone."""
+    y = x
     for r in range(spec.num_res_blocks):
-        y = rrdb_forward(sd, f"res_blocks.{r}", y)
-    y = first + _conv(sd, "conv2", y)
+        y = rrdb_forward(sd, f"res_blocks.{r}", y, tape)
+    return y
+
+
+def generator_forward(sd: Mapping[str, torch.Tensor], spec: GeneratorSpec, x: torch.Tensor, tape=None) -> torch.Tensor:
+    """generator.py:83-90.  x: (B, channels, H, W) -> (B, n_predictands, H*2^u, W*2^u)."""
+    first = _conv(sd, "conv1", x, tape=tape)
+    y = trunk_forward(sd, spec, first, tape)
+    y = first + _conv(sd, "conv2", y, tape=tape)
     for u in range(spec.num_upsample):
         # conv -> LeakyReLU -> PixelShuffle(2)  (generator.py:70-74)
-        y = F.pixel_shuffle(F.leaky_relu(_conv(sd, f"upsampling.{3 * u}", y), G_SLOPE), 2)
-    y = F.leaky_relu(_conv(sd, "conv3.0", y), G_SLOPE)
-    return _conv(sd, "conv3.2", y)
+        y = F.pixel_shuffle(_lrelu(_conv(sd, f"upsampling.{3 * u}", y, tape=tape), G_SLOPE, tape), 2)
+    y = _lrelu(_conv(sd, "conv3.0", y, tape=tape), G_SLOPE, tape)
+    return _conv(sd, "conv3.2", y, tape=tape)
 
 
-def critic_forward(sd: Mapping[str, torch.Tensor], spec: CriticSpec, x: torch.Tensor) -> torch.Tensor:
+def critic_forward(sd: Mapping[str, torch.Tensor], spec: CriticSpec, x: torch.Tensor, tape=None) -> torch.Tensor:
     """critic.py:101-106.  x: (B, nc, fine, fine) -> (B, 1)."""
     y = x
     for i, (_ci, _co, s) in enumerate(spec.widths):
-        y = F.leaky_relu(_conv(sd, f"features.{2 * i}", y, stride=s), C_SLOPE)
+        y = _lrelu(_conv(sd, f"features.{2 * i}", y, stride=s, tape=tape), C_SLOPE, tape)
     y = torch.flatten(y, 1)  # NCHW order: c*H*W + h*W + w
-    y = F.leaky_relu(F.linear(y, sd["classifier.0.weight"], sd["classifier.0.bias"]), C_SLOPE)
+    w1 = sd["classifier.0.weight"]
+    if tape is not None and tape.bf16:
+        y = tape.q(y)  # the CUDA path stores the features in bf16; the classifier itself runs in fp32
+    y = _lrelu(F.linear(y, w1, sd["classifier.0.bias"]), C_SLOPE, tape)
     return F.linear(y, sd["classifier.2.weight"], sd["classifier.2.bias"])
 
 

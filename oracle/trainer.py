@@ -50,14 +50,14 @@ class Hyper:
 # --------------------------------------------------------------------------
 # gradient penalty, as written (autograd double backward)
 # --------------------------------------------------------------------------
-def gradient_penalty(c_params, cspec: CriticSpec, real, fake, alpha, hp: Hyper):
+def gradient_penalty(c_params, cspec: CriticSpec, real, fake, alpha, hp: Hyper, tape=None):
     """wasserstein.py:87-117.  Returns ``gp_lambda * mean((||g||-1)^2)`` (the
     caller multiplies by gp_lambda a second time, wasserstein.py:40) together
     with the per-sample norms.  ``alpha``: (B,1,1,1)."""
     b = real.shape[0]
     a = alpha.to(real.dtype).expand_as(real)
     interp = (a * real.detach() + (1 - a) * fake.detach()).requires_grad_(True)
-    score = critic_forward(c_params, cspec, interp)
+    score = critic_forward(c_params, cspec, interp, tape)
     (g,) = torch.autograd.grad(score, interp, grad_outputs=torch.ones_like(score),
                                create_graph=True, retain_graph=True)
     norms = torch.sqrt(torch.sum(g.reshape(b, -1) ** 2, dim=1) + 1e-12)
@@ -65,17 +65,24 @@ def gradient_penalty(c_params, cspec: CriticSpec, real, fake, alpha, hp: Hyper):
 
 
 def critic_loss_and_grads(g_sd, gspec: GeneratorSpec, c_sd, cspec: CriticSpec,
-                          coarse, fine, alpha, hp: Hyper, dtype=None):
-    """One critic objective + parameter grads (wasserstein.py:35-52)."""
+                          coarse, fine, alpha, hp: Hyper, dtype=None, tapes=None, fake=None):
+    """One critic objective + parameter grads (wasserstein.py:35-52).
+    ``tapes``: optional {"gen", "real", "fake", "interp"} -> networks.MaskTape (parity diagnostics);
+    ``fake``: use this G(coarse) instead of running the generator (mask-pinned comparisons feed the
+    CUDA path's own fake so that the replayed masks belong to the critic input they were taken on)."""
+    tapes = tapes or {}
     gp_ = {k: (v.to(dtype) if dtype is not None else v) for k, v in g_sd.items()}
     cp = as_leaf_params(c_sd, dtype)
     if dtype is not None:
         coarse, fine, alpha = coarse.to(dtype), fine.to(dtype), alpha.to(dtype)
-    with torch.no_grad():  # the generator backward of wasserstein.py:52 is discarded (:65)
-        fake = generator_forward(gp_, gspec, coarse)
-    c_real = critic_forward(cp, cspec, fine)
-    c_fake = critic_forward(cp, cspec, fake)
-    gp, norms, g = gradient_penalty(cp, cspec, fine, fake, alpha, hp)
+    if fake is None:
+        with torch.no_grad():  # the generator backward of wasserstein.py:52 is discarded (:65)
+            fake = generator_forward(gp_, gspec, coarse, tapes.get("gen"))
+    elif dtype is not None:
+        fake = fake.to(dtype)
+    c_real = critic_forward(cp, cspec, fine, tapes.get("real"))
+    c_fake = critic_forward(cp, cspec, fake, tapes.get("fake"))
+    gp, norms, g = gradient_penalty(cp, cspec, fine, fake, alpha, hp, tapes.get("interp"))
     penalty = hp.gp_lambda * gp
     loss = c_fake.mean() - c_real.mean() + penalty
     grads = torch.autograd.grad(loss, list(cp.values()), allow_unused=True)
@@ -91,14 +98,16 @@ def critic_loss_and_grads(g_sd, gspec: GeneratorSpec, c_sd, cspec: CriticSpec,
 
 
 def generator_loss_and_grads(g_sd, gspec: GeneratorSpec, c_sd, cspec: CriticSpec,
-                             coarse, fine, hp: Hyper, dtype=None):
-    """One generator objective + parameter grads (wasserstein.py:65-80)."""
+                             coarse, fine, hp: Hyper, dtype=None, tapes=None):
+    """One generator objective + parameter grads (wasserstein.py:65-80).
+    ``tapes``: optional {"gen", "fake"} -> networks.MaskTape (parity diagnostics)."""
+    tapes = tapes or {}
     gp_ = as_leaf_params(g_sd, dtype)
     cp = {k: (v.to(dtype) if dtype is not None else v) for k, v in c_sd.items()}
     if dtype is not None:
         coarse, fine = coarse.to(dtype), fine.to(dtype)
-    fake = generator_forward(gp_, gspec, coarse)
-    c_fake = critic_forward(cp, cspec, fake)
+    fake = generator_forward(gp_, gspec, coarse, tapes.get("gen"))
+    c_fake = critic_forward(cp, cspec, fake, tapes.get("fake"))
     adv = -c_fake.mean() * hp.gamma
     l1 = (fake - fine).abs().mean()  # nn.L1Loss default 'mean' over all elements
     loss = adv + hp.content_lambda * l1

@@ -250,9 +250,10 @@ def test_adam_and_l1_kernels():
     assert torch.allclose(da.cpu(), 5.0 * torch.sign(a - b) / a.numel(), atol=1e-9)
 
 
-@pytest.mark.parametrize("precision", ["fp32"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_loss_curves_200_steps(precision):
-    """Loss curves of the drop-in trainer vs the oracle over 200 batches of the reference schedule."""
+    """Loss curves of the drop-in trainer vs the oracle over 200 batches of the reference schedule
+    (north_star: "loss curves must agree over 200 steps"), in the fp32 parity mode AND in the benchmarked bf16 mode."""
     G, C, g_sd, c_sd = pu.build_pair(TINY_G, TINY_C, precision, seed=4)
     gopt = torch.optim.Adam(G.parameters(), 2.5e-4, betas=(0.9, 0.99))
     copt = torch.optim.Adam(C.parameters(), 2.5e-4, betas=(0.9, 0.99))
@@ -260,9 +261,10 @@ def test_loss_curves_200_steps(precision):
     # Ground truth = fp64 oracle.  GAN dynamics amplify rounding differences once the critic has
     # learnt ||grad|| ~ 1 (the critic loss falls from ~100 to O(1) and changes sign), so the
     # reference's own fp32 run drifts from fp64 late in the curve; that measured drift is the
-    # yardstick:  (a) the first 20 steps must agree pointwise to 1e-3 relative,  (b) over all 200
-    # steps the deviation must stay within 3x the fp32-oracle-vs-fp64-oracle deviation plus 1e-3 of
-    # the curve's range.
+    # yardstick:  (a) the first 20 steps must agree pointwise to the mode's tolerance (1e-3 fp32, 2e-2 bf16),
+    # (b) over all 200 steps the deviation must stay within 3x the fp32-oracle-vs-fp64-oracle deviation plus
+    # that tolerance times the curve's range.
+    tol = TOL_OUT[precision]
     ref = otr.OracleTrainer(g_sd, TINY_G, c_sd, TINY_C, dtype=torch.float64)
     ref32 = otr.OracleTrainer(g_sd, TINY_G, c_sd, TINY_C)
     closs, gloss, rc, rg, rc32, rg32 = [], [], [], [], [], []
@@ -286,13 +288,14 @@ def test_loss_curves_200_steps(precision):
     rc, rg = torch.tensor(rc).double(), torch.tensor(rg).double()
     rc32, rg32 = torch.tensor(rc32).double(), torch.tensor(rg32).double()
     assert len(gloss) == 40
-    assert float(((closs - rc).abs() / rc.abs())[:20].max()) < 1e-3
-    assert float(((gloss - rg).abs() / rg.abs())[:4].max()) < 1e-3
-    for ours, r64, r32 in ((closs, rc, rc32), (gloss, rg, rg32)):
+    assert float(((closs - rc).abs() / rc.abs())[:20].max()) < tol
+    assert float(((gloss - rg).abs() / rg.abs())[:4].max()) < tol
+    for name, ours, r64, r32 in (("critic", closs, rc, rc32), ("generator", gloss, rg, rg32)):
         drift = float((r32 - r64).abs().max())
         span = float(r64.max() - r64.min())
         dev = float((ours - r64).abs().max())
-        print(f"loss curve: max|cuda-fp64| {dev:.4f}  max|fp32 oracle-fp64| {drift:.4f}  range {span:.2f}")
-        assert dev <= 3 * drift + 1e-3 * span, (dev, drift, span)
+        print(f"loss curve [{precision}] {name}: max|cuda-fp64| {dev:.4f}  max|fp32 oracle-fp64| {drift:.4f}  range {span:.2f}  "
+              f"(dev/range {dev / span:.2e})")
+        assert dev <= 3 * drift + tol * span, (dev, drift, span)
     tr.sync_optimizer_state()
     assert len(copt.state_dict()["state"]) == 13

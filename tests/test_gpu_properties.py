@@ -166,7 +166,7 @@ def test_deferred_conv_gradients_equal_plain_step():
     """Data-parallel overlap hook: with dg_critic_defer_conv_grads the critic iteration returns with the classifier gradients
     final and the conv gradients pending; after dg_critic_step_finish the bucket must equal the plain iteration's (same kernels;
     fp32 atomics -> tolerance).  Until the finish call every other critic entry point refuses to run."""
-    G, C, _, _ = pu.build_pair(CFG2_G, CFG2_C, "bf16", seed=1, critic_scale=1.9)
+    G, C, _g_sd, _c_sd = pu.build_pair(CFG2_G, CFG2_C, "bf16", seed=1, critic_scale=1.9)
     coarse, fine, alpha = synth_batch(8, 2, 16, seed=5, aseed=6)
     tr = pu.WassersteinGAN(G, C, None, None)
     lib = _lib.load()
@@ -189,9 +189,23 @@ def test_deferred_conv_gradients_equal_plain_step():
         torch.cuda.synchronize()
         return sc.cpu(), cg.cpu()
 
-    sc0, g0 = step(False)
+    # The conv / classifier weight-gradient reductions use fp32 atomics (red.global.add), so two runs of the SAME code differ by
+    # their summation order.  That run-to-run floor is measured here (plain vs plain, three pairs) and the deferred path must
+    # stay within 4x of it (+2e-4) on each slice; a real ordering bug (conv gradients unpacked before the side stream has finished,
+    # a stale classifier slice) is O(1), orders of magnitude above any floor.
+    plain = [step(False) for _ in range(4)]
+    sc0, g0 = plain[0]
+    floor_fc = max(pu.rel(g[off:], g0[off:]) for _s, g in plain[1:])
+    floor_conv = max(pu.rel(g[:off], g0[:off]) for _s, g in plain[1:])
     sc1, g1 = step(True)
     _lib.check(lib.dg_critic_defer_conv_grads(c, 0))
     assert torch.isfinite(g1).all()
     assert pu.rel(sc1, sc0) < 1e-5
-    assert pu.rel(g1[off:], g0[off:]) < 1e-4 and pu.rel(g1[:off], g0[:off]) < 1e-4
+    e_fc, e_conv = pu.rel(g1[off:], g0[off:]), pu.rel(g1[:off], g0[:off])
+    print(f"deferred vs plain: classifier {e_fc:.2e} (floor {floor_fc:.2e}), conv {e_conv:.2e} (floor {floor_conv:.2e})")
+    assert e_fc <= 4 * floor_fc + 2e-4 and e_conv <= 4 * floor_conv + 2e-4, (e_fc, floor_fc, e_conv, floor_conv)
+    assert max(e_fc, e_conv) < 5e-3  # sanity ceiling, far below an ordering bug
+    # both also agree with the fp32 oracle as well as the plain bf16 iteration does
+    oc = otr.critic_loss_and_grads(_g_sd, CFG2_G, _c_sd, CFG2_C, coarse, fine, alpha, otr.Hyper())
+    ref = torch.cat([v.reshape(-1) for v in oc["grads"].values()])
+    assert abs(pu.rel(g1, ref) - pu.rel(g0, ref)) < 1e-3
