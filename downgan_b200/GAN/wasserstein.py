@@ -17,7 +17,12 @@ Differences from the reference that do not change results:
   * the flattened gradient uses the actual batch size, not ``hp.batch_size``
     (the reference mis-shapes ragged batches, wasserstein.py:110);
   * mlflow logging / plotting (wasserstein.py:140-179) is out of scope; loss
-    scalars stay on the device in ``last_critic`` / ``last_generator``.
+    scalars stay on the device in ``last_critic`` / ``last_generator``.  The
+    per-batch metric pass itself (``gen_batch_and_log_metrics``,
+    mlflow_epoch.py:53-63: MAE / MSE / Wass with the updated weights) and the
+    test-set pass (wasserstein.py:159-172) are here: ``track_metrics`` /
+    ``testdataloader`` of ``_train_epoch``, epoch means in ``last_epoch_metrics``.
+    MS-SSIM needs the third-party pytorch_msssim package and is not provided.
 """
 from __future__ import annotations
 
@@ -34,6 +39,7 @@ from ..networks.generator import Generator
 
 CRITIC_SCALARS = ("critic_loss", "c_real_mean", "c_fake_mean", "gp", "penalty")
 GENERATOR_SCALARS = ("g_loss", "c_fake_mean", "l1")
+METRIC_SCALARS = ("MAE", "MSE", "Wass", "c_real_mean", "c_fake_mean")  # dg_metrics out8; hp.metrics_to_calculate = the first three
 
 
 class _FlatAdam:
@@ -106,6 +112,10 @@ class WassersteinGAN:
         # Off by default: measured 0.4 % slower than one all-reduce per iteration on 2 GPUs (two collectives + one more call
         # cost more than hiding 3.3 MB over NVLink saves), results identical (tools/dp_overlap_check.py).
         self.overlap_allreduce = os.environ.get("DG_OVERLAP_AR", "0") == "1"
+        self.freq_sep = False        # True: the iterations of GAN/wasserstein_fs.py (see WassersteinGANFS)
+        self.track_metrics = False   # True: _train_epoch runs the reference's per-batch metric pass on the training batches
+        self.last_epoch_metrics = None  # {"train": {"MAE", "MSE", "Wass"}, "test": {...}}: means over batches (mlflow_epoch.py:38-49)
+        self._m_scal = None
 
     # ---- helpers -------------------------------------------------------------
     @property
@@ -113,7 +123,8 @@ class WassersteinGAN:
         return self.G.conv1.weight.device
 
     def _hyper(self) -> _lib.Hyper:
-        return _lib.Hyper(float(hp.gp_lambda), float(hp.gamma), float(hp.content_lambda))
+        return _lib.Hyper(float(hp.gp_lambda), float(hp.gamma), float(hp.content_lambda),
+                          1 if getattr(self, "freq_sep", False) else 0, int(getattr(hp, "filter_size", 5)))
 
     def _prep(self, t: torch.Tensor) -> torch.Tensor:
         return t.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
@@ -205,6 +216,19 @@ class WassersteinGAN:
             self._g_adam.step(grads, scale)
         self.last_generator = self._g_scal
 
+    def _metrics_batch(self, coarse, fine, _fake_offset: Optional[int] = None) -> torch.Tensor:
+        """`gen_batch_and_log_metrics` (mlflow_epoch.py:53-63) for one batch: 8 floats on the device in METRIC_SCALARS
+        order, computed with the CURRENT weights of both networks.  `_fake_offset` (set by `_train_epoch`): G(coarse) is
+        still resident from the look-ahead pass and the generator has not been updated since, so it is not recomputed."""
+        coarse, fine = self._prep(coarse), self._prep(fine)
+        b = coarse.shape[0]
+        with torch.cuda.device(self.device):
+            g, c = self._handles(coarse)
+            out = torch.empty(8, device=self.device)
+            _lib.check(_lib.load().dg_metrics(g, c, None if _fake_offset is not None else coarse.data_ptr(),
+                                              int(_fake_offset or 0), fine.data_ptr(), b, out.data_ptr(), _lib.stream_ptr()))
+        return out
+
     def _gp(self, real, fake, critic, alpha: Optional[torch.Tensor] = None, want_grads: bool = False):
         """Gradient penalty value ``hp.gp_lambda * mean((||grad||-1)^2)`` (wasserstein.py:87-117).
         With ``want_grads`` also returns d(hp.gp_lambda * value)/d(critic params) as a flat tensor."""
@@ -261,7 +285,10 @@ class WassersteinGAN:
         Batches may live on the host: batch i+1 is copied to the device on a side stream while batch
         i trains, and the loss scalars of every step are copied back asynchronously into pinned
         memory (no per-step device synchronisation).  Returns a (steps, 8) CPU tensor of the critic
-        scalars (CRITIC_SCALARS order) — the reference logs the same quantities through mlflow."""
+        scalars (CRITIC_SCALARS order) — the reference logs the same quantities through mlflow.
+        With `self.track_metrics` every training batch is followed by the metric pass (wasserstein.py:140-146); with a
+        `testdataloader` the test-set pass runs after the loop (:159-172).  Their means over batches land in
+        `self.last_epoch_metrics`."""
         dev = self.device
         with torch.cuda.device(dev):
             if getattr(self, "_copy_stream", None) is None:
@@ -316,6 +343,10 @@ class WassersteinGAN:
             offsets = []  # look-ahead: sample offsets of the fakes of the next critic steps
             saved_steps = set()  # steps whose generator iteration reuses the look-ahead forward
             logs = []
+            track = bool(getattr(self, "track_metrics", False))
+            mlogs = []
+            if (track or testdataloader is not None) and getattr(self, "_metric_host", None) is None:
+                self._metric_host = torch.empty(1024, 8, dtype=torch.float32, pin_memory=True)
             while pending:
                 s = self.num_steps
                 if getattr(self, "lookahead", True) and not offsets and n_critic > 1 and s % n_critic != 0:
@@ -359,10 +390,23 @@ class WassersteinGAN:
                 ts = slot["bufs"]
                 coarse, fine = ts[0], ts[1]
                 alpha = ts[2] if len(ts) > 2 else None
-                self._critic_train_iteration(coarse, fine, alpha, _fake_offset=offsets.pop(0) if offsets else None)
-                if self.num_steps % n_critic == 0:
+                off = offsets.pop(0) if offsets else None
+                self._critic_train_iteration(coarse, fine, alpha, _fake_offset=off)
+                g_updated = self.num_steps % n_critic == 0
+                if g_updated:
                     self._generator_train_iteration(coarse, fine, _saved_forward=self.num_steps in saved_steps)
                     saved_steps.discard(self.num_steps)
+                if track:
+                    # the look-ahead fake of this batch is still G(coarse) unless the generator was just updated
+                    m = self._metrics_batch(coarse, fine, _fake_offset=None if g_updated else off)
+                    k = len(mlogs)
+                    if k >= self._metric_host.shape[0]:
+                        main.synchronize()
+                        grown = torch.empty(2 * (k + 1), 8, dtype=torch.float32, pin_memory=True)
+                        grown[:k].copy_(self._metric_host[:k])
+                        self._metric_host = grown
+                    self._metric_host[k].copy_(m, non_blocking=True)
+                    mlogs.append(k)
                 self.num_steps += 1
                 slot["done"] = torch.cuda.Event()
                 slot["done"].record(main)
@@ -377,7 +421,38 @@ class WassersteinGAN:
                 logs.append(k)
             self.last_enqueue_seconds = time.perf_counter() - t_enqueue0  # host time to enqueue the epoch (diagnostic)
             main.synchronize()
+            result = {}
+            if track:
+                result["train"] = self._metric_means(self._metric_host[:len(mlogs)])
+                if hasattr(dataloader, "skip_first_batch"):
+                    dataloader.skip_first_batch()  # RNG side effect of the reference's plot batch (wasserstein.py:155)
+            if testdataloader is not None:
+                # test-set pass (wasserstein.py:159-172): metrics only, no update; every batch needs its own generator forward
+                k = 0
+                for data in testdataloader:
+                    m = self._metrics_batch(data[0], data[1])
+                    if k >= self._metric_host.shape[0]:
+                        main.synchronize()
+                        grown = torch.empty(2 * (k + 1), 8, dtype=torch.float32, pin_memory=True)
+                        grown[:k].copy_(self._metric_host[:k])
+                        self._metric_host = grown
+                    self._metric_host[k].copy_(m, non_blocking=True)
+                    k += 1
+                main.synchronize()
+                result["test"] = self._metric_means(self._metric_host[:k])
+                if hasattr(testdataloader, "skip_first_batch"):
+                    testdataloader.skip_first_batch()  # wasserstein.py:175
+            if result:
+                self.last_epoch_metrics = result
         return self._log_host[:len(logs)].clone() if logs else torch.zeros(0, 8)
+
+    @staticmethod
+    def _metric_means(rows: torch.Tensor) -> dict:
+        """`post_epoch_metric_mean` (mlflow_epoch.py:38-49): the mean over batches of every tracked metric."""
+        if rows.shape[0] == 0:
+            return {k: float("nan") for k in hp.metrics_to_calculate}
+        m = rows.double().mean(0)
+        return {k: float(m[METRIC_SCALARS.index(k)]) for k in hp.metrics_to_calculate}
 
     def train(self, dataloader, testdataloader=None):
         self.num_steps = 0
@@ -388,3 +463,15 @@ class WassersteinGAN:
     def sync_optimizer_state(self) -> None:
         self._g_adam.sync_to_optimizer()
         self._c_adam.sync_to_optimizer()
+
+
+class WassersteinGANFS(WassersteinGAN):
+    """Wasserstein GAN with gradient penalty and frequency separation: drop-in for ``GAN/wasserstein_fs.py:15-91``.
+    The critic and the penalty see the high-pass parts ``x - low(x)`` of the real and generated fields, the content
+    loss compares their low-pass parts; ``low`` = ``hp.low(hp.rf(.))`` (hyperparams.py:31-35), one stencil kernel here
+    (``dg_lowpass``) with its adjoint in the generator's backward.  Upstream this class is not reachable from
+    ``train.py`` (``hp.freq_sep = False`` and its imports are broken); it is mirrored from its source statements."""
+
+    def __init__(self, G: Generator, C: Critic, G_optimizer, C_optimizer) -> None:
+        super().__init__(G, C, G_optimizer, C_optimizer)
+        self.freq_sep = True

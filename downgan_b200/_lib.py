@@ -33,7 +33,8 @@ class CriticConfig(C.Structure):
 
 
 class Hyper(C.Structure):
-    _fields_ = [("gp_lambda", C.c_float), ("gamma", C.c_float), ("content_lambda", C.c_float)]
+    _fields_ = [("gp_lambda", C.c_float), ("gamma", C.c_float), ("content_lambda", C.c_float),
+                ("freq_sep", C.c_int), ("filter_size", C.c_int)]
 
 
 _P = C.c_void_p
@@ -76,6 +77,9 @@ _SIGNATURES = {
     "dg_critic_activation": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "dg_generator_trunk_fwd": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "dg_generator_trunk_bwd": (C.c_int, [_P, _P, _P, _P, _P]),
+    "dg_metrics": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int, _P, _P]),
+    "dg_gather_rows": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int64, _P, _P]),
+    "dg_lowpass": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "dg_conv3x3_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_float, C.c_int, _P]),
     "dg_conv3x3_dgrad": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

@@ -16,5 +16,13 @@ print_every = 250
 save_every = 250
 use_cuda = True
 
-# Frequency separation is dead code in the reference (freq_sep = False, hyperparams.py:31)
+# Frequency separation parameters (hyperparams.py:30-35).  The reference builds `low = nn.AvgPool2d(filter_size, stride=1,
+# padding=0)` and `rf = nn.ReplicationPad2d(padding)` here; this path applies the same filter in one kernel (dg_lowpass).
+# freq_sep = False upstream: GAN/wasserstein_fs.py is not reachable from train.py; WassersteinGANFS below mirrors it anyway.
 freq_sep = False
+filter_size = 5
+padding = filter_size // 2
+
+# Metrics of the per-batch metric pass (hyperparams.py:38-43 `metrics_to_calculate`).  MAE, MSE and Wass are computed by
+# dg_metrics; "MSSSIM" needs the third-party pytorch_msssim package (absent here) and is not provided.
+metrics_to_calculate = ("MAE", "MSE", "Wass")

@@ -265,3 +265,13 @@ namespace dg {
 bool wgrad_im2col_supported(const WgradOp& op);
 int wgrad_im2col(const WgradOp& op, cudaStream_t st);
 }  // namespace dg
+
+namespace dg {
+// data-path kernels (dg_data.cu)
+int gather_rows(const float* src, const long long* idx_dev, int n_rows, long long row_elems, long long n_src, float* dst, cudaStream_t st);
+size_t metric_scratch_bytes();
+// out[0..4] = MAE(a,b), MSE(a,b), mean(scores[0:B]) - mean(scores[B:2B]), and the two means; deterministic two-stage reduction
+int metric_sums(const float* a, const float* b, long long n, const float* scores, int B, double* scratch, float* out, cudaStream_t st);
+// replicate-pad box filter on images with pixel stride cs (NHWC: cs = C; NCHW planes: cs = 1); mode 0 low, 1 high-pass, 2 adjoint
+int lowpass_replicate(const float* x, float* y, long long images, int H, int W, int cs, int radius, int mode, cudaStream_t st);
+}  // namespace dg

@@ -618,10 +618,10 @@ __global__ void build_critic_input_kernel(const float* __restrict__ real, const 
       const float r = real[(n * C + c) * HW + hw];
       const float f = fake_nchw ? fake[(n * C + c) * HW + hw] : fake[i * C + c];
       const float x = a * r + (1.f - a) * f;
-      if (mode == 0) {
+      if (mode == 0 || mode == 2) {  // mode 2: [real ; fake] only (metric pass)
         dst[i * C + c] = r;
         dst[(tot + i) * C + c] = f;
-        dst[(2 * tot + i) * C + c] = x;
+        if (mode == 0) dst[(2 * tot + i) * C + c] = x;
       } else {
         dst[i * C + c] = x;
       }
@@ -631,7 +631,7 @@ __global__ void build_critic_input_kernel(const float* __restrict__ real, const 
 int build_critic_input(const float* real, const float* fake, int fake_is_nchw, const float* alpha, float* dst, int B,
                        int C, int H, int W, int mode, cudaStream_t st) {
   const size_t HW = (size_t)H * W;
-  Prof prof(PC_INTERP, 0.0, (double)HW * B * C * 4.0 * (mode == 0 ? 5.0 : 3.0), st);
+  Prof prof(PC_INTERP, 0.0, (double)HW * B * C * 4.0 * (mode == 0 ? 5.0 : (mode == 2 ? 4.0 : 3.0)), st);
   build_critic_input_kernel<<<ew_grid(HW * B), 256, 0, st>>>(real, fake, fake_is_nchw, alpha, dst, B, C, HW, mode);
   DG_LAUNCH_CHECK();
   return 0;
@@ -1208,7 +1208,7 @@ CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank,
   return fn(map, dt, rank, addr, dims, strides, box, estr, il, sw, l2, oob);
 }
 }  // namespace dg
-namespace dg { int g_tune[DG_TUNE_KEYS] = {1, 1, 1, 0, 1, 0, 1, 1, 1, 1, 4, 1, 1, 3, 0, 0}; }  // see include/downgan_b200.h: dg_set_tuning
+namespace dg { int g_tune[DG_TUNE_KEYS] = {1, 1, 1, 0, 1, 0, 1, 1, 1, 1, 4, 1, 1, 3, 1, 0}; }  // see include/downgan_b200.h: dg_set_tuning
 extern "C" int dg_set_tuning(int key, int value) {
   if (key < 0 || key >= DG_TUNE_KEYS) { dg::set_error("dg_set_tuning: unknown key %d", key); return DG_ERR_INVALID; }
   const int prev = dg::g_tune[key];

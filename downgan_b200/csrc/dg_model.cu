@@ -810,6 +810,8 @@ struct dg_critic {
   void* dz[9] = {nullptr};   // dz[1..8]
   float *g = nullptr, *u = nullptr;        // (maxB,Hf,Hf,nc) fp32
   void *v0 = nullptr, *v1 = nullptr;       // JVP ping-pong
+  double* metric_scratch = nullptr;        // block partials of the MAE / MSE reduction (dg_metrics)
+  float *fs_real = nullptr, *fs_fake = nullptr;  // frequency separation: high-pass real (NCHW) / fake (NHWC), allocated on first use
   void* keep[9] = {nullptr};               // parity instrumentation (dg_set_tuning(15, 1)): the interpolates' activations a[1..8]
   int keep_batch = 0;
   float *sumsq = nullptr, *coef = nullptr, *norms = nullptr, *scal = nullptr;
@@ -953,6 +955,7 @@ extern "C" int dg_critic_create(const dg_critic_config* cfg, dg_critic** out) {
   CA(c->coef, B * sizeof(float));
   CA(c->norms, B * sizeof(float));
   CA(c->scal, 64);
+  CA(c->metric_scratch, metric_scratch_bytes());
 #undef CA
   if ((s = c->side.create(1)) != 0) { dg_critic_destroy(c); return s; }
   *out = c;
@@ -1271,6 +1274,17 @@ __global__ void critic_seed_kernel(float* seed, int B) {
 // as an NHWC fp32 tensor.
 static int critic_step_body(dg_generator* g, dg_critic* c, const dg_hyper* hp, const float* fake_nhwc, const float* fine,
                             const float* alpha, int B, float* c_grads_flat, float* scalars, cudaStream_t st) {
+  if (hp->freq_sep) {
+    // frequency separation (GAN/wasserstein_fs.py:41-51): the critic and the penalty see the high-pass parts
+    // x - low(x), low = AvgPool2d(filter_size, 1) o ReplicationPad2d(filter_size // 2)   (config/hyperparams.py:31-35)
+    DG_CHECK(hp->filter_size >= 1 && (hp->filter_size & 1), "frequency separation: filter_size %d must be odd", hp->filter_size);
+    const size_t fb = (size_t)c->maxB * c->Hf * c->Hf * c->nc * sizeof(float);
+    if (!c->fs_real) { DG_TRY(dev_alloc(c->pool, (void**)&c->fs_real, fb)); DG_TRY(dev_alloc(c->pool, (void**)&c->fs_fake, fb)); }
+    DG_TRY(lowpass_replicate(fine, c->fs_real, (long long)B * c->nc, c->Hf, c->Hf, 1, hp->filter_size / 2, 1, st));       // NCHW planes
+    DG_TRY(lowpass_replicate(fake_nhwc, c->fs_fake, B, c->Hf, c->Hf, c->nc, hp->filter_size / 2, 1, st));                 // NHWC
+    fine = c->fs_real;
+    fake_nhwc = c->fs_fake;
+  }
   // one 3B critic batch: [real ; fake ; alpha*real + (1-alpha)*fake]   (:37-38, :91-97)
   DG_TRY(build_critic_input(fine, fake_nhwc, 0, alpha, c->a0, B, c->nc, c->Hf, c->Hf, 0, st));
   const bool two_chain = g_tune[9] >= 2 && c->side.s != nullptr;
@@ -1436,14 +1450,35 @@ extern "C" int dg_critic_step_fake(dg_generator* g, dg_critic* c, const dg_hyper
 static int generator_step_body(dg_generator* g, dg_critic* c, const dg_hyper* hp, const float* fine, int B, float* g_grads_flat,
                                float* scalars, cudaStream_t st) {
   const long long n = (long long)B * g->Hf * g->Hf * g->Cout;
-  // c_fake = C(fake); adversarial seed d(-gamma*mean)/dscore = -gamma/B
-  DG_CUDA(cudaMemcpyAsync(c->a0, g->fake, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  const int R = hp->filter_size / 2;
+  if (hp->freq_sep) {
+    DG_CHECK(hp->filter_size >= 1 && (hp->filter_size & 1), "frequency separation: filter_size %d must be odd", hp->filter_size);
+    const size_t fb = (size_t)c->maxB * c->Hf * c->Hf * c->nc * sizeof(float);
+    if (!c->fs_real) { DG_TRY(dev_alloc(c->pool, (void**)&c->fs_real, fb)); DG_TRY(dev_alloc(c->pool, (void**)&c->fs_fake, fb)); }
+    // c_fake = C(fake - low(fake))   (wasserstein_fs.py:75-82)
+    DG_TRY(lowpass_replicate(g->fake, c->a0, B, g->Hf, g->Hf, g->Cout, R, 1, st));
+  } else {
+    // c_fake = C(fake)
+    DG_CUDA(cudaMemcpyAsync(c->a0, g->fake, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  }
+  // adversarial seed d(-gamma*mean)/dscore = -gamma/B
   DG_TRY(critic_forward_internal(c, B, st));
   DG_TRY(fill(c->seed, -hp->gamma / B, B, st));
   DG_TRY(critic_backward_chain(c, B, 0, B, c->g, st));
   // content loss + its seed, added to the adversarial input-gradient   (wasserstein.py:78, losses.py:51-53)
   DG_TRY(nchw_to_nhwc(fine, tv(g->fine_nhwc, 0, g->Cout), B, g->Cout, g->Hf, g->Hf, st));
-  DG_TRY(l1_loss(g->fake, g->fine_nhwc, n, hp->content_lambda, g->l1, g->dfake, c->g, st));
+  if (hp->freq_sep) {
+    // L1 on the low-pass parts (wasserstein_fs.py:88).  With L = low (linear) and gh = dAdv/d(fake_high):
+    //   dLoss/dfake = (I - L^T) gh + L^T s,  s = content_lambda * sign(low(fake) - low(fine)) / n   =  gh + L^T (s - gh)
+    DG_TRY(lowpass_replicate(g->fake, c->fs_fake, B, g->Hf, g->Hf, g->Cout, R, 0, st));
+    DG_TRY(lowpass_replicate(g->fine_nhwc, c->fs_real, B, g->Hf, g->Hf, g->Cout, R, 0, st));
+    DG_TRY(l1_loss(c->fs_fake, c->fs_real, n, hp->content_lambda, g->l1, g->dfake, nullptr, st));                    // dfake = s
+    DG_TRY(scale_add(tv(c->fs_fake, 0, 1), tv(g->dfake, 0, 1), 1.f, tv(c->g, 0, 1), -1.f, (size_t)n, 1, st));       // s - gh
+    DG_TRY(lowpass_replicate(c->fs_fake, c->fs_real, B, g->Hf, g->Hf, g->Cout, R, 2, st));                           // L^T (s - gh)
+    DG_TRY(scale_add(tv(g->dfake, 0, 1), tv(c->g, 0, 1), 1.f, tv(c->fs_real, 0, 1), 1.f, (size_t)n, 1, st));        // gh + ...
+  } else {
+    DG_TRY(l1_loss(g->fake, g->fine_nhwc, n, hp->content_lambda, g->l1, g->dfake, c->g, st));
+  }
   DG_TRY(gen_scalars(c->scores, B, g->l1, hp->gamma, hp->content_lambda, scalars, st));
   DG_TRY(gen_backward_internal(g, g_grads_flat, nullptr, st));
   c->saved_batch = 0;
@@ -1486,6 +1521,47 @@ extern "C" int dg_generator_step_saved(dg_generator* g, dg_critic* c, const dg_h
   DG_TRY(g->side.join(st));  // a deferred look-ahead chain (dg_generator_lookahead_first) may still be running
   DG_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(float), st));
   return generator_step_body(g, c, hp, fine, batch, g_grads_flat, scalars, st);
+}
+
+// Per-batch metric pass, mlflow_tools/mlflow_epoch.py:53-63 (`gen_batch_and_log_metrics`): fake = G(coarse) with the CURRENT
+// generator weights, mean C(real) and mean C(fake) with the CURRENT critic weights, MAE = content_loss(real, fake)
+// (losses.py:40-55), MSE = content_MSELoss (:58-68), Wass = wass_loss(creal, cfake) = creal - cfake (:8-9).  MS-SSIM
+// (losses.py:12-38) comes from the third-party pytorch_msssim package and is not part of this path.
+// One generator forward (skipped when `coarse` is NULL: the fake is taken from the look-ahead buffer, valid while the
+// generator weights have not changed since that pass), ONE critic forward over [real ; fake] (2B rows), one fused
+// MAE + MSE reduction over the two fp32 fields.
+extern "C" int dg_metrics(dg_generator* g, dg_critic* c, const float* coarse, int fake_offset, const float* fine, int batch,
+                          float* out8, void* stream) {
+  if (c && c->pending_finish) { set_error("dg_metrics: dg_critic_step_finish has not been called"); return DG_ERR_STATE; }
+  DG_CHECK(g && c && fine && out8, "dg_metrics: null argument");
+  DG_CHECK(batch >= 1 && batch <= c->maxB && batch <= g->maxB, "dg_metrics: batch %d too large", batch);
+  DG_CHECK(g->Hf == c->Hf && g->Cout == c->nc, "dg_metrics: generator output does not match critic input");
+  if (!g->packed || !c->packed) { set_error("dg_metrics: weights not packed"); return DG_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* fake = nullptr;
+  if (coarse) {
+    DG_TRY(g->side.join(st));
+    DG_TRY(nchw_to_nhwc(coarse, g->act(g->x0, g->Cin), batch, g->Cin, g->Hc, g->Hc, st));
+    DG_TRY(gen_forward_internal(g, batch, 0, st));
+    g->saved_batch = 0;
+    g->lookahead = 0;
+    fake = g->fake;
+  } else {
+    if (fake_offset < 0 || fake_offset + batch > g->lookahead) {
+      set_error("dg_metrics: samples [%d,%d) are not covered by the last look-ahead pass (%d samples)", fake_offset, fake_offset + batch,
+                g->lookahead);
+      return DG_ERR_STATE;
+    }
+    if (g->side.dirty && !(fake_offset >= g->ready_lo && fake_offset + batch <= g->ready_hi)) DG_TRY(g->side.join(st));
+    fake = g->fake + (size_t)fake_offset * g->Hf * g->Hf * g->Cout;
+  }
+  DG_TRY(c->side.join(st));
+  DG_TRY(build_critic_input(fine, fake, 0, nullptr, c->a0, batch, c->nc, c->Hf, c->Hf, 2, st));  // [real ; fake], no interpolates
+  DG_TRY(critic_forward_internal(c, 2 * batch, st));
+  const long long n = (long long)batch * c->Hf * c->Hf * c->nc;
+  DG_TRY(metric_sums(c->a0, c->a0 + n, n, c->scores, batch, c->metric_scratch, out8, st));
+  c->saved_batch = 0;
+  return 0;
 }
 
 // ===========================================================================

@@ -1,8 +1,8 @@
 // tcgen05 kernels for the critic classifier's hidden layer (classifier.0: 8F*(fine/16)^2 -> 100, critic.py:94-96), sm_100a.
 //
-// STATUS: compiled and wired behind dg_set_tuning(14, 1), default OFF - written at the end of round 1 without GPU time
-// left, NOT yet validated on hardware (tests/test_gpu_fc_umma.py is skipped unless DG_TEST_FC_UMMA=1).  The CUDA-core
-// kernels of dg_kernels.cu remain the shipped path.
+// STATUS: validated on a B200 in round 2 (tests/test_gpu_fc_umma.py: scalars and every gradient against the CUDA-core
+// kernels at B = 5 / 16 / 64; profiles/README.md has the A/B) and ON by default (dg_set_tuning(14, 0) selects the CUDA-core
+// kernels of dg_kernels.cu, which remain for fp32 mode and for shapes outside fc_umma_supported).
 //
 // profiles/per_layer_roofline_r01g.md: the five classifier launches of a critic iteration take 138 us more than their
 // roofline time on the CUDA cores (~10 TFLOP/s).  All three products are small GEMMs with one long dimension (K = 8192):

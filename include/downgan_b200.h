@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DG_ABI_VERSION 1
+#define DG_ABI_VERSION 2
 
 typedef enum dg_status {
   DG_OK = 0,
@@ -77,6 +77,9 @@ typedef struct dg_hyper {
   float gp_lambda;       /* 10; applied twice as in wasserstein.py:40,117 */
   float gamma;           /* 0.01 */
   float content_lambda;  /* 5 */
+  int freq_sep;          /* hyperparams.py:31 (False): != 0 runs the iterations of GAN/wasserstein_fs.py:28-91 - the critic and
+                            the penalty see x - low(x), the content loss compares low(fake) with low(fine) */
+  int filter_size;       /* hyperparams.py:32 (5): low = AvgPool2d(filter_size, stride 1) o ReplicationPad2d(filter_size // 2) */
 } dg_hyper;
 
 typedef struct dg_generator dg_generator;
@@ -226,6 +229,25 @@ int dg_critic_activation(dg_critic* c, int which, int s0, int batch, float* out,
 int dg_generator_trunk_fwd(dg_generator* g, const float* x, int batch, float* y, void* stream);
 int dg_generator_trunk_bwd(dg_generator* g, const float* d_y, float* d_x, float* grads_flat, void* stream);
 
+/* ---- per-batch metric pass (mlflow_tools/mlflow_epoch.py:53-63 gen_batch_and_log_metrics) -----------------------
+ * out8 (device): [0] MAE = content_loss(real, fake) (GAN/losses.py:40-55)  [1] MSE = content_MSELoss (:58-68)
+ * [2] Wass = wass_loss(mean C(real), mean C(fake)) = their difference (:8-9)  [3] mean C(real)  [4] mean C(fake)  [5..7] 0,
+ * with fake = G(coarse) and both networks' CURRENT weights.  coarse == NULL: fake is taken from samples
+ * [fake_offset, fake_offset + batch) of the last look-ahead pass (valid while the generator has not been updated since).
+ * MS-SSIM (losses.py:12-38) is computed by the third-party pytorch_msssim package in the reference and is not provided. */
+int dg_metrics(dg_generator* g, dg_critic* c, const float* coarse, int fake_offset, const float* fine, int batch,
+               float* out8, void* stream);
+
+/* ---- batch assembly (GAN/dataloader.py:25-33 __getitem__ per sample + torch's default collate) -------------------
+ * dst[r] = src[idx[r]] for r < n_rows; a row is row_elems contiguous floats, src holds n_src rows, idx is a DEVICE array of
+ * int64 row numbers (the shuffled order of the epoch).  One coalesced gather from the HBM-resident dataset. */
+int dg_gather_rows(const float* src, const int64_t* idx, int n_rows, int64_t row_elems, int64_t n_src, float* dst, void* stream);
+
+/* ---- frequency-separation filter (config/hyperparams.py:31-35; GAN/wasserstein_fs.py:41-47) ----------------------
+ * x, y: `planes` contiguous (h, w) fp32 images (NCHW tensors: planes = N*C).  mode 0: y = low(x) = AvgPool2d(filter_size, 1)
+ * (ReplicationPad2d(filter_size // 2)(x));  mode 1: y = x - low(x);  mode 2: y = low^T(x) (adjoint, used by the backward). */
+int dg_lowpass(const float* x, float* y, int64_t planes, int h, int w, int filter_size, int mode, void* stream);
+
 /* Number of kernel launches this library has enqueued since load (for bench.py's gpu_launches). */
 int64_t dg_launch_count(void);
 
@@ -259,7 +281,7 @@ int dg_profile_report(double* out, int n_classes);
  * key 13 = k > 0 (with key 9 == 1): the real + fake rows of the weight gradients of critic layers 0 .. k-1 are enqueued on
  * the side stream during the input-gradient chain, their interpolates' rows during the JVP chain (0: one 3B launch per layer).
  * key 14: classifier.0 products (forward, input gradient, weight gradient) on the tcgen05 kernels of csrc/dg_umma_fc.cu (1)
- * or on the CUDA-core kernels (0, default: the tcgen05 variants have not been validated on hardware yet).
+ * (1, default: validated in round 2, tests/test_gpu_fc_umma.py; +1.8 % on the cfg-2 step) or on the CUDA-core kernels (0).
  * key 15: parity instrumentation - the fused critic iteration keeps a copy of the interpolates' activations for
  * dg_critic_activation(101..108) (0, default: off, no copy).
  * Returns the previous value, or DG_ERR_INVALID for an unknown key. */

@@ -13,7 +13,17 @@ TEST INFRASTRUCTURE ONLY.  Runs in the build container, where
   4. writes ``tests/golden/tiny.npz`` (inputs, weights, outputs, gradients of
      a small configuration) and ``tests/golden/cfg1_summary.json`` (per-tensor
      gradient norms etc. of BASELINE cfg-1) for the tests that run where the
-     reference is absent.
+     reference is absent,
+  5. (round 2) pins the adjacent rows of SURVEY.md §8f on the same tiny configuration and writes
+     ``tests/golden/tiny_extra.json`` + ``tests/golden/ref_tiny_{generator,critic}_state_dict.pth``:
+       * the per-batch metrics through the reference's OWN ``content_loss`` / ``content_MSELoss`` / ``wass_loss``
+         (GAN/losses.py, imported with a stub for its absent third-party ``pytorch_msssim`` dependency) as
+         ``gen_batch_and_log_metrics`` calls them (mlflow_epoch.py:53-63),
+       * the frequency-separation iterations by executing the statements of GAN/wasserstein_fs.py:36-91 on the
+         reference modules with the filters of config/hyperparams.py:31-35 (that file itself cannot be imported:
+         ``import stage as s``), asserted bit-equal to ``oracle.trainer.*_fs``,
+       * ``torch.save(module.state_dict())`` of the reference modules = what ``mlflow.pytorch.log_state_dict`` stores
+         (mlflow_epoch.py:65-69), for the checkpoint-compatibility tests.
 
 Usage:  python -m oracle.make_golden
 """
@@ -158,6 +168,101 @@ def check_config(name, gspec: onet.GeneratorSpec, cspec: onet.CriticSpec, b, see
     return g_sd, c_sd, coarse, fine, alpha, oc, og
 
 
+def _ref_losses():
+    """GAN/losses.py with a stub for `pytorch_msssim` (only SSIM_Loss, which is out of scope, needs it)."""
+    import types
+    if "pytorch_msssim" not in sys.modules:
+        stub = types.ModuleType("pytorch_msssim")
+        stub.MS_SSIM = object
+        sys.modules["pytorch_msssim"] = stub
+    sys.path.insert(0, REF)
+    from DoWnGAN.GAN import losses  # type: ignore
+    return losses
+
+
+def ref_fs_critic_step_grads(G, C, coarse, fine, alpha, hp: otr.Hyper, filter_size=5):
+    """wasserstein_fs.py:36-60 + its _gp (:94-124) on the reference modules; filters as hyperparams.py:31-35."""
+    low = torch.nn.AvgPool2d(filter_size, stride=1, padding=0)
+    rf = torch.nn.ReplicationPad2d(filter_size // 2)
+    fake = G(coarse)
+    fake_low = low(rf(fake))
+    real_low = low(rf(fine))
+    fake_high = fake - fake_low
+    real_high = fine - real_low
+    c_real = C(real_high)
+    c_fake = C(fake_high)
+    a = alpha.expand_as(real_high)
+    interpolated = (a * real_high.data + (1 - a) * fake_high.data).requires_grad_(True)
+    ci = C(interpolated)
+    gradients = torch.autograd.grad(outputs=ci, inputs=interpolated, grad_outputs=torch.ones(ci.size()),
+                                    create_graph=True, retain_graph=True)[0]
+    gn = torch.sqrt(torch.sum(gradients.view(fine.size(0), -1) ** 2, dim=1) + 1e-12)
+    gp = hp.gp_lambda * torch.mean((gn - 1) ** 2)
+    C.zero_grad()
+    loss = torch.mean(c_fake) - torch.mean(c_real) + hp.gp_lambda * gp
+    loss.backward(retain_graph=True)
+    grads = OrderedDict((k, (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p)))
+                        for k, p in C.named_parameters())
+    return loss.detach(), gp.detach(), grads
+
+
+def ref_fs_generator_step_grads(G, C, coarse, fine, hp: otr.Hyper, filter_size=5):
+    """wasserstein_fs.py:71-91 on the reference modules."""
+    low = torch.nn.AvgPool2d(filter_size, stride=1, padding=0)
+    rf = torch.nn.ReplicationPad2d(filter_size // 2)
+    G.zero_grad()
+    fake = G(coarse)
+    fake_low = low(rf(fake))
+    real_low = low(rf(fine))
+    fake_high = fake - fake_low
+    c_fake = C(fake_high)
+    g_loss = -torch.mean(c_fake) * hp.gamma
+    g_loss = g_loss + hp.content_lambda * torch.nn.L1Loss()(fake_low, real_low)
+    g_loss.backward()
+    return g_loss.detach(), OrderedDict((k, p.grad.detach().clone()) for k, p in G.named_parameters())
+
+
+def extra_rows(gspec, cspec, g_sd, c_sd, coarse, fine, alpha):
+    """Step 5 of the module docstring; returns the dict written to tiny_extra.json."""
+    Generator, Critic = _ref_modules()
+    hp = otr.Hyper()
+    C = Critic(cspec.coarse_dim, cspec.fine_dim, cspec.nc)
+    G = Generator(gspec.filters, cspec.fine_dim, gspec.channels, gspec.n_predictands, gspec.num_res_blocks, gspec.num_upsample)
+    C.load_state_dict(c_sd)
+    G.load_state_dict(g_sd)
+    torch.save(G.state_dict(), os.path.join(GOLD, "ref_tiny_generator_state_dict.pth"))
+    torch.save(C.state_dict(), os.path.join(GOLD, "ref_tiny_critic_state_dict.pth"))
+    # metrics, as gen_batch_and_log_metrics computes them
+    losses = _ref_losses()
+    with torch.no_grad():
+        fake = G(coarse).detach()
+        creal = torch.mean(C(fine)).detach()
+        cfake = torch.mean(C(fake)).detach()
+    ref_m = {"MAE": losses.content_loss(fine, fake, "cpu"), "MSE": losses.content_MSELoss(fine, fake, "cpu"),
+             "Wass": losses.wass_loss(creal, cfake, "cpu")}
+    om = otr.batch_metrics(g_sd, gspec, c_sd, cspec, coarse, fine)
+    for k, v in ref_m.items():
+        assert torch.equal(v, om[k]), f"metric {k}: reference {float(v)} oracle {float(om[k])}"
+    # frequency separation
+    loss, gp, cgr = ref_fs_critic_step_grads(G, C, coarse, fine, alpha, hp)
+    oc = otr.critic_loss_and_grads_fs(g_sd, gspec, c_sd, cspec, coarse, fine, alpha, hp)
+    assert torch.equal(oc["loss"], loss) and torch.equal(oc["gp"], gp)
+    for k in cgr:
+        assert torch.equal(cgr[k], oc["grads"][k]), f"FS critic grad mismatch {k}"
+    gl, ggr = ref_fs_generator_step_grads(G, C, coarse, fine, hp)
+    og = otr.generator_loss_and_grads_fs(g_sd, gspec, c_sd, cspec, coarse, fine, hp)
+    assert torch.equal(og["loss"], gl)
+    for k in ggr:
+        assert torch.equal(ggr[k], og["grads"][k]), f"FS generator grad mismatch {k}"
+    print("[tiny] reference==oracle bit-exact (metrics MAE/MSE/Wass via GAN/losses.py; frequency-separation critic and "
+          "generator losses + all gradients)")
+    return {"metrics": {k: float(v) for k, v in ref_m.items()}, "c_real_mean": float(creal), "c_fake_mean": float(cfake),
+            "fs_critic_loss": float(loss), "fs_gp": float(gp), "fs_gen_loss": float(gl), "fs_l1": float(og["l1"]),
+            "fs_dC_norm": {k: float(v.norm()) for k, v in cgr.items()},
+            "fs_dG_total_norm": float(torch.sqrt(sum((v.double() ** 2).sum() for v in ggr.values()))),
+            "fs_dG_norm_tail": {k: float(v.norm()) for k, v in list(ggr.items())[-10:]}}
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -180,6 +285,10 @@ def main():
         blob["dG/" + k] = v.numpy()
     np.savez_compressed(os.path.join(GOLD, "tiny.npz"), **blob)
     print("wrote tiny.npz", os.path.getsize(os.path.join(GOLD, "tiny.npz")) // 1024, "KiB")
+    extra = extra_rows(gspec, cspec, g_sd, c_sd, coarse, fine, alpha)
+    with open(os.path.join(GOLD, "tiny_extra.json"), "w") as f:
+        json.dump(extra, f, indent=1)
+    print("wrote tiny_extra.json and the reference state_dict checkpoints")
 
     # ---- cfg-1 (BASELINE.json configs[0]): summary only ----------------------
     gspec = onet.GeneratorSpec(filters=16, channels=2)

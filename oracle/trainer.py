@@ -100,7 +100,10 @@ def critic_loss_and_grads(g_sd, gspec: GeneratorSpec, c_sd, cspec: CriticSpec,
 def generator_loss_and_grads(g_sd, gspec: GeneratorSpec, c_sd, cspec: CriticSpec,
                              coarse, fine, hp: Hyper, dtype=None, tapes=None):
     """One generator objective + parameter grads (wasserstein.py:65-80).
-    ``tapes``: optional {"gen", "fake"} -> networks.MaskTape (parity diagnostics)."""
+    ``tapes``: optional {"gen", "fake"} -> networks.MaskTape (parity diagnostics); ``tapes["l1_sign"]``: a tensor of
+    the signs sign(fake - fine) to use for the L1 term's derivative (|.| is the generator objective's other kink: where
+    |fake - fine| is below the CUDA path's rounding error of `fake` its sign — the whole gradient seed of that element —
+    differs; pinning it makes the L1 term the linear function ((fake - fine) * sign).mean())."""
     tapes = tapes or {}
     gp_ = as_leaf_params(g_sd, dtype)
     cp = {k: (v.to(dtype) if dtype is not None else v) for k, v in c_sd.items()}
@@ -109,7 +112,10 @@ def generator_loss_and_grads(g_sd, gspec: GeneratorSpec, c_sd, cspec: CriticSpec
     fake = generator_forward(gp_, gspec, coarse, tapes.get("gen"))
     c_fake = critic_forward(cp, cspec, fake, tapes.get("fake"))
     adv = -c_fake.mean() * hp.gamma
-    l1 = (fake - fine).abs().mean()  # nn.L1Loss default 'mean' over all elements
+    if tapes.get("l1_sign") is not None:
+        l1 = ((fake - fine) * tapes["l1_sign"].to(fake.dtype)).mean()
+    else:
+        l1 = (fake - fine).abs().mean()  # nn.L1Loss default 'mean' over all elements
     loss = adv + hp.content_lambda * l1
     grads = torch.autograd.grad(loss, list(gp_.values()))
     gd = OrderedDict((k, g.detach()) for k, g in zip(gp_.keys(), grads))
@@ -207,7 +213,11 @@ class OracleTrainer:
     """State + schedule of the reference trainer (wasserstein.py:16-55,131-147)
     with injectable alpha.  Metrics logging and mlflow are out of scope."""
 
-    def __init__(self, g_sd, gspec: GeneratorSpec, c_sd, cspec: CriticSpec, hp: Optional[Hyper] = None, dtype=None):
+    def __init__(self, g_sd, gspec: GeneratorSpec, c_sd, cspec: CriticSpec, hp: Optional[Hyper] = None, dtype=None,
+                 emulate_bf16: bool = False):
+        # emulate_bf16: every conv / linear input and weight rounded to bf16 (networks.MaskTape(bf16=True)), fp32 master weights
+        # and fp32 Adam - what bf16 STORAGE alone does to the reference's trajectory (yardstick of the bf16 loss-curve test)
+        self.emulate_bf16 = emulate_bf16
         self.hp = hp or Hyper()
         self.gspec, self.cspec = gspec, cspec
         self.dtype = dtype
@@ -217,13 +227,19 @@ class OracleTrainer:
         self.g_adam, self.c_adam = AdamState(), AdamState()
         self.num_steps = 0
 
+    def _tapes(self, names):
+        from .networks import MaskTape
+        return {k: MaskTape(bf16=True) for k in names} if self.emulate_bf16 else None
+
     def critic_iteration(self, coarse, fine, alpha):
-        out = critic_loss_and_grads(self.g, self.gspec, self.c, self.cspec, coarse, fine, alpha, self.hp, self.dtype)
+        out = critic_loss_and_grads(self.g, self.gspec, self.c, self.cspec, coarse, fine, alpha, self.hp, self.dtype,
+                                    tapes=self._tapes(("gen", "real", "fake", "interp")))
         adam_update(self.c, out["grads"], self.c_adam, self.hp)
         return out
 
     def generator_iteration(self, coarse, fine):
-        out = generator_loss_and_grads(self.g, self.gspec, self.c, self.cspec, coarse, fine, self.hp, self.dtype)
+        out = generator_loss_and_grads(self.g, self.gspec, self.c, self.cspec, coarse, fine, self.hp, self.dtype,
+                                       tapes=self._tapes(("gen", "fake")))
         adam_update(self.g, out["grads"], self.g_adam, self.hp)
         return out
 
@@ -235,3 +251,70 @@ class OracleTrainer:
             g_out = self.generator_iteration(coarse, fine)
         self.num_steps += 1
         return c_out, g_out
+
+
+# --------------------------------------------------------------------------
+# per-batch metric pass (mlflow_tools/mlflow_epoch.py:53-63, table config/hyperparams.py:38-43)
+# --------------------------------------------------------------------------
+def batch_metrics(g_sd, gspec: GeneratorSpec, c_sd, cspec: CriticSpec, coarse, fine, dtype=None):
+    """``gen_batch_and_log_metrics``: fake = G(coarse).detach(); creal = mean C(real); cfake = mean C(fake);
+    MAE = content_loss = nn.L1Loss (losses.py:40-55), MSE = content_MSELoss = nn.MSELoss (:58-68),
+    Wass = wass_loss(creal, cfake) = creal - cfake (:8-9).  MSSSIM (:12-38) needs pytorch_msssim (absent) and is left out."""
+    cast = (lambda t: t.to(dtype)) if dtype is not None else (lambda t: t)
+    g = {k: cast(v) for k, v in g_sd.items()}
+    c = {k: cast(v) for k, v in c_sd.items()}
+    coarse, fine = cast(coarse), cast(fine)
+    with torch.no_grad():
+        fake = generator_forward(g, gspec, coarse)
+        creal = critic_forward(c, cspec, fine).mean()
+        cfake = critic_forward(c, cspec, fake).mean()
+        return {"MAE": (fine - fake).abs().mean(), "MSE": ((fine - fake) ** 2).mean(), "Wass": creal - cfake,
+                "c_real_mean": creal, "c_fake_mean": cfake}
+
+
+# --------------------------------------------------------------------------
+# frequency separation (GAN/wasserstein_fs.py:28-91; filters config/hyperparams.py:31-35)
+# --------------------------------------------------------------------------
+def low_pass(x: torch.Tensor, filter_size: int = 5) -> torch.Tensor:
+    """``hp.low(hp.rf(x))``: ReplicationPad2d(filter_size // 2) then AvgPool2d(filter_size, stride=1, padding=0)."""
+    p = filter_size // 2
+    return F.avg_pool2d(F.pad(x, (p, p, p, p), mode="replicate"), filter_size, stride=1, padding=0)
+
+
+def critic_loss_and_grads_fs(g_sd, gspec: GeneratorSpec, c_sd, cspec: CriticSpec, coarse, fine, alpha, hp: Hyper,
+                             filter_size: int = 5, dtype=None):
+    """wasserstein_fs.py:36-60: the critic and the penalty see the high-pass parts x - low(x)."""
+    gp_ = {k: (v.to(dtype) if dtype is not None else v) for k, v in g_sd.items()}
+    cp = as_leaf_params(c_sd, dtype)
+    if dtype is not None:
+        coarse, fine, alpha = coarse.to(dtype), fine.to(dtype), alpha.to(dtype)
+    with torch.no_grad():
+        fake = generator_forward(gp_, gspec, coarse)
+        fake_high = fake - low_pass(fake, filter_size)
+        real_high = fine - low_pass(fine, filter_size)
+    c_real = critic_forward(cp, cspec, real_high)
+    c_fake = critic_forward(cp, cspec, fake_high)
+    gp, norms, _g = gradient_penalty(cp, cspec, real_high, fake_high, alpha, hp)
+    loss = c_fake.mean() - c_real.mean() + hp.gp_lambda * gp
+    grads = torch.autograd.grad(loss, list(cp.values()), allow_unused=True)
+    gd = OrderedDict((k, torch.zeros_like(p) if gr is None else gr.detach()) for (k, p), gr in zip(cp.items(), grads))
+    return {"loss": loss.detach(), "gp": gp.detach(), "c_real_mean": c_real.mean().detach(),
+            "c_fake_mean": c_fake.mean().detach(), "norms": norms.detach(), "grads": gd}
+
+
+def generator_loss_and_grads_fs(g_sd, gspec: GeneratorSpec, c_sd, cspec: CriticSpec, coarse, fine, hp: Hyper,
+                                filter_size: int = 5, dtype=None):
+    """wasserstein_fs.py:71-91: adversarial term on the high-pass fake, L1 between the low-pass parts."""
+    gp_ = as_leaf_params(g_sd, dtype)
+    cp = {k: (v.to(dtype) if dtype is not None else v) for k, v in c_sd.items()}
+    if dtype is not None:
+        coarse, fine = coarse.to(dtype), fine.to(dtype)
+    fake = generator_forward(gp_, gspec, coarse)
+    fake_low = low_pass(fake, filter_size)
+    real_low = low_pass(fine, filter_size)
+    c_fake = critic_forward(cp, cspec, fake - fake_low)
+    l1 = (fake_low - real_low).abs().mean()
+    loss = -c_fake.mean() * hp.gamma + hp.content_lambda * l1
+    grads = torch.autograd.grad(loss, list(gp_.values()))
+    return {"loss": loss.detach(), "l1": l1.detach(), "c_fake_mean": c_fake.mean().detach(),
+            "grads": OrderedDict((k, g.detach()) for k, g in zip(gp_.keys(), grads))}

@@ -108,6 +108,10 @@ def generator_step_with_masks(G, C, gspec, cspec, coarse, fine):
                                      _lib.stream_ptr()))
     torch.cuda.synchronize()
     masks = {"gen": generator_masks(g, gspec, b, hc), "fake": critic_masks(c, cspec, 0, b) + [_fc_mask(c, 0, b)]}
+    with torch.no_grad():
+        fake = G(cd).cpu()  # deterministic forward kernels: the fake the iteration differentiated
+    # the L1 term's kink: sign(fake - fine) as the CUDA path saw it (losses.py:51-53 via wasserstein.py:78)
+    masks["l1_sign"] = torch.sign(fake - fine)
     return sg.cpu(), pu.flat_to_dict(G, gg), masks
 
 
@@ -162,11 +166,14 @@ def generator_parity(G, C, gspec, cspec, g_sd, c_sd, coarse, fine, hp=None, emul
     sg, gg, masks = generator_step_with_masks(G, C, gspec, cspec, coarse, fine)
     rec = {k: onet.MaskTape() for k in ("gen", "fake")}
     free = otr.generator_loss_and_grads(g_sd, gspec, c_sd, cspec, coarse, fine, hp, tapes=rec)
-    pin = otr.generator_loss_and_grads(g_sd, gspec, c_sd, cspec, coarse, fine, hp,
-                                       tapes={k: onet.MaskTape(v) for k, v in masks.items()})
+    l1_sign = masks.pop("l1_sign")
+    pin_tapes = {k: onet.MaskTape(v) for k, v in masks.items()}
+    pin_tapes["l1_sign"] = l1_sign
+    pin = otr.generator_loss_and_grads(g_sd, gspec, c_sd, cspec, coarse, fine, hp, tapes=pin_tapes)
     out = {"scalars": sg, "free": free, "pinned": pin,
            "err_free": tensor_errors(gg, free["grads"]), "err_pinned": tensor_errors(gg, pin["grads"]),
-           "flips": {k: flip_stats(masks[k], rec[k]) for k in masks}, "grads": gg}
+           "flips": {k: flip_stats(masks[k], rec[k]) for k in masks}, "grads": gg,
+           "l1_sign_flips": float((l1_sign != torch.sign(free["fake"] - fine)).float().mean())}
     if emulate:
         emu = otr.generator_loss_and_grads(g_sd, gspec, c_sd, cspec, coarse, fine, hp,
                                            tapes={k: onet.MaskTape(bf16=True) for k in ("gen", "fake")})

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/downgan_b200.h but not exported"
     assert set(syms) == set(_lib.EXPORTS), set(syms) ^ set(_lib.EXPORTS)
-    assert lib.dg_abi_version() == 1
+    assert lib.dg_abi_version() == 2
 
 
 @pytest.mark.parametrize("filters,channels,rrdb", [(16, 2, 16), (16, 7, 16), (32, 7, 23), (8, 3, 2)])

@@ -1,13 +1,7 @@
-"""Opt-in parity test of the tcgen05 classifier kernels (csrc/dg_umma_fc.cu, dg_set_tuning key 14).  They were written at the
-end of round 1 with no GPU time left, so the shipped default is the CUDA-core path and this test only runs with
-DG_TEST_FC_UMMA=1 (a descriptor mistake traps the context, which would take every later test in the process down with it):
-
-    DG_TEST_FC_UMMA=1 python -m pytest tests/test_gpu_fc_umma.py -m gpu -x -q
-
-It runs the fused critic iteration and the generator iteration with key 14 off and on at cfg-1 size and compares scalars
-and gradients (bf16 operand rounding of dz / classifier.0.weight is the only intended difference)."""
-import os
-
+"""Parity test of the tcgen05 classifier kernels (csrc/dg_umma_fc.cu, dg_set_tuning key 14, on by default since round 2).
+It runs the fused critic iteration and the generator iteration with key 14 off (CUDA-core classifier) and on at cfg-1 /
+cfg-2 / ragged batch sizes and compares scalars and gradients (bf16 operand rounding of dz / classifier.0.weight is the only
+intended difference); the absolute check against the oracle is tests/test_gpu_masks.py, which runs with the default (on)."""
 import pytest
 import torch
 
@@ -18,8 +12,7 @@ from oracle import networks as onet
 import parity_util as pu
 from test_gpu_parity import _run_steps
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DG_TEST_FC_UMMA") != "1", reason="tcgen05 classifier kernels are opt-in (not yet validated)")]
+pytestmark = pytest.mark.gpu
 
 
 def _flat(d):

@@ -262,11 +262,16 @@ def test_loss_curves_200_steps(precision):
     # learnt ||grad|| ~ 1 (the critic loss falls from ~100 to O(1) and changes sign), so the
     # reference's own fp32 run drifts from fp64 late in the curve; that measured drift is the
     # yardstick:  (a) the first 20 steps must agree pointwise to the mode's tolerance (1e-3 fp32, 2e-2 bf16),
-    # (b) over all 200 steps the deviation must stay within 3x the fp32-oracle-vs-fp64-oracle deviation plus
-    # that tolerance times the curve's range.
+    # (b) over all 200 steps the deviation must stay within 3x the yardstick-oracle-vs-fp64-oracle deviation plus
+    # that tolerance times the curve's range.  Yardstick oracle: fp32 mode - the reference's own fp32 run; bf16 mode - the
+    # reference's code with every conv operand rounded to bf16 (OracleTrainer(emulate_bf16=True)): the steep fall of the critic
+    # loss around step 45 moves by a step or two under ANY bf16 storage rounding (measured on the CPU: emulated-bf16 oracle vs
+    # fp64 max deviation 15.8 of a range of 100, fp32 oracle 0.69), so that is the scale a bf16 run can be held to.
+    # (c) bf16 only: the step at which the critic loss first falls below half its initial value agrees within 2 steps, and
+    # the mean of the last 100 steps (the settled regime) within 2e-2 of the curve's range.
     tol = TOL_OUT[precision]
     ref = otr.OracleTrainer(g_sd, TINY_G, c_sd, TINY_C, dtype=torch.float64)
-    ref32 = otr.OracleTrainer(g_sd, TINY_G, c_sd, TINY_C)
+    ref32 = otr.OracleTrainer(g_sd, TINY_G, c_sd, TINY_C, emulate_bf16=(precision == "bf16"))
     closs, gloss, rc, rg, rc32, rg32 = [], [], [], [], [], []
     for step in range(200):
         coarse, fine, alpha = synth_batch(4, 3, 8, seed=1000 + step % 7, aseed=step)
@@ -297,5 +302,12 @@ def test_loss_curves_200_steps(precision):
         print(f"loss curve [{precision}] {name}: max|cuda-fp64| {dev:.4f}  max|fp32 oracle-fp64| {drift:.4f}  range {span:.2f}  "
               f"(dev/range {dev / span:.2e})")
         assert dev <= 3 * drift + tol * span, (dev, drift, span)
+    if precision == "bf16":
+        half = 0.5 * float(rc[0])
+        first = lambda c: int((c < half).nonzero()[0]) if bool((c < half).any()) else len(c)
+        print(f"loss curve [bf16] critic: falls below {half:.1f} at step {first(closs)} (fp64 oracle {first(rc)}, emulated-bf16 oracle "
+              f"{first(rc32)}); mean of the last 100 steps {float(closs[100:].mean()):.3f} (fp64 {float(rc[100:].mean()):.3f})")
+        assert abs(first(closs) - first(rc)) <= 2
+        assert abs(float(closs[100:].mean()) - float(rc[100:].mean())) <= 2e-2 * float(rc.max() - rc.min())
     tr.sync_optimizer_state()
     assert len(copt.state_dict()["state"]) == 13

@@ -147,3 +147,34 @@ def test_mask_tape_record_replay(tiny):
     num = sum(float((ge["grads"][k] - ga["grads"][k]).norm()) ** 2 for k in ga["grads"])
     den = sum(float(ga["grads"][k].norm()) ** 2 for k in ga["grads"])
     assert 0 < (num / den) ** 0.5 < 0.3
+
+
+def test_adjacent_rows_match_reference_values(tiny):
+    """tiny_extra.json holds what the REFERENCE's own code gave (oracle/make_golden.py step 5): GAN/losses.py metrics as
+    gen_batch_and_log_metrics calls them, and the frequency-separation statements of GAN/wasserstein_fs.py on the reference modules."""
+    t, gspec, cspec, g_sd, c_sd = tiny
+    with open(os.path.join(GOLD, "tiny_extra.json")) as f:
+        x = json.load(f)
+    hp = otr.Hyper()
+    m = otr.batch_metrics(g_sd, gspec, c_sd, cspec, t["coarse"], t["fine"])
+    for k in ("MAE", "MSE", "Wass"):
+        assert abs(float(m[k]) - x["metrics"][k]) <= 1e-6 * max(abs(x["metrics"][k]), 1e-3), k
+    oc = otr.critic_loss_and_grads_fs(g_sd, gspec, c_sd, cspec, t["coarse"], t["fine"], t["alpha"], hp)
+    og = otr.generator_loss_and_grads_fs(g_sd, gspec, c_sd, cspec, t["coarse"], t["fine"], hp)
+    assert abs(float(oc["loss"]) - x["fs_critic_loss"]) <= 1e-5 * abs(x["fs_critic_loss"])
+    assert abs(float(og["loss"]) - x["fs_gen_loss"]) <= 1e-5 * abs(x["fs_gen_loss"])
+    for k, n in x["fs_dC_norm"].items():
+        assert abs(float(oc["grads"][k].norm()) - n) <= 1e-4 * n + 1e-9, k
+    # the low-pass filter restated = the module pair of config/hyperparams.py:31-35
+    xin = torch.randn(2, 2, 9, 11, generator=torch.Generator().manual_seed(0))
+    ref = torch.nn.AvgPool2d(5, stride=1, padding=0)(torch.nn.ReplicationPad2d(2)(xin))
+    assert torch.equal(otr.low_pass(xin, 5), ref)
+
+
+def test_reference_checkpoints_load_on_cpu():
+    """The torch.save'd reference state_dicts have exactly the keys / shapes the product modules register (strict load)."""
+    from downgan_b200.networks import Critic, Generator
+    g = Generator(8, 64, 3, 2, num_res_blocks=2)
+    c = Critic(8, 64, 2)
+    g.load_state_dict(torch.load(os.path.join(GOLD, "ref_tiny_generator_state_dict.pth"), weights_only=True), strict=True)
+    c.load_state_dict(torch.load(os.path.join(GOLD, "ref_tiny_critic_state_dict.pth"), weights_only=True), strict=True)

@@ -70,7 +70,8 @@ def main():
         if scale != 1.0:
             rg = mu.generator_parity(G, C, G_SPEC, C_SPEC, g_sd, c_sd, coarse, fine)
             sg = rg["scalars"]
-            print(f"\ngenerator loss {float(sg[0]):.6f} (oracle {float(rg['free']['loss']):.6f})")
+            print(f"\ngenerator loss {float(sg[0]):.6f} (oracle {float(rg['free']['loss']):.6f}); sign(fake - fine) of the L1 term differs "
+                  f"from the oracle's on {rg['l1_sign_flips']:.3e} of the elements (pinned as well in the \"masks pinned\" column)")
             table("generator iteration (`wasserstein.py:58-80`)", rg, top=12)
         del G, C
 
