@@ -2,10 +2,16 @@
 the CPU oracle on identical seeded inputs.
 
 Tolerances (BASELINE.json north_star): fp32 mode <= 1e-3 relative; bf16 mode
-<= 2e-2 relative for generator output, critic scores and GP value.  Parameter
-gradients in bf16 mode are dominated by LeakyReLU mask flips (BASELINE.md §5:
-the emulated bf16 floor is 7.5e-2 / 1.1e-1 per tensor) and are checked against
-that measured floor, reported separately from the fp32 mode that meets 1e-3.
+<= 2e-2 relative for generator output, critic scores and GP value.  bf16
+parameter gradients are asserted at <= 2e-2 PER TENSOR in tests/test_gpu_masks.py,
+with the LeakyReLU masks (and the L1 term's signs) pinned to the ones the CUDA
+path took.  The FREE-RUNNING bf16 gradients checked in this file carry the
+mask-flip floor of bf16 storage itself: profiles/parity_r02.md measures it on
+the B200 next to the emulated-bf16 ORACLE's own error against the fp32 oracle
+(critic flat 2.0e-2 .. 4.7e-2 vs 1.9e-2 .. 4.2e-2 emulated; worst tensor
+features.0.bias 2.4e-1 vs 1.6e-1 emulated; generator flat 0.8e-2 .. 1.3e-2 vs
+1.1e-2), so the bounds below (flat 1e-1, per tensor 2.5e-1) are ~2x that
+measured floor, not a kernel-accuracy claim.
 """
 import os
 
