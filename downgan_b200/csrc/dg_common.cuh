@@ -119,6 +119,7 @@ struct ConvOp {
   // tcgen05 path extras (bf16 mode)
   const void* w_umma = nullptr;  // packed bf16 weights for the tcgen05 kernel (null -> direct kernel)
   int narrow_ok = 0;             // Co < 16: w_umma holds a zero-padded 16-column image (set only where one is packed)
+  const void* w_ig = nullptr;    // K-major bf16 weight image [tap][CoP][Ci] for the streaming implicit-GEMM kernel (null: not packed)
 };
 
 struct WgradOp {
@@ -197,6 +198,9 @@ bool critic_head_supported(int B);
 int critic_head(float* a9, const float* b1, const float* w2, const float* b2, float* scores, float* seed, float* dz9,
                 float* scalars, int B, int K, float slope, cudaStream_t st);
 int gp_norms(const float* g, int B, size_t per_sample, float* sumsq, cudaStream_t st);
+// sum of squares per sample + norms / penalty value / dGP/dg coefficients in ONE launch (last block finishes, fixed-order combine)
+int gp_norms_finish(const float* g, int B, size_t per_sample, float gp_lambda, float* sumsq, float* norms, float* coef, float* scalars,
+                    int write_loss, cudaStream_t st);
 int gp_finish(const float* sumsq, int B, float gp_lambda, float* norms, float* coef, float* scalars, int write_loss, cudaStream_t st);
 int gp_scale(const float* g, const float* coef, float* u, int B, size_t per_sample, cudaStream_t st);
 int l1_loss(const float* a, const float* b, long long n, float scale, float* loss_out, float* d_a,
@@ -229,6 +233,11 @@ struct UmmaPackDesc { long long off; int Ci, CoP; };
 bool wgrad_umma_supported(const WgradOp& op);
 int wgrad_umma(const WgradOp& op, cudaStream_t st);
 int pack_umma(const float* packed, void* dst_bf16, const UmmaPackDesc* table_dev, int n, int max_elems, cudaStream_t st);
+// streaming implicit-GEMM conv (dg_umma_conv_ig.cu): both operands by TMA per (tap, channel block); weight image [tap][CoP][Ci]
+int pack_ig(const float* packed, void* dst_bf16, const UmmaPackDesc* table_dev, int n, int max_elems, cudaStream_t st);
+bool conv_ig_supported(const ConvOp& op);
+bool conv_ig_preferred(const ConvOp& op);
+int conv_ig(const ConvOp& op, cudaStream_t st);
 
 }  // namespace dg
 

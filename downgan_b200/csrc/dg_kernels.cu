@@ -1029,58 +1029,95 @@ int critic_means(const float* scores, int B, float* scalars, cudaStream_t st) {
 }
 
 // sumsq[b] += sum over the sample of g^2 (vectorised, one atomic per block)
-__global__ void gp_norms_kernel(const float* __restrict__ g, size_t per_sample, float* __restrict__ sumsq) {
+// per-sample sum of squares of the input gradient (wasserstein.py:110-114), then - in the LAST block to finish - the norms, the
+// penalty value and dGP/dg coefficients  lam^2 * (2/B) * (n-1)/n  (wasserstein.py:114-117,40).  Block partials go to
+// part[b][blockIdx.x] and are combined in a fixed order (deterministic, no float atomics, no memset launch); one launch instead
+// of memset + reduction + finish.
+__device__ unsigned int g_gp_done = 0;  // completion counter (one gradient-penalty pass at a time per process, see header)
+constexpr int GPN_MAXBX = 32;
+__global__ void __launch_bounds__(256) gp_norms_finish_kernel(const float* __restrict__ g, size_t per_sample, float* __restrict__ part,
+                                                              int B, float lam, float* __restrict__ sumsq, float* __restrict__ norms,
+                                                              float* __restrict__ coef, float* __restrict__ scalars, int write_loss) {
   __shared__ float sh[32];
+  __shared__ bool last;
   const int b = blockIdx.y;
   const float4* gp = reinterpret_cast<const float4*>(g + (size_t)b * per_sample);
   const size_t n4 = per_sample >> 2;
   float s = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    const float4 v = gp[i];
+    const float4 v = __ldg(gp + i);
     s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0)
     for (size_t i = n4 << 2; i < per_sample; ++i) { const float v = g[(size_t)b * per_sample + i]; s += v * v; }
   s = block_sum(s, sh);
-  if (threadIdx.x == 0) atomicAdd(&sumsq[b], s);
-}
-int gp_norms(const float* g, int B, size_t per_sample, float* sumsq, cudaStream_t st) {
-  DG_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float) * B, st));
-  Prof prof(PC_GP_NORMS, 0.0, (double)per_sample * B * 4.0, st);
-  unsigned bx = (unsigned)((per_sample / 4 + 1023) / 1024);
-  if (bx < 1) bx = 1;
-  if (bx > 32) bx = 32;
-  gp_norms_kernel<<<dim3(bx, B), 256, 0, st>>>(g, per_sample, sumsq);
-  DG_LAUNCH_CHECK();
-  return 0;
-}
-// norms, GP value, and dGP/dg coefficient  lam^2 * (2/B) * (n-1)/n   (wasserstein.py:110-117,40)
-__global__ void gp_finish_kernel(const float* __restrict__ sumsq, int B, float lam, float* __restrict__ norms,
-                                 float* __restrict__ coef, float* __restrict__ scalars, int write_loss) {
-  __shared__ float sh[32];
+  if (threadIdx.x == 0) {
+    part[(size_t)b * GPN_MAXBX + blockIdx.x] = s;
+    __threadfence();
+    last = (atomicAdd(&g_gp_done, 1u) == gridDim.x * gridDim.y - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
   float acc = 0.f;
   for (int i = threadIdx.x; i < B; i += blockDim.x) {
-    const float n = sqrtf(sumsq[i] + 1e-12f);
+    float t = 0.f;
+    for (unsigned k = 0; k < gridDim.x; ++k) t += __ldcg(part + (size_t)i * GPN_MAXBX + k);
+    sumsq[i] = t;
+    const float n = sqrtf(t + 1e-12f);
     if (norms) norms[i] = n;
     if (coef) coef[i] = lam * lam * (2.f / B) * (n - 1.f) / n;
     acc += (n - 1.f) * (n - 1.f);
   }
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0) {
-    const float gp = lam * acc / B;
-    scalars[3] = gp;
-    scalars[4] = lam * gp;
-    if (write_loss) scalars[0] = scalars[2] - scalars[1] + lam * gp;
+    const float gpv = lam * acc / B;
+    scalars[3] = gpv;
+    scalars[4] = lam * gpv;
+    if (write_loss) scalars[0] = scalars[2] - scalars[1] + lam * gpv;
+    g_gp_done = 0;
   }
 }
-int gp_finish(const float* sumsq, int B, float lam, float* norms, float* coef, float* scalars, int write_loss,
-              cudaStream_t st) {
-  gp_finish_kernel<<<1, 256, 0, st>>>(sumsq, B, lam, norms, coef, scalars, write_loss);
+static float* g_gp_part = nullptr;
+static int g_gp_part_B = 0;
+int gp_norms_finish(const float* g, int B, size_t per_sample, float gp_lambda, float* sumsq, float* norms, float* coef, float* scalars,
+                    int write_loss, cudaStream_t st) {
+  if (B > g_gp_part_B) {  // scratch for the block partials, grown on first use / larger batches (not on the steady-state path)
+    if (g_gp_part) cudaFree(g_gp_part);
+    DG_CUDA(cudaMalloc(&g_gp_part, sizeof(float) * (size_t)B * GPN_MAXBX));
+    g_gp_part_B = B;
+  }
+  Prof prof(PC_GP_NORMS, 0.0, (double)per_sample * B * 4.0, st);
+  unsigned bx = (unsigned)((per_sample / 4 + 1023) / 1024);
+  if (bx < 1) bx = 1;
+  if (bx > GPN_MAXBX) bx = GPN_MAXBX;
+  gp_norms_finish_kernel<<<dim3(bx, B), 256, 0, st>>>(g, per_sample, g_gp_part, B, gp_lambda, sumsq, norms, coef, scalars, write_loss);
   DG_LAUNCH_CHECK();
   return 0;
 }
+int gp_norms(const float* g, int B, size_t per_sample, float* sumsq, cudaStream_t st) {
+  (void)g; (void)B; (void)per_sample; (void)sumsq; (void)st;
+  set_error("gp_norms: superseded by gp_norms_finish");
+  return DG_ERR_STATE;
+}
+int gp_finish(const float* sumsq, int B, float lam, float* norms, float* coef, float* scalars, int write_loss, cudaStream_t st) {
+  (void)sumsq; (void)B; (void)lam; (void)norms; (void)coef; (void)scalars; (void)write_loss; (void)st;
+  set_error("gp_finish: superseded by gp_norms_finish");
+  return DG_ERR_STATE;
+}
 __global__ void gp_scale_kernel(const float* __restrict__ g, const float* __restrict__ coef, float* __restrict__ u,
                                 size_t per_sample, size_t total) {
+  if ((per_sample & 3) == 0) {  // float4 path: a vector never straddles two samples
+    const size_t n4 = total >> 2, ps4 = per_sample >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* u4 = reinterpret_cast<float4*>(u);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+      const float c = __ldg(coef + i / ps4);
+      const float4 v = __ldg(g4 + i);
+      u4[i] = make_float4(c * v.x, c * v.y, c * v.z, c * v.w);
+    }
+    return;
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
     u[i] = coef[i / per_sample] * g[i];
 }
@@ -1091,19 +1128,30 @@ int gp_scale(const float* g, const float* coef, float* u, int B, size_t per_samp
 }
 
 // mean |a-b| (+ seed scale*sign(a-b)/n [+ d_add])   (losses.py:51-53)
-__global__ void l1_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float scale,
-                          float* __restrict__ loss, float* __restrict__ d_a, const float* __restrict__ d_add) {
+__global__ void __launch_bounds__(256) l1_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float scale,
+                                                 float* __restrict__ loss, float* __restrict__ d_a, const float* __restrict__ d_add,
+                                                 int vec) {
   __shared__ float sh[32];
   float s = 0.f;
   const float k = scale / (float)n;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float d = a[i] - b[i];
+  auto one = [&](float x, float y, float add) {
+    const float d = x - y;
     s += fabsf(d);
-    if (d_a) {
-      float gsign = d > 0.f ? k : (d < 0.f ? -k : 0.f);
-      if (d_add) gsign += d_add[i];
-      d_a[i] = gsign;
-    }
+    return (d > 0.f ? k : (d < 0.f ? -k : 0.f)) + add;
+  };
+  const long long n4 = vec ? (n >> 2) : 0;
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 x = __ldg(a4 + i), y = __ldg(b4 + i);
+    float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d_a && d_add) ad = __ldg(reinterpret_cast<const float4*>(d_add) + i);
+    const float4 o = make_float4(one(x.x, y.x, ad.x), one(x.y, y.y, ad.y), one(x.z, y.z, ad.z), one(x.w, y.w, ad.w));
+    if (d_a) reinterpret_cast<float4*>(d_a)[i] = o;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float o = one(a[i], b[i], (d_a && d_add) ? d_add[i] : 0.f);
+    if (d_a) d_a[i] = o;
   }
   s = block_sum(s, sh);
   if (threadIdx.x == 0) atomicAdd(loss, s / (float)n);
@@ -1112,7 +1160,8 @@ int l1_loss(const float* a, const float* b, long long n, float scale, float* los
             cudaStream_t st) {
   DG_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
   Prof prof(PC_L1, 0.0, (double)n * 4.0 * (2.0 + (d_a ? 1.0 : 0.0) + (d_add ? 1.0 : 0.0)), st);
-  l1_kernel<<<ew_grid((size_t)n), 256, 0, st>>>(a, b, n, scale, loss_out, d_a, d_add);
+  const int vec = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)d_a | (uintptr_t)d_add) & 15) == 0;
+  l1_kernel<<<ew_grid((size_t)(vec ? (n + 3) / 4 : n)), 256, 0, st>>>(a, b, n, scale, loss_out, d_a, d_add, vec);
   DG_LAUNCH_CHECK();
   return 0;
 }
@@ -1140,25 +1189,38 @@ int gen_scalars(const float* scores, int B, const float* l1, float gamma, float 
 // ---------------------------------------------------------------------------
 // fused Adam over a flat buffer (torch.optim.Adam semantics, no amsgrad/decay)
 // ---------------------------------------------------------------------------
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, long long n, float b1, float b2, float eps, float step_size,
-                            float inv_sqrt_bc2, float gscale) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gi = g[i] * gscale;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, float b1, float b2, float eps, float step_size,
+                                                   float inv_sqrt_bc2, float gscale, int vec) {
+  // 16-byte loads / stores over the flat buffer (vec: all four pointers 16-byte aligned), scalar grid-stride tail
+  const long long n4 = vec ? (n >> 2) : 0;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  auto upd = [&](float& pi, float gi, float& mi, float& vi) {
+    gi *= gscale;
+    mi = b1 * mi + (1.f - b1) * gi;
+    vi = b2 * vi + (1.f - b2) * gi * gi;
+    pi -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  };
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = p4[i], mm = m4[i], vv = v4[i];
+    const float4 gg = __ldg(g4 + i);
+    upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y); upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
   }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    upd(p[i], g[i], m[i], v[i]);
 }
 int adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int step,
          float gscale, cudaStream_t st) {
   Prof prof(PC_ADAM, 0.0, (double)n * 28.0, st);
   const double bc1 = 1.0 - pow((double)b1, (double)step);
   const double bc2 = 1.0 - pow((double)b2, (double)step);
-  adam_kernel<<<ew_grid((size_t)n), 256, 0, st>>>(p, g, m, v, n, b1, b2, eps, (float)(lr / bc1),
-                                                   (float)(1.0 / sqrt(bc2)), gscale);
+  const int vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
+  adam_kernel<<<ew_grid((size_t)(vec ? (n + 3) / 4 : n)), 256, 0, st>>>(p, g, m, v, n, b1, b2, eps, (float)(lr / bc1),
+                                                                       (float)(1.0 / sqrt(bc2)), gscale, vec);
   DG_LAUNCH_CHECK();
   return 0;
 }
@@ -1208,7 +1270,7 @@ CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank,
   return fn(map, dt, rank, addr, dims, strides, box, estr, il, sw, l2, oob);
 }
 }  // namespace dg
-namespace dg { int g_tune[DG_TUNE_KEYS] = {1, 1, 1, 0, 1, 0, 1, 1, 1, 1, 4, 1, 1, 3, 1, 0}; }  // see include/downgan_b200.h: dg_set_tuning
+namespace dg { int g_tune[DG_TUNE_KEYS] = {1, 1, 1, 0, 1, 0, 1, 1, 1, 1, 4, 1, 1, 3, 1, 0, 1, 1}; }  // see include/downgan_b200.h: dg_set_tuning
 extern "C" int dg_set_tuning(int key, int value) {
   if (key < 0 || key >= DG_TUNE_KEYS) { dg::set_error("dg_set_tuning: unknown key %d", key); return DG_ERR_INVALID; }
   const int prev = dg::g_tune[key];

@@ -90,8 +90,40 @@ int dev_alloc(std::vector<void*>& pool, void** out, size_t bytes) {
   return 0;
 }
 
+// DG_LOG_FALLBACK=1: one stderr line per distinct shape that leaves the tcgen05 kernels for the CUDA-core ones (diagnostic)
+void log_fallback(const char* what, int ci, int co, int h, int w, int b, int stride, int bf) {
+  static const bool on = getenv("DG_LOG_FALLBACK") != nullptr;
+  if (!on) return;
+  static std::vector<long long> seen;
+  const long long key = ((((long long)ci * 1024 + co) * 4096 + h) * 4 + stride) * 2 + (what[0] == 'w');
+  if (std::find(seen.begin(), seen.end(), key) != seen.end()) return;
+  seen.push_back(key);
+  fprintf(stderr, "[dg fallback] %s on CUDA cores: Ci %d Co %d %dx%d B %d stride %d %s\n", what, ci, co, h, w, b, stride, bf ? "bf16" : "fp32");
+}
+
 int run_wgrad(const WgradOp& w0, cudaStream_t st) {
   WgradOp w = w0;
+  // Wide or non-power-of-two channel counts (the dense-block layers of F = 32 / 64 generators: Ci = 96, 160, 192, 256, 320):
+  // the TMA-fed kernel takes power-of-two channel blocks <= 128, each writing its own rows of dW (as the batched launch of
+  // the F = 16 trunk does); the bias gradient rides on the first block.
+  if (g_tune[2] && w.x.bf && w.dy.bf && w.Ci % 16 == 0 && w.dw_ci_total == 0 && (w.Ci > 128 || (w.Ci & (w.Ci - 1)))) {
+    std::vector<WgradOp> blocks;
+    bool ok = true;
+    for (int c0 = 0; c0 < w.Ci && ok;) {
+      int cb = 128;
+      while (cb > w.Ci - c0) cb >>= 1;
+      WgradOp o = w;
+      o.x.coff = w.x.coff + c0; o.Ci = cb; o.dw_ci_total = w.Ci; o.dw_ci_off = c0;
+      if (c0 > 0) o.dbias = nullptr;
+      ok = wgrad_ws_supported(o);
+      blocks.push_back(o);
+      c0 += cb;
+    }
+    if (ok) {
+      for (const WgradOp& o : blocks) DG_TRY(wgrad_ws(o, st));
+      return 0;
+    }
+  }
   // bias gradient over a leading part of the batch: only the first-layer tcgen05 kernel folds it in; elsewhere it is
   // a column sum over those samples
   const bool ws_path = g_tune[2] && wgrad_ws_supported(w);
@@ -103,6 +135,7 @@ int run_wgrad(const WgradOp& w0, cudaStream_t st) {
   if (wgrad_im2col_supported(w)) return wgrad_im2col(w, st);
   if (wgrad_skinny_supported(w)) return wgrad_skinny(w, st);
   if (wgrad_umma_supported(w)) return wgrad_umma(w, st);
+  log_fallback("wgrad", w.Ci, w.Co, w.Hin, w.Win, w.B, w.stride, w.x.bf);
   return wgrad_direct(w, st);
 }
 
@@ -112,8 +145,10 @@ int run_conv(const ConvOp& op, cudaStream_t st) {
   if (op.Co < 16 && op.narrow_ok && ws && g_tune[0] && g_tune[7] && op.w_umma && umma_ws_supported(op))
     return conv_umma_ws(op, st);  // narrow output on tensor cores
   if (conv_skinny_supported(op)) return conv_skinny(op, st);
+  if (op.w_ig && conv_ig_preferred(op)) return conv_ig(op, st);  // late critic layers / wide dense layers: streaming implicit GEMM
   if (ws && g_tune[0] && op.w_umma && umma_ws_supported(op)) return conv_umma_ws(op, st);
   if (op.w_umma && umma_supported(op)) return conv_umma(op, st);
+  log_fallback("conv", op.Ci, op.Co, op.Hout, op.Wout, op.B, op.stride, op.x.bf);
   return conv_direct(op, st);
 }
 
@@ -137,6 +172,7 @@ struct dg_generator {
   PackDesc *tab_fwd = nullptr, *tab_dgrad = nullptr;
   int n_fwd = 0, n_dgrad = 0, max_fwd = 0, max_dgrad = 0;
   bf16 *pk_u = nullptr, *pkd_u = nullptr;  // tcgen05 B-operand images (bf16 mode)
+  bf16 *pk_ig = nullptr, *pkd_ig = nullptr;  // K-major images [tap][CoP][Ci] for the streaming implicit-GEMM kernel
   bf16* pk_trunk = nullptr;                // slice-major images of the dense convs for the fused trunk kernel
   bf16* pkd_trunk = nullptr;               // same for the dense data-gradient matrices (fused trunk backward)
   void** d_ptrs_dev = nullptr;             // device copy of Dall[]
@@ -316,6 +352,8 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
   GA(g->pkd, sizeof(float) * std::max<long long>(pkd, 1));
   GA(g->pk_u, sizeof(bf16) * (pk + 64));
   GA(g->pkd_u, sizeof(bf16) * (std::max<long long>(pkd, 1) + 64));
+  GA(g->pk_ig, sizeof(bf16) * (pk + 64));
+  GA(g->pkd_ig, sizeof(bf16) * (std::max<long long>(pkd, 1) + 64));
   GA(g->pk_trunk, sizeof(bf16) * ((size_t)std::max(1, g->R * 3) * 9 * F * F * 15 + 64));
   GA(g->pkd_trunk, sizeof(bf16) * ((size_t)std::max(1, g->R * 3) * 9 * F * F * 15 + 64));
   if ((s = upload_table(g->pool, tf, &g->tab_fwd)) != 0) { dg_generator_destroy(g); return s; }
@@ -385,6 +423,10 @@ extern "C" int dg_generator_pack(dg_generator* g, const float* params, void* str
   DG_TRY(g->side.join(st));  // a deferred look-ahead chain (dg_generator_lookahead_first) may still be running
   DG_TRY(pack_weights2(params, g->pk, g->pk_u, g->tab_fwd, g->n_fwd, g->max_fwd, g->pkd, g->pkd_u, g->tab_dgrad, g->n_dgrad,
                        g->max_dgrad, st));
+  if (g->bf && g_tune[16]) {
+    DG_TRY(pack_ig(g->pk, g->pk_ig, g->utab_fwd, g->n_ufwd, g->max_ufwd, st));
+    DG_TRY(pack_ig(g->pkd, g->pkd_ig, g->utab_dgrad, g->n_udgrad, g->max_udgrad, st));
+  }
   if (trunk_fused_supported(g->F, g->Hc, g->R, g->bf))
   {
     DG_TRY(pack_trunk_slices(g->pk + g->layers[g->idx_db(0, 0, 1)].pk_off, g->pk_trunk, g->R * 3, 0, st));
@@ -407,7 +449,7 @@ static int gen_trunk_forward(dg_generator* g, int s0, int B, int save_count, cud
     op.x = x; op.Hin = H; op.Win = H; op.Ci = l.Ci;
     op.y = y; op.Hout = H; op.Wout = H; op.Co = l.Co;
     op.B = B; op.w = g->pk + l.pk_off; op.bias = g->pk + l.pkb_off;
-    if (g->bf) op.w_umma = g->pk_u + l.pk_off;
+    if (g->bf) { op.w_umma = g->pk_u + l.pk_off; op.w_ig = g->pk_ig + l.pk_off; }
     return op;
   };
   const bool fused_trunk = trunk_fused_supported(F, Hc, g->R, g->bf);
@@ -456,7 +498,7 @@ static int gen_forward_range(dg_generator* g, int s0, int B, int save_count, cud
     op.x = x; op.Hin = H; op.Win = H; op.Ci = l.Ci;
     op.y = y; op.Hout = H; op.Wout = H; op.Co = l.Co;
     op.B = B; op.w = g->pk + l.pk_off; op.bias = g->pk + l.pkb_off;
-    if (g->bf) op.w_umma = g->pk_u + l.pk_off;
+    if (g->bf) { op.w_umma = g->pk_u + l.pk_off; op.w_ig = g->pk_ig + l.pk_off; }
     return op;
   };
   void* first = g->R > 0 ? g->db[0] : g->trunk_out;
@@ -582,7 +624,7 @@ static int gen_trunk_backward(dg_generator* g, int B, bool& side_on, cudaStream_
         op.x = g->act(g->D, 5 * F, 0); op.Hin = Hc; op.Win = Hc; op.Ci = (5 - k) * F;
         op.y = g->act(g->D, 5 * F, (5 - k) * F); op.Hout = Hc; op.Wout = Hc; op.Co = F;
         op.B = B; op.w = g->pkd + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + k];
-        if (g->bf) op.w_umma = g->pkd_u + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + k];
+        if (g->bf) { op.w_umma = g->pkd_u + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + k]; op.w_ig = g->pkd_ig + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + k]; }
         op.act = ACT_MASK; op.slope = G_SLOPE; op.mask = g->act(buf, 5 * F, k * F);
         DG_TRY(run_conv(op, st));
       }
@@ -606,7 +648,7 @@ static int gen_trunk_backward(dg_generator* g, int B, bool& side_on, cudaStream_
       op.x = g->act(g->D, 5 * F, 0); op.Hin = Hc; op.Win = Hc; op.Ci = 5 * F;
       op.y = g->act(gout, F); op.Hout = Hc; op.Wout = Hc; op.Co = F;
       op.B = B; op.w = g->pkd + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + 0];
-      if (g->bf) op.w_umma = g->pkd_u + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + 0];
+      if (g->bf) { op.w_umma = g->pkd_u + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + 0]; op.w_ig = g->pkd_ig + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + 0]; }
       op.r1 = g->act(gin, F); op.s1 = s_in;
       if (d == 0) { op.r2 = g->act(g->gR, F); op.s2 = 1.f; }
       DG_TRY(run_conv(op, st));
@@ -668,7 +710,7 @@ static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_co
     op.x = dy; op.Hin = H; op.Win = H; op.Ci = l.Co;
     op.y = dx; op.Hout = H; op.Wout = H; op.Co = l.Ci;
     op.B = B; op.w = g->pkd + l.pkd_off;
-    if (g->bf) op.w_umma = g->pkd_u + l.pkd_off;
+    if (g->bf) { op.w_umma = g->pkd_u + l.pkd_off; op.w_ig = g->pkd_ig + l.pkd_off; }
     return op;
   };
   void* last_up = g->U > 0 ? g->up[g->U - 1] : g->t1;
@@ -800,6 +842,7 @@ struct dg_critic {
   PackDesc *tab_fwd = nullptr, *tab_dgrad = nullptr;
   int n_fwd = 0, n_dgrad = 0, max_fwd = 0, max_dgrad = 0;
   bf16 *pk_u = nullptr, *pkd_u = nullptr;
+  bf16 *pk_ig = nullptr, *pkd_ig = nullptr;  // K-major images [tap][CoP][Ci] for the streaming implicit-GEMM kernel
   UmmaPackDesc *utab_fwd = nullptr, *utab_dgrad = nullptr;
   int n_ufwd = 0, n_udgrad = 0, max_ufwd = 1, max_udgrad = 1;
   bool packed = false;
@@ -929,6 +972,8 @@ extern "C" int dg_critic_create(const dg_critic_config* cfg, dg_critic** out) {
   CA(c->pkd, sizeof(float) * pkd);
   CA(c->pk_u, sizeof(bf16) * (pk + 64));
   CA(c->pkd_u, sizeof(bf16) * (pkd + 64));
+  CA(c->pk_ig, sizeof(bf16) * (pk + 64));
+  CA(c->pkd_ig, sizeof(bf16) * (pkd + 64));
   if ((s = upload_table(c->pool, tf, &c->tab_fwd)) != 0) { dg_critic_destroy(c); return s; }
   if ((s = upload_table(c->pool, td, &c->tab_dgrad)) != 0) { dg_critic_destroy(c); return s; }
   if ((s = upload_utable(c->pool, uf, &c->utab_fwd)) != 0) { dg_critic_destroy(c); return s; }
@@ -974,6 +1019,10 @@ extern "C" int dg_critic_pack(dg_critic* c, const float* params, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DG_TRY(pack_weights2(params, c->pk, c->pk_u, c->tab_fwd, c->n_fwd, c->max_fwd, c->pkd, c->pkd_u, c->tab_dgrad, c->n_dgrad,
                        c->max_dgrad, st));
+  if (c->bf && g_tune[16]) {
+    DG_TRY(pack_ig(c->pk, c->pk_ig, c->utab_fwd, c->n_ufwd, c->max_ufwd, st));
+    DG_TRY(pack_ig(c->pkd, c->pkd_ig, c->utab_dgrad, c->n_udgrad, c->max_udgrad, st));
+  }
   c->packed = true;
   return 0;
 }
@@ -987,7 +1036,7 @@ static int critic_forward_internal(dg_critic* c, int NB, cudaStream_t st, int s0
     op.x = x; op.Hin = c->Hin[i]; op.Win = c->Hin[i]; op.Ci = l.Ci;
     op.y = tv_batch(c->act(c->a[i + 1], l.Co), c->pix(i), s0); op.Hout = c->Hout[i]; op.Wout = c->Hout[i]; op.Co = l.Co;
     op.B = NB; op.w = c->pk + l.pk_off; op.bias = (i == 0) ? c->pk + c->pk_b0 : nullptr;
-    if (c->bf) op.w_umma = c->pk_u + l.pk_off;
+    if (c->bf) { op.w_umma = c->pk_u + l.pk_off; op.w_ig = c->pk_ig + l.pk_off; }
     op.stride = l.stride; op.act = ACT_LRELU; op.slope = C_SLOPE;
     DG_TRY(run_conv(op, st));
     x = op.y;
@@ -1040,7 +1089,7 @@ static int critic_backward_chain(dg_critic* c, int NB, int n0, int n1, float* g_
     op.x = tv_batch(c->act(c->dz[i + 1], l.Co), c->pix(i), s0); op.Hin = c->Hout[i]; op.Win = c->Hout[i]; op.Ci = l.Co;
     op.y = tv_batch(c->act(c->dz[i], l.Ci), c->pix(i - 1), s0); op.Hout = c->Hin[i]; op.Wout = c->Hin[i]; op.Co = l.Ci;
     op.B = NB; op.w = c->pkd + l.pkd_off;
-    if (c->bf) op.w_umma = c->pkd_u + l.pkd_off;
+    if (c->bf) { op.w_umma = c->pkd_u + l.pkd_off; op.w_ig = c->pkd_ig + l.pkd_off; }
     op.transposed = (l.stride == 2);
     op.act = ACT_MASK; op.slope = C_SLOPE; op.mask = tv_batch(c->act(c->a[i], l.Ci), c->pix(i - 1), s0);
     DG_TRY(run_conv(op, st));
@@ -1097,7 +1146,7 @@ static int critic_gp_second_order(dg_critic* c, int n0, int B, cudaStream_t st) 
     op.x = v; op.Hin = c->Hin[i]; op.Win = c->Hin[i]; op.Ci = l.Ci;
     op.y = c->act(pp[i & 1], l.Co); op.Hout = c->Hout[i]; op.Wout = c->Hout[i]; op.Co = l.Co;
     op.B = B; op.w = c->pk + l.pk_off; op.bias = nullptr; op.stride = l.stride;
-    if (c->bf) op.w_umma = c->pk_u + l.pk_off;
+    if (c->bf) { op.w_umma = c->pk_u + l.pk_off; op.w_ig = c->pk_ig + l.pk_off; }
     op.act = ACT_MASK; op.slope = C_SLOPE; op.mask = tv_batch(c->act(c->a[i + 1], l.Co), c->pix(i), n0);
     DG_TRY(run_conv(op, st));
     v = op.y;
@@ -1112,8 +1161,7 @@ static int critic_gp_second_order(dg_critic* c, int n0, int B, cudaStream_t st) 
 static int critic_gp_first_order(dg_critic* c, const dg_hyper* hp, int n0, int B, float* scalars, int write_loss,
                                  float* norms_out, cudaStream_t st, float* u_out = nullptr) {
   const size_t per = (size_t)c->Hf * c->Hf * c->nc;
-  DG_TRY(gp_norms(c->g, B, per, c->sumsq, st));
-  DG_TRY(gp_finish(c->sumsq, B, hp->gp_lambda, norms_out ? norms_out : c->norms, c->coef, scalars, write_loss, st));
+  DG_TRY(gp_norms_finish(c->g, B, per, hp->gp_lambda, c->sumsq, norms_out ? norms_out : c->norms, c->coef, scalars, write_loss, st));
   DG_TRY(gp_scale(c->g, c->coef, u_out ? u_out : c->u, B, per, st));
   (void)n0;
   return 0;
@@ -1158,7 +1206,7 @@ static int critic_second_order_and_wgrads(dg_critic* c, int B, cudaStream_t st, 
     op.x = v; op.Hin = c->Hin[i]; op.Win = c->Hin[i]; op.Ci = l.Ci;
     op.y = tv_batch(c->act(c->a[i + 1], l.Co), c->pix(i), n0); op.Hout = c->Hout[i]; op.Wout = c->Hout[i]; op.Co = l.Co;
     op.B = B; op.w = c->pk + l.pk_off; op.bias = nullptr; op.stride = l.stride;
-    if (c->bf) op.w_umma = c->pk_u + l.pk_off;
+    if (c->bf) { op.w_umma = c->pk_u + l.pk_off; op.w_ig = c->pk_ig + l.pk_off; }
     op.act = ACT_MASK; op.slope = C_SLOPE; op.mask = op.y;
     DG_TRY(run_conv(op, st));
     v = op.y;
@@ -1589,7 +1637,7 @@ struct Scratch {
 }  // namespace
 
 static int prim_setup(Scratch& s, int precision, const float* w, int ci, int co, int mode, float** pk, cudaStream_t st,
-                      bf16** pk_u = nullptr) {
+                      bf16** pk_u = nullptr, bf16** pk_ig = nullptr) {
   const bool dgrad = mode != 0;
   const size_t elems = dgrad ? packed_w_elems(co, ci) : packed_w_elems(ci, co);
   DG_TRY(dev_alloc(s.pool, (void**)pk, elems * sizeof(float)));
@@ -1610,6 +1658,10 @@ static int prim_setup(Scratch& s, int precision, const float* w, int ci, int co,
       DG_TRY(dev_alloc(s.pool, (void**)&udev, sizeof(u)));
       DG_CUDA(cudaMemcpy(udev, &u, sizeof(u), cudaMemcpyHostToDevice));
       DG_TRY(pack_umma(*pk, *pk_u, udev, 1, (int)elems, st));
+      if (pk_ig) {
+        DG_TRY(dev_alloc(s.pool, (void**)pk_ig, (elems + 64) * sizeof(bf16)));
+        DG_TRY(pack_ig(*pk, *pk_ig, udev, 1, (int)elems, st));
+      }
     }
   }
   return 0;
@@ -1623,15 +1675,15 @@ extern "C" int dg_conv3x3_fwd(const float* x, const float* w, const float* bias,
   const int bf = precision == DG_BF16;
   const size_t esz = bf ? 2 : 4;
   const int ho = (hin - 1) / stride + 1, wo = (win - 1) / stride + 1;
-  float* pk; void *xi, *yo; bf16* pku;
-  DG_TRY(prim_setup(s, precision, w, ci, co, 0, &pk, st, &pku));
+  float* pk; void *xi, *yo; bf16 *pku, *pkig = nullptr;
+  DG_TRY(prim_setup(s, precision, w, ci, co, 0, &pk, st, &pku, &pkig));
   DG_TRY(dev_alloc(s.pool, &xi, (size_t)batch * hin * win * ci * esz));
   DG_TRY(dev_alloc(s.pool, &yo, (size_t)batch * ho * wo * co * esz));
   DG_TRY(nchw_to_nhwc(x, tv(xi, bf, ci), batch, ci, hin, win, st));
   ConvOp op;
   op.x = tv(xi, bf, ci); op.Hin = hin; op.Win = win; op.Ci = ci;
   op.y = tv(yo, bf, co); op.Hout = ho; op.Wout = wo; op.Co = co;
-  op.B = batch; op.w = pk; op.bias = bias; op.stride = stride; op.w_umma = pku;
+  op.B = batch; op.w = pk; op.bias = bias; op.stride = stride; op.w_umma = pku; op.w_ig = pkig;
   if (slope != 1.f) { op.act = ACT_LRELU; op.slope = slope; }
   DG_TRY(run_conv(op, st));
   DG_TRY(nhwc_to_nchw(tv(yo, bf, co), y, batch, co, ho, wo, st));
@@ -1647,15 +1699,15 @@ extern "C" int dg_conv3x3_dgrad(const float* dy, const float* w, float* dx, int 
   const int bf = precision == DG_BF16;
   const size_t esz = bf ? 2 : 4;
   const int ho = (hin - 1) / stride + 1, wo = (win - 1) / stride + 1;
-  float* pk; void *dyi, *dxo; bf16* pku;
-  DG_TRY(prim_setup(s, precision, w, ci, co, stride == 2 ? 2 : 1, &pk, st, &pku));
+  float* pk; void *dyi, *dxo; bf16 *pku, *pkig = nullptr;
+  DG_TRY(prim_setup(s, precision, w, ci, co, stride == 2 ? 2 : 1, &pk, st, &pku, &pkig));
   DG_TRY(dev_alloc(s.pool, &dyi, (size_t)batch * ho * wo * co * esz));
   DG_TRY(dev_alloc(s.pool, &dxo, (size_t)batch * hin * win * ci * esz));
   DG_TRY(nchw_to_nhwc(dy, tv(dyi, bf, co), batch, co, ho, wo, st));
   ConvOp op;
   op.x = tv(dyi, bf, co); op.Hin = ho; op.Win = wo; op.Ci = co;
   op.y = tv(dxo, bf, ci); op.Hout = hin; op.Wout = win; op.Co = ci;
-  op.B = batch; op.w = pk; op.transposed = (stride == 2); op.w_umma = pku;
+  op.B = batch; op.w = pk; op.transposed = (stride == 2); op.w_umma = pku; op.w_ig = pkig;
   DG_TRY(run_conv(op, st));
   DG_TRY(nhwc_to_nchw(tv(dxo, bf, ci), dx, batch, ci, hin, win, st));
   DG_CUDA(cudaStreamSynchronize(st));

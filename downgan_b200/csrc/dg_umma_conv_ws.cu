@@ -60,6 +60,7 @@ struct WsArgs {
   unsigned tile_tx;  // bytes one tile's TMA loads deliver
   unsigned over;     // tail pad: bytes the last M-tile's rows may read past the last box region
   unsigned long long* trace;  // debug timeline (DG_WS_TRACE=1), null otherwise
+  int early;                  // 1: the producer fills the ring before the weight staging / block barrier (dg_set_tuning(17, .))
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -188,18 +189,55 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_ws_kernel(const __grid_con
   auto tfull_bar = [&](int q) { return bar0 + 8u * (2 * WS_MAX_STAGE + q); };
   auto tempty_bar = [&](int q) { return bar0 + 8u * (2 * WS_MAX_STAGE + 2 + q); };
 
-  if (warp == WS_MMA_WARP) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)a.tmem_cols);
-  if (tid == 0) {
-    for (int s = 0; s < WS_MAX_STAGE; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int q = 0; q < 2; ++q) {
-      mbar_init(tfull_bar(q), 1);
-      mbar_init(tempty_bar(q), WS_EPI_WARPS);
-    }
-  }
   const uint32_t sa0 = (smem_u32(smem) + 1023u) & ~1023u;  // swizzle atoms repeat every 1024 bytes
+  const int my_tiles = ((int)blockIdx.x < a.tiles_total) ? (a.tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  // TMA loads of tile `it` into ring slot it % S (whole producer warp; one elected lane issues)
+  auto produce_tile = [&](int it) {
+    const int tile = blockIdx.x + it * gridDim.x;
+    const int s = it % S;
+    if (lane == 0) WS_TRACE(0, it, 0);
+    mbar_wait_ws(empty_bar(s), (((uint32_t)(it / S)) & 1u) ^ 1u);
+    if (lane == 0) WS_TRACE(0, it, 1);
+    const uint32_t sa = sa0 + s * a.a_bytes;
+    const int n = tile / a.tiles_per_img;
+    const int y0 = (tile - n * a.tiles_per_img) * a.TH;
+    if (elect_one_sync()) {
+      mbar_expect_tx(full_bar(s), a.tile_tx);
+#pragma unroll
+      for (int sub = 0; sub < ((MODE == S2_FWD) ? 4 : 1); ++sub) {
+        int cx, cy;
+        if (MODE == S1) { cx = -1; cy = y0 - 1; }
+        else if (MODE == S2_FWD) { cx = -2 + (sub & 1); cy = 2 * (y0 - 1) + (sub >> 1); }
+        else { cx = 0; cy = y0; }
+        for (int blk = 0; blk < a.nblk; ++blk)
+          tma_load_4d(sa + (sub * a.nblk + blk) * a.RB, &tmap, blk * a.Cb, cx, cy, n, full_bar(s));
+      }
+    }
+    __syncwarp();
+    if (lane == 0) WS_TRACE(0, it, 2);
+  };
+  const int pre_tiles = a.early ? min(S, my_tiles) : 0;
+
+  if (warp == WS_MMA_WARP) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)a.tmem_cols);
+  if (warp == WS_PROD_WARP) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+      for (int s = 0; s < WS_MAX_STAGE; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int q = 0; q < 2; ++q) {
+        mbar_init(tfull_bar(q), 1);
+        mbar_init(tempty_bar(q), WS_EPI_WARPS);
+      }
+    }
+    __syncwarp();
+    // The first ring slots are filled BEFORE the weights are staged and the block synchronises: the first tiles' load latency
+    // (tensor-map fetch, L2 / HBM round trip) overlaps the weight staging, the TMEM allocation and the barrier.  The ring
+    // [sa0, sa0 + S * a_bytes) and the weight image behind it are disjoint.  (PDL: the activations are the previous kernel's.)
+    if (pre_tiles > 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int it = 0; it < pre_tiles; ++it) produce_tile(it);
+  }
   const uint32_t sw = sa0 + a.w_off;
   {
     // weights: planes [tap*nplanes + pl], NT rows of 16 B each; row j of the chunk is output channel
@@ -230,36 +268,10 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_ws_kernel(const __grid_con
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t tmem = tmem_slot;
   constexpr int ncls = (MODE == S2_DGRAD) ? 4 : 1;
-  const int my_tiles = ((int)blockIdx.x < a.tiles_total) ? (a.tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == WS_PROD_WARP) {
     // ================= TMA producer =================
-    const int trows = a.TH + ((MODE == S1) ? 2 : 1);
-    (void)trows;
-    for (int it = 0; it < my_tiles; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int s = it % S;
-      if (lane == 0) WS_TRACE(0, it, 0);
-      mbar_wait_ws(empty_bar(s), (((uint32_t)(it / S)) & 1u) ^ 1u);
-      if (lane == 0) WS_TRACE(0, it, 1);
-      const uint32_t sa = sa0 + s * a.a_bytes;
-      const int n = tile / a.tiles_per_img;
-      const int y0 = (tile - n * a.tiles_per_img) * a.TH;
-      if (elect_one_sync()) {
-        mbar_expect_tx(full_bar(s), a.tile_tx);
-#pragma unroll
-        for (int sub = 0; sub < ((MODE == S2_FWD) ? 4 : 1); ++sub) {
-          int cx, cy;
-          if (MODE == S1) { cx = -1; cy = y0 - 1; }
-          else if (MODE == S2_FWD) { cx = -2 + (sub & 1); cy = 2 * (y0 - 1) + (sub >> 1); }
-          else { cx = 0; cy = y0; }
-          for (int blk = 0; blk < a.nblk; ++blk)
-            tma_load_4d(sa + (sub * a.nblk + blk) * a.RB, &tmap, blk * a.Cb, cx, cy, n, full_bar(s));
-        }
-      }
-      __syncwarp();
-      if (lane == 0) WS_TRACE(0, it, 2);
-    }
+    for (int it = pre_tiles; it < my_tiles; ++it) produce_tile(it);
   } else if (warp == WS_MMA_WARP) {
     // ================= MMA issue =================
     // The whole warp runs the (warp-uniform) loops so that descriptors live in uniform registers; one
@@ -574,6 +586,7 @@ bool plan_ws(const ConvOp& op, WsArgs& a, int& ctas_per_sm) {
   a.magic_pw = (unsigned)((0x100000000ULL + PW - 1) / PW);
   a.perm = perm;
   a.trace = nullptr;
+  a.early = g_tune[17] ? 1 : 0;
   a.tile_tx = (unsigned)(nsub * PW * (bestTH + hrows) * op.Ci * 2);
   a.Fsh = perm ? op.Co / 4 : 1;
   ctas_per_sm = best_cps;

@@ -284,8 +284,12 @@ int dg_profile_report(double* out, int n_classes);
  * (1, default: validated in round 2, tests/test_gpu_fc_umma.py; +1.8 % on the cfg-2 step) or on the CUDA-core kernels (0).
  * key 15: parity instrumentation - the fused critic iteration keeps a copy of the interpolates' activations for
  * dg_critic_activation(101..108) (0, default: off, no copy).
+ * key 16: streaming implicit-GEMM conv kernel (csrc/dg_umma_conv_ig.cu) on the shapes where it is the faster tcgen05 kernel
+ * (1, default) or never (0: every tcgen05 conv on the weights-stationary kernel, the round-1 behaviour).
+ * key 17: the TMA producer of the weights-stationary conv kernel fills its ring before the CTA stages its weights and
+ * synchronises (1, default) or after (0).
  * Returns the previous value, or DG_ERR_INVALID for an unknown key. */
-#define DG_TUNE_KEYS 16
+#define DG_TUNE_KEYS 18
 int dg_set_tuning(int key, int value);
 
 #ifdef __cplusplus
