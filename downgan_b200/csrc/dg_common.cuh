@@ -235,6 +235,8 @@ int wgrad_umma(const WgradOp& op, cudaStream_t st);
 int pack_umma(const float* packed, void* dst_bf16, const UmmaPackDesc* table_dev, int n, int max_elems, cudaStream_t st);
 // streaming implicit-GEMM conv (dg_umma_conv_ig.cu): both operands by TMA per (tap, channel block); weight image [tap][CoP][Ci]
 int pack_ig(const float* packed, void* dst_bf16, const UmmaPackDesc* table_dev, int n, int max_elems, cudaStream_t st);
+int pack_ig2(const float* packed, void* dst_bf16, const UmmaPackDesc* table_dev, int n, int max_elems, const float* packed2,
+             void* dst2_bf16, const UmmaPackDesc* table2_dev, int n2, int max_elems2, cudaStream_t st);
 bool conv_ig_supported(const ConvOp& op);
 bool conv_ig_preferred(const ConvOp& op);
 int conv_ig(const ConvOp& op, cudaStream_t st);

@@ -176,10 +176,12 @@ struct dg_generator {
   bf16* pk_trunk = nullptr;                // slice-major images of the dense convs for the fused trunk kernel
   bf16* pkd_trunk = nullptr;               // same for the dense data-gradient matrices (fused trunk backward)
   void** d_ptrs_dev = nullptr;             // device copy of Dall[]
-  UmmaPackDesc *utab_fwd = nullptr, *utab_dgrad = nullptr;
-  int n_ufwd = 0, n_udgrad = 0, max_ufwd = 1, max_udgrad = 1;
+  UmmaPackDesc *utab_fwd = nullptr, *utab_dgrad = nullptr, *utab_igfwd = nullptr;
+  int n_ufwd = 0, n_udgrad = 0, max_ufwd = 1, max_udgrad = 1, n_igfwd = 0;
   std::vector<long long> db_dgrad_off;  // [(r*3+d)*5 + k] packed offset of Wt_k
   bool packed = false;
+  bool use_ig = false;  // some layer may run on the streaming implicit-GEMM kernel (F >= 32 or maps wider than a TMA halo box):
+                        // the F = 16 / 128x128 generator never does, so its K-major weight images are not packed at all
   // activations
   void* x0 = nullptr;
   std::vector<void*> db;  // R*3 concat buffers (B,Hc,Hc,5F)
@@ -279,6 +281,7 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
   g->Cin = cfg->channels; g->Cout = cfg->n_predictands; g->Hf = g->Hc << g->U; g->maxB = cfg->max_batch;
   gen_enumerate(*cfg, g->layers, g->n_params);
   const int F = g->F;
+  g->use_ig = g->bf && (F >= 32 || g->Hf > 254);
   // ---- packed layouts + tables
   std::vector<PackDesc> tf, td;
   long long pk = 0, pkd = 0;
@@ -345,6 +348,12 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
         }
   }
   g->n_ufwd = (int)uf.size(); g->n_udgrad = (int)ud.size();
+  // the streaming kernel also takes narrow outputs (conv3.2: F -> n_predictands as N = 16 with zero pad columns)
+  std::vector<UmmaPackDesc> igf = uf;
+  if (g->bf)
+    for (auto& l : g->layers)
+      if (!umma_ok(l.Ci, l.Co) && umma_img_ok(l.Ci, l.Co)) igf.push_back({l.pk_off, l.Ci, round_up(l.Co, 16)});
+  g->n_igfwd = (int)igf.size();
   int s = 0;
 #define GA(ptr, bytes) if ((s = dev_alloc(g->pool, (void**)&(ptr), (bytes))) != 0) { dg_generator_destroy(g); return s; }
   GA(g->pk, sizeof(float) * pk);
@@ -360,6 +369,7 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
   if ((s = upload_table(g->pool, td, &g->tab_dgrad)) != 0) { dg_generator_destroy(g); return s; }
   if ((s = upload_utable(g->pool, uf, &g->utab_fwd)) != 0) { dg_generator_destroy(g); return s; }
   if ((s = upload_utable(g->pool, ud, &g->utab_dgrad)) != 0) { dg_generator_destroy(g); return s; }
+  if ((s = upload_utable(g->pool, igf, &g->utab_igfwd)) != 0) { dg_generator_destroy(g); return s; }
   // ---- activations
   const size_t B = g->maxB, pc = (size_t)g->Hc * g->Hc, pf = (size_t)g->Hf * g->Hf;
   GA(g->x0, B * pc * g->Cin * g->esz);
@@ -423,9 +433,9 @@ extern "C" int dg_generator_pack(dg_generator* g, const float* params, void* str
   DG_TRY(g->side.join(st));  // a deferred look-ahead chain (dg_generator_lookahead_first) may still be running
   DG_TRY(pack_weights2(params, g->pk, g->pk_u, g->tab_fwd, g->n_fwd, g->max_fwd, g->pkd, g->pkd_u, g->tab_dgrad, g->n_dgrad,
                        g->max_dgrad, st));
-  if (g->bf && g_tune[16]) {
-    DG_TRY(pack_ig(g->pk, g->pk_ig, g->utab_fwd, g->n_ufwd, g->max_ufwd, st));
-    DG_TRY(pack_ig(g->pkd, g->pkd_ig, g->utab_dgrad, g->n_udgrad, g->max_udgrad, st));
+  if (g->use_ig && g_tune[16]) {
+    DG_TRY(pack_ig2(g->pk, g->pk_ig, g->utab_igfwd, g->n_igfwd, g->max_ufwd, g->pkd, g->pkd_ig, g->utab_dgrad, g->n_udgrad,
+                    g->max_udgrad, st));
   }
   if (trunk_fused_supported(g->F, g->Hc, g->R, g->bf))
   {
@@ -449,7 +459,7 @@ static int gen_trunk_forward(dg_generator* g, int s0, int B, int save_count, cud
     op.x = x; op.Hin = H; op.Win = H; op.Ci = l.Ci;
     op.y = y; op.Hout = H; op.Wout = H; op.Co = l.Co;
     op.B = B; op.w = g->pk + l.pk_off; op.bias = g->pk + l.pkb_off;
-    if (g->bf) { op.w_umma = g->pk_u + l.pk_off; op.w_ig = g->pk_ig + l.pk_off; }
+    if (g->bf) { op.w_umma = g->pk_u + l.pk_off; op.w_ig = g->use_ig ? g->pk_ig + l.pk_off : nullptr; }
     return op;
   };
   const bool fused_trunk = trunk_fused_supported(F, Hc, g->R, g->bf);
@@ -498,7 +508,7 @@ static int gen_forward_range(dg_generator* g, int s0, int B, int save_count, cud
     op.x = x; op.Hin = H; op.Win = H; op.Ci = l.Ci;
     op.y = y; op.Hout = H; op.Wout = H; op.Co = l.Co;
     op.B = B; op.w = g->pk + l.pk_off; op.bias = g->pk + l.pkb_off;
-    if (g->bf) { op.w_umma = g->pk_u + l.pk_off; op.w_ig = g->pk_ig + l.pk_off; }
+    if (g->bf) { op.w_umma = g->pk_u + l.pk_off; op.w_ig = g->use_ig ? g->pk_ig + l.pk_off : nullptr; }
     return op;
   };
   void* first = g->R > 0 ? g->db[0] : g->trunk_out;
@@ -624,7 +634,7 @@ static int gen_trunk_backward(dg_generator* g, int B, bool& side_on, cudaStream_
         op.x = g->act(g->D, 5 * F, 0); op.Hin = Hc; op.Win = Hc; op.Ci = (5 - k) * F;
         op.y = g->act(g->D, 5 * F, (5 - k) * F); op.Hout = Hc; op.Wout = Hc; op.Co = F;
         op.B = B; op.w = g->pkd + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + k];
-        if (g->bf) { op.w_umma = g->pkd_u + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + k]; op.w_ig = g->pkd_ig + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + k]; }
+        if (g->bf) { op.w_umma = g->pkd_u + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + k]; op.w_ig = g->use_ig ? g->pkd_ig + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + k] : nullptr; }
         op.act = ACT_MASK; op.slope = G_SLOPE; op.mask = g->act(buf, 5 * F, k * F);
         DG_TRY(run_conv(op, st));
       }
@@ -648,7 +658,7 @@ static int gen_trunk_backward(dg_generator* g, int B, bool& side_on, cudaStream_
       op.x = g->act(g->D, 5 * F, 0); op.Hin = Hc; op.Win = Hc; op.Ci = 5 * F;
       op.y = g->act(gout, F); op.Hout = Hc; op.Wout = Hc; op.Co = F;
       op.B = B; op.w = g->pkd + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + 0];
-      if (g->bf) { op.w_umma = g->pkd_u + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + 0]; op.w_ig = g->pkd_ig + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + 0]; }
+      if (g->bf) { op.w_umma = g->pkd_u + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + 0]; op.w_ig = g->use_ig ? g->pkd_ig + g->db_dgrad_off[(size_t)(r * 3 + d) * 5 + 0] : nullptr; }
       op.r1 = g->act(gin, F); op.s1 = s_in;
       if (d == 0) { op.r2 = g->act(g->gR, F); op.s2 = 1.f; }
       DG_TRY(run_conv(op, st));
@@ -710,7 +720,7 @@ static int gen_backward_internal(dg_generator* g, float* grads_flat, float* d_co
     op.x = dy; op.Hin = H; op.Win = H; op.Ci = l.Co;
     op.y = dx; op.Hout = H; op.Wout = H; op.Co = l.Ci;
     op.B = B; op.w = g->pkd + l.pkd_off;
-    if (g->bf) { op.w_umma = g->pkd_u + l.pkd_off; op.w_ig = g->pkd_ig + l.pkd_off; }
+    if (g->bf) { op.w_umma = g->pkd_u + l.pkd_off; op.w_ig = g->use_ig ? g->pkd_ig + l.pkd_off : nullptr; }
     return op;
   };
   void* last_up = g->U > 0 ? g->up[g->U - 1] : g->t1;
@@ -843,8 +853,8 @@ struct dg_critic {
   int n_fwd = 0, n_dgrad = 0, max_fwd = 0, max_dgrad = 0;
   bf16 *pk_u = nullptr, *pkd_u = nullptr;
   bf16 *pk_ig = nullptr, *pkd_ig = nullptr;  // K-major images [tap][CoP][Ci] for the streaming implicit-GEMM kernel
-  UmmaPackDesc *utab_fwd = nullptr, *utab_dgrad = nullptr;
-  int n_ufwd = 0, n_udgrad = 0, max_ufwd = 1, max_udgrad = 1;
+  UmmaPackDesc *utab_fwd = nullptr, *utab_dgrad = nullptr, *utab_igdgrad = nullptr;
+  int n_ufwd = 0, n_udgrad = 0, max_ufwd = 1, max_udgrad = 1, n_igdgrad = 0;
   bool packed = false;
   // activations for up to NBmax samples
   float* a0 = nullptr;       // NHWC fp32 input batch
@@ -965,6 +975,14 @@ extern "C" int dg_critic_create(const dg_critic_config* cfg, dg_critic** out) {
       if (umma_ok(l.Co, l.Ci)) { ud.push_back({l.pkd_off, l.Co, round_up(l.Ci, 16)}); c->max_udgrad = std::max(c->max_udgrad, 9 * l.Ci * l.Co); }
     }
   c->n_ufwd = (int)uf.size(); c->n_udgrad = (int)ud.size();
+  // the streaming kernel also takes the narrow layer-1 data gradient (W -> nc as N = 16 with zero pad columns)
+  std::vector<UmmaPackDesc> igd = ud;
+  if (c->bf)
+    for (int i = 0; i < 8; ++i) {
+      const Layer& l = c->L[i];
+      if (!umma_ok(l.Co, l.Ci) && umma_img_ok(l.Co, l.Ci)) igd.push_back({l.pkd_off, l.Co, round_up(l.Ci, 16)});
+    }
+  c->n_igdgrad = (int)igd.size();
   int s = 0;
 #define CA(ptr, bytes) if ((s = dev_alloc(c->pool, (void**)&(ptr), (bytes))) != 0) { dg_critic_destroy(c); return s; }
   CA(c->pk, sizeof(float) * pk);
@@ -978,6 +996,7 @@ extern "C" int dg_critic_create(const dg_critic_config* cfg, dg_critic** out) {
   if ((s = upload_table(c->pool, td, &c->tab_dgrad)) != 0) { dg_critic_destroy(c); return s; }
   if ((s = upload_utable(c->pool, uf, &c->utab_fwd)) != 0) { dg_critic_destroy(c); return s; }
   if ((s = upload_utable(c->pool, ud, &c->utab_dgrad)) != 0) { dg_critic_destroy(c); return s; }
+  if ((s = upload_utable(c->pool, igd, &c->utab_igdgrad)) != 0) { dg_critic_destroy(c); return s; }
   const size_t NB = c->NBmax, B = c->maxB, pf = (size_t)c->Hf * c->Hf;
   CA(c->a0, NB * pf * c->nc * sizeof(float));
   size_t vmax = 0;
@@ -1020,8 +1039,8 @@ extern "C" int dg_critic_pack(dg_critic* c, const float* params, void* stream) {
   DG_TRY(pack_weights2(params, c->pk, c->pk_u, c->tab_fwd, c->n_fwd, c->max_fwd, c->pkd, c->pkd_u, c->tab_dgrad, c->n_dgrad,
                        c->max_dgrad, st));
   if (c->bf && g_tune[16]) {
-    DG_TRY(pack_ig(c->pk, c->pk_ig, c->utab_fwd, c->n_ufwd, c->max_ufwd, st));
-    DG_TRY(pack_ig(c->pkd, c->pkd_ig, c->utab_dgrad, c->n_udgrad, c->max_udgrad, st));
+    DG_TRY(pack_ig2(c->pk, c->pk_ig, c->utab_fwd, c->n_ufwd, c->max_ufwd, c->pkd, c->pkd_ig, c->utab_igdgrad, c->n_igdgrad,
+                    c->max_udgrad, st));
   }
   c->packed = true;
   return 0;
@@ -1101,7 +1120,7 @@ static int critic_backward_chain(dg_critic* c, int NB, int n0, int n1, float* g_
     op.x = tv_batch(c->act(c->dz[1], l.Co), c->pix(0), n0); op.Hin = c->Hout[0]; op.Win = c->Hout[0]; op.Ci = l.Co;
     op.y = tv(g_out, 0, l.Ci); op.Hout = c->Hin[0]; op.Wout = c->Hin[0]; op.Co = l.Ci;
     op.B = n1; op.w = c->pkd + l.pkd_off;
-    if (c->bf && umma_img_ok(l.Co, l.Ci)) { op.w_umma = c->pkd_u + l.pkd_off; op.narrow_ok = 1; }
+    if (c->bf && umma_img_ok(l.Co, l.Ci)) { op.w_umma = c->pkd_u + l.pkd_off; op.w_ig = c->pkd_ig + l.pkd_off; op.narrow_ok = 1; }
     DG_TRY(run_conv(op, st));
   }
   return 0;

@@ -333,7 +333,22 @@ __global__ void __launch_bounds__(IG_THREADS, 1) conv_ig_kernel(const __grid_con
               for (int j = 0; j < 16; ++j) v[j] *= (t[j] > 0.f ? 1.f : op.slope);
             }
           }
-          ig_st16(op.y, pix * op.y.pitch + op.y.coff + nc, v);
+          if (op.Co < 16) {  // narrow layer: only the first Co columns exist
+            const size_t o = pix * op.y.pitch + op.y.coff;
+            if (op.y.bf) {
+#pragma unroll
+              for (int j = 0; j < 15; ++j)  // static indices: v[] stays in registers
+                if (j < op.Co) ((bf16*)op.y.p)[o + j] = __float2bfloat16_rn(v[j]);
+            } else if (op.Co == 2 && ((o & 1) == 0)) {
+              *reinterpret_cast<float2*>((float*)op.y.p + o) = make_float2(v[0], v[1]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 15; ++j)
+                if (j < op.Co) ((float*)op.y.p)[o + j] = v[j];
+            }
+          } else {
+            ig_st16(op.y, pix * op.y.pitch + op.y.coff + nc, v);
+          }
         }
         m0 = nm0; m1 = nm1;
       }
@@ -353,14 +368,16 @@ inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 bool plan_ig(const ConvOp& op, IgArgs& a) {
   if (!op.w_ig || !op.x.bf) return false;
-  if (op.Ci % 16 || op.Co % 16 || op.Co > 256 || op.Co < 16) return false;
+  const bool narrow = op.Co < 16;  // e.g. conv3.2 (F -> 2): N = 16 MMA columns of a zero-padded weight image, only Co of them stored
+  if (op.Ci % 16 || (!narrow && op.Co % 16) || op.Co > 256 || op.Co < 1) return false;
+  if (narrow && (!op.narrow_ok || op.r1.p || op.r2.p || op.act == ACT_MASK)) return false;
   if (op.shuffle != SHUF_NONE) return false;
   if (op.x.pitch % 8 || op.x.coff % 8) return false;
   auto aligned = [](const TV& t) {
     if (!t.p) return true;
     return t.bf ? (t.pitch % 8 == 0 && t.coff % 8 == 0) : (t.pitch % 4 == 0 && t.coff % 4 == 0);
   };
-  if (!aligned(op.r1) || !aligned(op.r2) || !aligned(op.mask) || !aligned(op.y)) return false;
+  if (!aligned(op.r1) || !aligned(op.r2) || !aligned(op.mask) || (!narrow && !aligned(op.y))) return false;
   int mode;  // 0: stride 1, 1: stride-2 forward, 2: stride-2 data gradient
   if (op.transposed) {
     if (op.Hout != 2 * op.Hin || op.Wout != 2 * op.Win) return false;
@@ -482,28 +499,37 @@ int ig_map_b(const ConvOp& op, const IgArgs& a, CUtensorMap* out) {
   return 0;
 }
 
-// fp32 packed [tap][Ci][CoP] -> bf16 K-major [tap][CoP][Ci]; element offsets are shared with the fp32 packed buffer
-__global__ void pack_ig_kernel(const float* __restrict__ packed, bf16* __restrict__ dst, const UmmaPackDesc* __restrict__ table, int n) {
-  const int e = blockIdx.y;
-  if (e >= n) return;
-  const UmmaPackDesc d = table[e];
+// fp32 packed [tap][Ci][CoP] -> bf16 K-major [tap][CoP][Ci]; element offsets are shared with the fp32 packed buffer.
+// Two (source, destination, table) sets per launch: the forward and the data-gradient images of a network in one go.
+struct PackIgSet { const float* packed; bf16* dst; const UmmaPackDesc* table; int n; };
+__global__ void pack_ig_kernel(const PackIgSet s0, const PackIgSet s1) {
+  const bool second = (int)blockIdx.y >= s0.n;
+  const PackIgSet& s = second ? s1 : s0;
+  const int e = second ? (int)blockIdx.y - s0.n : (int)blockIdx.y;
+  if (e >= s.n) return;
+  const UmmaPackDesc d = s.table[e];
   const int total = 9 * d.Ci * d.CoP;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int ci = i % d.Ci;
     const int t = i / d.Ci;
     const int co = t % d.CoP, tap = t / d.CoP;
-    dst[d.off + i] = __float2bfloat16_rn(packed[d.off + ((size_t)tap * d.Ci + ci) * d.CoP + co]);
+    s.dst[d.off + i] = __float2bfloat16_rn(s.packed[d.off + ((size_t)tap * d.Ci + ci) * d.CoP + co]);
   }
 }
 
 }  // namespace
 
-int pack_ig(const float* packed, void* dst_bf16, const UmmaPackDesc* table_dev, int n, int max_elems, cudaStream_t st) {
-  if (n <= 0) return 0;
-  const int bx = std::max(1, std::min(64, (max_elems + 255) / 256));
-  pack_ig_kernel<<<dim3(bx, n), 256, 0, st>>>(packed, (bf16*)dst_bf16, table_dev, n);
+int pack_ig2(const float* packed, void* dst_bf16, const UmmaPackDesc* table_dev, int n, int max_elems, const float* packed2,
+             void* dst2_bf16, const UmmaPackDesc* table2_dev, int n2, int max_elems2, cudaStream_t st) {
+  if (n + n2 <= 0) return 0;
+  const int bx = std::max(1, std::min(64, (std::max(max_elems, max_elems2) + 255) / 256));
+  const PackIgSet s0{packed, (bf16*)dst_bf16, table_dev, n}, s1{packed2, (bf16*)dst2_bf16, table2_dev, n2};
+  pack_ig_kernel<<<dim3(bx, n + n2), 256, 0, st>>>(s0, s1);
   DG_LAUNCH_CHECK();
   return 0;
+}
+int pack_ig(const float* packed, void* dst_bf16, const UmmaPackDesc* table_dev, int n, int max_elems, cudaStream_t st) {
+  return pack_ig2(packed, dst_bf16, table_dev, n, max_elems, nullptr, nullptr, nullptr, 0, 1, st);
 }
 
 bool conv_ig_supported(const ConvOp& op) {
@@ -528,7 +554,7 @@ bool conv_ig_preferred(const ConvOp& op) {
   IgArgs a;
   if (!plan_ig(op, a)) return false;
   if (force == 2) return true;
-  if (!(op.w_umma && umma_ws_supported(op))) return op.Co >= 64 || !(op.w_umma && umma_supported(op));  // (Co = 32: 0.8 - 0.9x of the cp.async kernel)
+  if (!(op.w_umma && umma_ws_supported(op))) return op.Co >= 64 || op.Co < 16 || !(op.w_umma && umma_supported(op));  // (Co = 32: 0.8 - 0.9x of the cp.async kernel)
   const int npos = a.Ht * a.Wt;
   if (op.Ci >= 128 && op.Co >= 128 && npos <= 256) return true;                               // L7 forward / data gradient / JVP
   if (op.Ci >= 64 && op.Co >= 128 && npos <= 256 && !op.transposed) return true;                // L6 forward / JVP

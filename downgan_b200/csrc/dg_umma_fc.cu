@@ -13,7 +13,11 @@
 // (K-major planar [k/8][row][8] as in dg_umma_conv.cu, MN-major planar [mn/8][k][8] as in dg_umma_wgrad_im2col.cu),
 // converting the fp32 operands (weights, dz) to bf16 on the way, issues 7..12 tcgen05.mma per M-tile from one thread and
 // drains the TMEM accumulator with eight warps (two per lane quarter, alternating 16-column pieces).
+#include <stdlib.h>
+
 #include <algorithm>
+
+#include <cuda.h>
 
 #include "dg_umma.cuh"
 
@@ -303,8 +307,32 @@ int fc_dgrad_umma(const float* dz, const float* w, void* dx, int NB, int K, int 
   return 0;
 }
 
+// DG_FC_CHECK=1 (diagnostic): print every operand's extent against the allocation that holds it
+static void fcu_check(const char* what, const void* p, size_t bytes) {
+  typedef CUresult (*Fn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  static Fn fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult r;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &q, cudaEnableDefault, &r) != cudaSuccess || !q) return;
+    fn = (Fn)q;
+  }
+  CUdeviceptr base = 0; size_t size = 0;
+  const CUresult r = fn(&base, &size, (CUdeviceptr)p);
+  const long long off = (long long)((CUdeviceptr)p - base);
+  fprintf(stderr, "[fc check] %s: ptr %p needs %zu bytes; allocation base %p size %zu (offset %lld, room %lld)%s rc=%d\n", what, p, bytes,
+          (void*)base, size, off, (long long)size - off, ((long long)size - off < (long long)bytes) ? "  <-- OUT OF RANGE" : "", (int)r);
+}
+
 // dw += dz^T x
 int fc_wgrad_umma(const float* dz, const void* x, float* dw, int NB, int K, int N, cudaStream_t st) {
+  static const bool chk = getenv("DG_FC_CHECK") != nullptr;
+  if (chk) {
+    fprintf(stderr, "[fc check] fc_wgrad_umma NB %d K %d N %d\n", NB, K, N);
+    fcu_check("dz", dz, (size_t)NB * N * 4);
+    fcu_check("x", x, (size_t)NB * K * 2);
+    fcu_check("dw", dw, (size_t)N * K * 4);
+  }
   FcuArgs a{};
   a.x = x; a.dz = dz; a.dw = dw; a.NB = NB; a.K = K; a.N = N; a.rows = fcu_round(NB, 16);
   const size_t smem = (size_t)2 * 16 * a.rows * 16 + 256;

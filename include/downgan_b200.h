@@ -287,7 +287,7 @@ int dg_profile_report(double* out, int n_classes);
  * key 16: streaming implicit-GEMM conv kernel (csrc/dg_umma_conv_ig.cu) on the shapes where it is the faster tcgen05 kernel
  * (1, default) or never (0: every tcgen05 conv on the weights-stationary kernel, the round-1 behaviour).
  * key 17: the TMA producer of the weights-stationary conv kernel fills its ring before the CTA stages its weights and
- * synchronises (1, default) or after (0).
+ * synchronises (1) or after (0, default: measured -0.5 % on the cfg-2 step, profiles/README.md).
  * Returns the previous value, or DG_ERR_INVALID for an unknown key. */
 #define DG_TUNE_KEYS 18
 int dg_set_tuning(int key, int value);

@@ -5,7 +5,7 @@ import csv, json, re, sys
 from collections import OrderedDict
 
 CLASS_OF = [  # kernel-name prefix -> bench.py roofline class (csrc: prof_begin(PC_*))
-    ("conv_ws_kernel", "conv_tcgen05"), ("conv_umma_kernel", "conv_tcgen05"), ("conv_l1_kernel", "conv_tcgen05"),
+    ("conv_ws_kernel", "conv_tcgen05"), ("conv_ig_kernel", "conv_tcgen05"), ("conv_umma_kernel", "conv_tcgen05"), ("conv_l1_kernel", "conv_tcgen05"),
     ("wgrad_ws", "wgrad_tcgen05"), ("wgrad_l1_kernel", "wgrad_tcgen05"), ("wgrad_umma", "wgrad_tcgen05"),
     ("trunk_", "dense_block_tcgen05"), ("fc_", "linear"), ("fc2_", "linear"), ("critic_small_grads", "linear"),
     ("conv_co2", "conv_direct"), ("conv_ci2", "conv_direct"), ("conv_direct", "conv_direct"),

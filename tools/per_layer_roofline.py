@@ -40,13 +40,13 @@ def schedule():
     s += [(f"L{l} dgrad (3B)",) + conv(l, 3 * B, "dgrad") for l in range(7, 0, -1)]
     ci, co, hi, ho = LAY[0]
     s += [("L0 dgrad (interp, B)", 2.0 * B * hi * hi * 2 * 9 * 16, B * hi * hi * (16 * 2 + 2 * 4))]
-    s += [("GP norms", 0.0, B * 128 * 128 * 2 * 4), ("GP finish", 0.0, 0.0), ("GP scale (u)", 0.0, 2 * B * 128 * 128 * 2 * 4)]
+    s += [("GP norms + finish (one launch)", 0.0, B * 128 * 128 * 2 * 4), ("GP scale (u)", 0.0, 2 * B * 128 * 128 * 2 * 4)]
     for l in range(8):
         s += [(f"L{l} wgrad (3B)",) + conv(l, 3 * B, "wgrad"), (f"L{l} JVP (B)",) + conv(l, B, "jvp")]
     s += [("fc1 wgrad (3B)", 2.0 * 3 * B * FC_IN * FC_H, 3 * B * FC_IN * 2 + 2 * FC_IN * FC_H * 4),
           ("fc1 JVP (B)", 2.0 * B * FC_IN * FC_H, B * FC_IN * 2 + FC_IN * FC_H * 4), ("fc1 JVP finish", 0.0, 0.0),
           ("small classifier grads", 0.0, 0.0), ("unpack gradients", 0.0, 2 * 1112313 * 4), ("Adam", 0.0, 1112313 * 28),
-          ("pack weights (fwd + dgrad images)", 0.0, 1112313 * 4 * 3)]
+          ("pack weights (fwd + dgrad images)", 0.0, 1112313 * 4 * 3), ("pack K-major images (streaming kernel)", 0.0, 292896 * 2 * 6)]
     return s
 
 
