@@ -157,9 +157,12 @@ struct PackDesc {
   int dst_CoP;         // CoP of the destination op
   int umma;            // 1: also emit the bf16 tcgen05 B-operand image (same element offset) while packing
 };
-int pack_weights(const float* params, float* packed, void* packed_umma, const PackDesc* table_dev, int n, int max_elems, cudaStream_t st);
+// packed_ig (optional): also emit the K-major bf16 image [tap][CoP][rows] of the streaming implicit-GEMM kernel for d.umma entries
+int pack_weights(const float* params, float* packed, void* packed_umma, const PackDesc* table_dev, int n, int max_elems, cudaStream_t st,
+                 void* packed_ig = nullptr);
 int pack_weights2(const float* params, float* packed, void* packed_umma, const PackDesc* table_dev, int n, int max_elems, float* packed2,
-                  void* packed_umma2, const PackDesc* table2_dev, int n2, int max_elems2, cudaStream_t st);
+                  void* packed_umma2, const PackDesc* table2_dev, int n2, int max_elems2, cudaStream_t st, void* packed_ig = nullptr,
+                  void* packed_ig2 = nullptr);
 int unpack_wgrads(const float* packed, float* grads, const PackDesc* table_dev, int n, int max_elems, cudaStream_t st);
 
 int nchw_to_nhwc(const float* src, TV dst, int B, int C, int H, int W, cudaStream_t st);

@@ -297,6 +297,31 @@ static int colsum_slot(cudaStream_t st) {
   return 0;
 }
 
+// Last-block combine of the per-block partial column sums, by all 256 threads of the block: thread t owns channel t % C' and every
+// (256 / C')-th block (C' = C rounded up to a power of two), fp64 partials are then added in a fixed order - deterministic, and
+// nblocks / (256 / C') dependent-free loads per thread instead of nblocks serial ones on C threads (the 888-block sums of the
+// generator's tail layers spent 30 - 50 us in that loop).
+__device__ __forceinline__ void colsum_combine(const float* __restrict__ part, unsigned nblocks, int C, float* __restrict__ out, int t) {
+  __shared__ double shd[256];
+  for (int c0 = 0; c0 < C; c0 += 256) {
+    const int Cc = min(C - c0, 256);
+    int Cp = 1;
+    while (Cp < Cc) Cp <<= 1;
+    const int ngrp = 256 / Cp, c = t % Cp, grp = t / Cp;
+    double acc = 0.0;
+    if (c < Cc)
+      for (unsigned b = grp; b < nblocks; b += ngrp) acc += (double)__ldcg(part + (size_t)b * C + c0 + c);
+    shd[t] = acc;
+    __syncthreads();
+    if (grp == 0 && c < Cc) {
+      double tot = 0.0;
+      for (int g2 = 0; g2 < ngrp; ++g2) tot += shd[g2 * Cp + c];
+      out[c0 + c] += (float)tot;
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void colsum_kernel(TV dy, size_t pixels, int C, float* out, size_t pix_per_block, int slot) {
   __shared__ float sh[8][33];
   __shared__ bool last;
@@ -324,11 +349,7 @@ __global__ void colsum_kernel(TV dy, size_t pixels, int C, float* out, size_t pi
   __syncthreads();
   if (!last) return;
   __threadfence();
-  for (int c = threadIdx.y * 32 + threadIdx.x; c < C; c += 256) {
-    double t = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) t += (double)g_colsum_part[(size_t)b * C + c];
-    out[c] += (float)t;
-  }
+  colsum_combine(g_colsum_part, gridDim.x, C, out, threadIdx.y * 32 + threadIdx.x);
   if (threadIdx.x == 0 && threadIdx.y == 0) g_colsum_done = 0;
 }
 // bf16 rows with C in {16,32,64,128,256}: 16-byte loads (8 channels per thread), four pixels in flight per
@@ -378,11 +399,7 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(TV dy, size_t pixels, i
   __syncthreads();
   if (!last) return;
   __threadfence();
-  for (int c = threadIdx.x; c < C; c += 256) {
-    double t = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) t += (double)g_colsum_part[(size_t)b * C + c];
-    out[c] += (float)t;
-  }
+  colsum_combine(g_colsum_part, gridDim.x, C, out, threadIdx.x);
   if (threadIdx.x == 0) g_colsum_done = 0;
 }
 int colsum(TV dy, size_t pixels, int C, float* out, cudaStream_t st) {
@@ -456,8 +473,9 @@ int colsum_dense_blocks(void* const* d_bufs_dev, int n_blocks, size_t rows, floa
 __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src, float* __restrict__ dst, bf16* __restrict__ udst,
                                                    const PackDesc* __restrict__ tab, int unpack, int n1,
                                                    float* __restrict__ dst2, bf16* __restrict__ udst2,
-                                                   const PackDesc* __restrict__ tab2) {
-  if ((int)blockIdx.y >= n1) { dst = dst2; udst = udst2; tab = tab2 - n1; }
+                                                   const PackDesc* __restrict__ tab2, bf16* __restrict__ igdst,
+                                                   bf16* __restrict__ igdst2) {
+  if ((int)blockIdx.y >= n1) { dst = dst2; udst = udst2; tab = tab2 - n1; igdst = igdst2; }
   const PackDesc d = tab[blockIdx.y];
   if (d.mode == 4) {
     // linear weight (Co = N rows, Ci = K cols) with the NCHW -> NHWC column permutation (K = C*HW, C = slice_off): per row a
@@ -523,7 +541,12 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src
     } else {
       const float v = s_base[s_idx];
       d_base[p_idx] = v;
-      if (d.umma) udst[d.dst_off + (((tp * (R >> 3) + (row >> 3)) * cols + col) << 3) + (row & 7u)] = __float2bfloat16_rn(v);
+      if (d.umma) {
+        const bf16 vb = __float2bfloat16_rn(v);
+        udst[d.dst_off + (((tp * (R >> 3) + (row >> 3)) * cols + col) << 3) + (row & 7u)] = vb;
+        // K-major image [tap][CoP][rows] of the streaming implicit-GEMM kernel (dg_umma_conv_ig.cu), same element offset
+        if (igdst) igdst[d.dst_off + (tp * cols + col) * R + row] = vb;
+      }
     }
   }
 }
@@ -531,27 +554,30 @@ static inline int pack_blocks(int max_elems) {
   int bx = (max_elems + 1023) / 1024;  // ~4 elements per thread
   return bx < 1 ? 1 : (bx > 512 ? 512 : bx);
 }
-int pack_weights(const float* params, float* packed, void* packed_umma, const PackDesc* tab, int n, int max_elems, cudaStream_t st) {
+int pack_weights(const float* params, float* packed, void* packed_umma, const PackDesc* tab, int n, int max_elems, cudaStream_t st,
+                 void* packed_ig) {
   if (n == 0) return 0;
-  pack_kernel<<<dim3(pack_blocks(max_elems), n), 256, 0, st>>>(params, packed, (bf16*)packed_umma, tab, 0, n, nullptr, nullptr, nullptr);
+  pack_kernel<<<dim3(pack_blocks(max_elems), n), 256, 0, st>>>(params, packed, (bf16*)packed_umma, tab, 0, n, nullptr, nullptr, nullptr,
+                                                               (bf16*)packed_ig, nullptr);
   DG_LAUNCH_CHECK();
   return 0;
 }
 // forward and data-gradient tables of one network in ONE launch
 int pack_weights2(const float* params, float* packed, void* packed_umma, const PackDesc* tab, int n, int max_elems, float* packed2,
-                  void* packed_umma2, const PackDesc* tab2, int n2, int max_elems2, cudaStream_t st) {
+                  void* packed_umma2, const PackDesc* tab2, int n2, int max_elems2, cudaStream_t st, void* packed_ig, void* packed_ig2) {
   if (n == 0 || n2 == 0) {
-    DG_TRY(pack_weights(params, packed, packed_umma, tab, n, max_elems, st));
-    return pack_weights(params, packed2, packed_umma2, tab2, n2, max_elems2, st);
+    DG_TRY(pack_weights(params, packed, packed_umma, tab, n, max_elems, st, packed_ig));
+    return pack_weights(params, packed2, packed_umma2, tab2, n2, max_elems2, st, packed_ig2);
   }
   pack_kernel<<<dim3(pack_blocks(std::max(max_elems, max_elems2)), n + n2), 256, 0, st>>>(params, packed, (bf16*)packed_umma, tab, 0, n,
-                                                                                       packed2, (bf16*)packed_umma2, tab2);
+                                                                                       packed2, (bf16*)packed_umma2, tab2,
+                                                                                       (bf16*)packed_ig, (bf16*)packed_ig2);
   DG_LAUNCH_CHECK();
   return 0;
 }
 int unpack_wgrads(const float* packed, float* grads, const PackDesc* tab, int n, int max_elems, cudaStream_t st) {
   if (n == 0) return 0;
-  pack_kernel<<<dim3(pack_blocks(max_elems), n), 256, 0, st>>>(packed, grads, nullptr, tab, 1, n, nullptr, nullptr, nullptr);
+  pack_kernel<<<dim3(pack_blocks(max_elems), n), 256, 0, st>>>(packed, grads, nullptr, tab, 1, n, nullptr, nullptr, nullptr, nullptr, nullptr);
   DG_LAUNCH_CHECK();
   return 0;
 }

@@ -431,12 +431,9 @@ extern "C" int dg_generator_pack(dg_generator* g, const float* params, void* str
   DG_CHECK(g && params, "dg_generator_pack: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   DG_TRY(g->side.join(st));  // a deferred look-ahead chain (dg_generator_lookahead_first) may still be running
+  const bool g_ig = g->use_ig && g_tune[16];  // K-major images of the streaming kernel ride on the same launch
   DG_TRY(pack_weights2(params, g->pk, g->pk_u, g->tab_fwd, g->n_fwd, g->max_fwd, g->pkd, g->pkd_u, g->tab_dgrad, g->n_dgrad,
-                       g->max_dgrad, st));
-  if (g->use_ig && g_tune[16]) {
-    DG_TRY(pack_ig2(g->pk, g->pk_ig, g->utab_igfwd, g->n_igfwd, g->max_ufwd, g->pkd, g->pkd_ig, g->utab_dgrad, g->n_udgrad,
-                    g->max_udgrad, st));
-  }
+                       g->max_dgrad, st, g_ig ? g->pk_ig : nullptr, g_ig ? g->pkd_ig : nullptr));
   if (trunk_fused_supported(g->F, g->Hc, g->R, g->bf))
   {
     DG_TRY(pack_trunk_slices(g->pk + g->layers[g->idx_db(0, 0, 1)].pk_off, g->pk_trunk, g->R * 3, 0, st));
@@ -1036,12 +1033,9 @@ extern "C" int dg_critic_pack(dg_critic* c, const float* params, void* stream) {
   if (c && c->pending_finish) { set_error("dg_critic_pack: dg_critic_step_finish has not been called"); return DG_ERR_STATE; }
   DG_CHECK(c && params, "dg_critic_pack: null argument");
   cudaStream_t st = (cudaStream_t)stream;
+  const bool c_ig = c->bf && g_tune[16];  // K-major images of the streaming kernel ride on the same launch
   DG_TRY(pack_weights2(params, c->pk, c->pk_u, c->tab_fwd, c->n_fwd, c->max_fwd, c->pkd, c->pkd_u, c->tab_dgrad, c->n_dgrad,
-                       c->max_dgrad, st));
-  if (c->bf && g_tune[16]) {
-    DG_TRY(pack_ig2(c->pk, c->pk_ig, c->utab_fwd, c->n_ufwd, c->max_ufwd, c->pkd, c->pkd_ig, c->utab_igdgrad, c->n_igdgrad,
-                    c->max_udgrad, st));
-  }
+                       c->max_dgrad, st, c_ig ? c->pk_ig : nullptr, c_ig ? c->pkd_ig : nullptr));
   c->packed = true;
   return 0;
 }

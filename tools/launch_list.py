@@ -28,7 +28,7 @@ by_id = OrderedDict()
 for r in rows[start:]:
     if len(r) < len(hdr):
         continue
-    name = re.sub(r"\(.*", "", r[I["Kernel Name"]]).replace("dg::", "").replace("<unnamed>::", "").replace("void ", "")
+    name = re.sub(r"\(.*", "", r[I["Kernel Name"]]).replace("dg::", "").replace("<unnamed>::", "").replace("unnamed>::", "").replace("void ", "")
     e = by_id.setdefault(r[I["ID"]], {"name": name, "grid": r[I["Grid Size"]], "us": 0.0, "rd": None, "wr": None})
     v = float(r[I["Metric Value"]].replace(",", "")) * unit_scale(r[I["Metric Unit"]])
     m = r[I["Metric Name"]]

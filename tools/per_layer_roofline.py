@@ -46,7 +46,7 @@ def schedule():
     s += [("fc1 wgrad (3B)", 2.0 * 3 * B * FC_IN * FC_H, 3 * B * FC_IN * 2 + 2 * FC_IN * FC_H * 4),
           ("fc1 JVP (B)", 2.0 * B * FC_IN * FC_H, B * FC_IN * 2 + FC_IN * FC_H * 4), ("fc1 JVP finish", 0.0, 0.0),
           ("small classifier grads", 0.0, 0.0), ("unpack gradients", 0.0, 2 * 1112313 * 4), ("Adam", 0.0, 1112313 * 28),
-          ("pack weights (fwd + dgrad images)", 0.0, 1112313 * 4 * 3), ("pack K-major images (streaming kernel)", 0.0, 292896 * 2 * 6)]
+          ("pack weights (fwd + dgrad + K-major images)", 0.0, 1112313 * 4 * 3 + 292896 * 2 * 2)]
     return s
 
 
@@ -61,7 +61,7 @@ def main():
     for r in rows[st:]:
         if len(r) < len(hdr):
             continue
-        n = re.sub(r"\(.*", "", r[I["Kernel Name"]]).replace("dg::", "").replace("<unnamed>::", "").replace("void ", "")
+        n = re.sub(r"\(.*", "", r[I["Kernel Name"]]).replace("dg::", "").replace("<unnamed>::", "").replace("unnamed>::", "").replace("void ", "")
         e = by.setdefault(r[I["ID"]], {"n": n, "us": 0.0, "dram": 0.0})
         v = float(r[I["Metric Value"]].replace(",", ""))
         sc = {"ns": 1e-3, "us": 1, "ms": 1e3, "byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[I["Metric Unit"]], 1)
