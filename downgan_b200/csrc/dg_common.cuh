@@ -271,7 +271,7 @@ int wgrad_umma_batched(const WgradOp* ops, int n, void* table_dev, std::vector<u
 namespace dg {
 int pack_trunk_slices(const float* pk_first_dense, void* dst_bf16, int n_db, int bwd, cudaStream_t st);
 int trunk_bwd_fused(const void* g_in, void* g_out, void* const* fwd_bufs_dev, void* const* d_bufs_dev, const void* w_slices,
-                    int R, int B, cudaStream_t st);
+                    int R, int B, cudaStream_t st, int r0 = 0);
 }  // namespace dg
 
 namespace dg {

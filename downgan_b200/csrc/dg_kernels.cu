@@ -402,8 +402,50 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(TV dy, size_t pixels, i
   colsum_combine(g_colsum_part, gridDim.x, C, out, threadIdx.x);
   if (threadIdx.x == 0) g_colsum_done = 0;
 }
+// fp32 rows with C in {1, 2, 4} and no channel offset (the 2-channel fine fields: conv3.2's bias gradient sums dL/dfake): the
+// generic kernel would use C of its 32 channel lanes; here a thread reads float4 = 4 / C whole pixels per load.
+__global__ void __launch_bounds__(256) colsum_small_kernel(const float* __restrict__ x, size_t n_elems, int C, float* out,
+                                                           size_t elems_per_block, int slot) {
+  __shared__ float sh[256 * 4];
+  __shared__ bool last;
+  float* const g_colsum_part = g_colsum_parts[slot];
+  unsigned int& g_colsum_done = g_colsum_dones[slot];
+  const size_t e0 = (size_t)blockIdx.x * elems_per_block, e1 = min(n_elems, e0 + elems_per_block);  // multiples of 4
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (size_t i = (e0 >> 2) + threadIdx.x; i < (e1 >> 2); i += 256) {
+    const float4 v = __ldg(x4 + i);
+    acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sh[threadIdx.x * 4 + j] = acc[j];
+  __syncthreads();
+  if ((int)threadIdx.x < C) {  // element j of a float4 belongs to channel j % C
+    float t = 0.f;
+    for (int q = 0; q < 256; ++q)
+      for (int j = threadIdx.x; j < 4; j += C) t += sh[q * 4 + j];
+    g_colsum_part[(size_t)blockIdx.x * C + threadIdx.x] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(&g_colsum_done, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  colsum_combine(g_colsum_part, gridDim.x, C, out, threadIdx.x);
+  if (threadIdx.x == 0) g_colsum_done = 0;
+}
 int colsum(TV dy, size_t pixels, int C, float* out, cudaStream_t st) {
   DG_CHECK(C <= COLSUM_MAX_C, "colsum: %d channels > %d", C, COLSUM_MAX_C);
+  if (!dy.bf && (C == 1 || C == 2 || C == 4) && dy.pitch == C && dy.coff == 0 && ((uintptr_t)dy.p & 15) == 0 && ((pixels * C) & 3) == 0 &&
+      pixels >= 4096) {
+    const size_t n = pixels * C;
+    size_t epb = ((n + 148 * 4 - 1) / (148 * 4) + 1023) & ~(size_t)1023;
+    const unsigned grid = (unsigned)((n + epb - 1) / epb);
+    colsum_small_kernel<<<grid, 256, 0, st>>>((const float*)dy.p, n, C, out, epb, colsum_slot(st));
+    DG_LAUNCH_CHECK();
+    return 0;
+  }
   const bool vec = dy.bf && (C == 16 || C == 32 || C == 64 || C == 128 || C == 256) && dy.pitch % 8 == 0 && dy.coff % 8 == 0 &&
                    pixels >= 4096;
   if (vec) {
@@ -1296,7 +1338,7 @@ CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank,
   return fn(map, dt, rank, addr, dims, strides, box, estr, il, sw, l2, oob);
 }
 }  // namespace dg
-namespace dg { int g_tune[DG_TUNE_KEYS] = {1, 1, 1, 0, 1, 0, 1, 1, 1, 1, 4, 1, 1, 3, 1, 0, 1, 0}; }  // see include/downgan_b200.h: dg_set_tuning
+namespace dg { int g_tune[DG_TUNE_KEYS] = {1, 1, 1, 0, 1, 0, 1, 1, 1, 1, 4, 1, 1, 3, 1, 0, 1, 0, 2}; }  // see include/downgan_b200.h: dg_set_tuning
 extern "C" int dg_set_tuning(int key, int value) {
   if (key < 0 || key >= DG_TUNE_KEYS) { dg::set_error("dg_set_tuning: unknown key %d", key); return DG_ERR_INVALID; }
   const int prev = dg::g_tune[key];

@@ -195,6 +195,7 @@ struct dg_generator {
   std::vector<unsigned char> wg_shadow;
   void* wgws_table_dev = nullptr; // same for the TMA-fed kernel (plans + tensor maps)
   std::vector<unsigned char> wgws_shadow;
+  std::vector<std::vector<unsigned char>> wgws_parts;  // host shadows of the per-range tables (trunk backward in RRDB ranges)
   void *D = nullptr, *gR = nullptr, *gx0 = nullptr, *gx1 = nullptr, *gT1 = nullptr, *gA = nullptr, *gB = nullptr;
   std::vector<void*> gU;   // gU[u]: dz of upsample stage u, (B, Hc<<u, Hc<<u, 4F); one buffer per stage (no ping-pong), so
                            // weight gradients on the side stream never race a later data-gradient store; gU[U-1] == gB
@@ -396,7 +397,7 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
     g->Dall[0] = g->D;
     for (int i = 1; i < g->R * 3; ++i) GA(g->Dall[i], B * pc * 5 * F * g->esz);
     GA(g->wg_table_dev, wgrad_umma_args_size() * (size_t)g->R * 15);
-    GA(g->wgws_table_dev, wgrad_ws_batch_bytes(g->R * 15 * 2));
+    GA(g->wgws_table_dev, 4 * wgrad_ws_batch_bytes(g->R * 15 * 2));  // up to four RRDB ranges, one table each
     GA(g->d_ptrs_dev, sizeof(void*) * g->Dall.size());
     if (cudaMemcpy(g->d_ptrs_dev, g->Dall.data(), sizeof(void*) * g->Dall.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
       set_error("cudaMemcpy(d_ptrs) failed"); dg_generator_destroy(g); return DG_ERR_CUDA;
@@ -603,19 +604,53 @@ static int gen_trunk_backward(dg_generator* g, int B, bool& side_on, cudaStream_
     side_on = false;
   }
   if (fused_bwd) {
-    // persistent tcgen05 kernel: the whole data-gradient chain of the trunk, dz slices saved per block
-    DG_TRY(trunk_bwd_fused(g->gR, g->gR, (void* const*)g->db_ptrs_dev, (void* const*)g->d_ptrs_dev, g->pkd_trunk, g->R, B, st));
-    for (int r = g->R - 1; r >= 0; --r)
-      for (int d = 2; d >= 0; --d)
-        for (int k = 1; k <= 5; ++k) {
-          const Layer& l = g->layers[g->idx_db(r, d, k)];
-          WgradOp w;
-          memset(&w, 0, sizeof(w));
-          w.x = g->act(g->db[r * 3 + d], 5 * F, 0); w.Hin = Hc; w.Win = Hc; w.Ci = l.Ci;
-          w.dy = g->act(g->Dall[(size_t)r * 3 + d], 5 * F, (5 - k) * F); w.Hout = Hc; w.Wout = Hc; w.Co = l.Co;
-          w.B = B; w.stride = 1; w.dw = g->gpk + l.pk_off; w.dbias = g->gpk + l.pkb_off;
-          wops.push_back(w);
-        }
+    // Persistent tcgen05 kernel: the data-gradient chain of the trunk, dz slices saved per block.  The chain is launched in
+    // g_tune[18] RRDB ranges (last range first): the dense convs' weight gradients of a range only need that range's dz, so
+    // they are enqueued on the side stream as soon as the range's kernel is (one image per CTA: 64 of 148 SMs at cfg-2) and run
+    // beside the NEXT range's data gradients instead of after the whole chain (measured: profiles/README.md).
+    auto dense_wgrads = [&](int r_lo, int r_hi, int part, cudaStream_t s2) -> int {
+      std::vector<WgradOp> blk;
+      blk.reserve((size_t)(r_hi - r_lo) * 15 * 2);
+      for (int r = r_hi - 1; r >= r_lo; --r)
+        for (int d = 2; d >= 0; --d)
+          for (int k = 1; k <= 5; ++k) {
+            const Layer& l = g->layers[g->idx_db(r, d, k)];
+            WgradOp w;
+            memset(&w, 0, sizeof(w));
+            w.x = g->act(g->db[r * 3 + d], 5 * F, 0); w.Hin = Hc; w.Win = Hc; w.Ci = l.Ci;
+            w.dy = g->act(g->Dall[(size_t)r * 3 + d], 5 * F, (5 - k) * F); w.Hout = Hc; w.Wout = Hc; w.Co = l.Co;
+            w.B = B; w.stride = 1; w.dw = g->gpk + l.pk_off; w.dbias = g->gpk + l.pkb_off;
+            if (!(g_tune[4] && F == 16)) { wops.push_back(w); continue; }
+            for (int c0 = 0; c0 < w.Ci;) {  // power-of-two channel blocks for the TMA-fed kernel
+              int cb = 64;
+              while (cb > w.Ci - c0) cb >>= 1;
+              WgradOp o = w;
+              o.x.coff = w.x.coff + c0; o.Ci = cb; o.dbias = nullptr;
+              o.dw_ci_total = w.Ci; o.dw_ci_off = c0;
+              blk.push_back(o);
+              c0 += cb;
+            }
+          }
+      if (blk.empty()) return 0;
+      if ((int)g->wgws_parts.size() <= part) g->wgws_parts.resize(part + 1);
+      char* table = (char*)g->wgws_table_dev + (size_t)part * wgrad_ws_batch_bytes(g->R * 15 * 2);
+      DG_TRY(wgrad_ws_batched(blk.data(), (int)blk.size(), table, g->wgws_parts[part], 2, s2));
+      // bias gradients of the range = column sums of its dz buffers
+      const Layer& l0 = g->layers[g->idx_db(r_lo, 0, 1)];
+      return colsum_dense_blocks((void* const*)g->d_ptrs_dev + 3 * r_lo, (r_hi - r_lo) * 3, (size_t)B * Hc * Hc, g->gpk + l0.pkb_off, s2);
+    };
+    int nsplit = std::max(1, std::min(std::min(g_tune[18], 4), g->R));
+    if (!(side_on && g_tune[4] && F == 16)) nsplit = 1;
+    for (int p = nsplit - 1; p >= 0; --p) {
+      const int r_lo = (int)((long long)g->R * p / nsplit), r_hi = (int)((long long)g->R * (p + 1) / nsplit);
+      DG_TRY(trunk_bwd_fused(g->gR, g->gR, (void* const*)g->db_ptrs_dev, (void* const*)g->d_ptrs_dev, g->pkd_trunk, r_hi - r_lo, B, st, r_lo));
+      if (p > 0) {  // overlaps the next range's kernel
+        DG_TRY(g->side.fork(st));
+        DG_TRY(dense_wgrads(r_lo, r_hi, p, g->side.s));
+      } else {
+        DG_TRY(dense_wgrads(r_lo, r_hi, p, st));
+      }
+    }
   }
   for (int r = fused_bwd ? -1 : g->R - 1; r >= 0; --r) {
     // g->gR holds dL/d(RRDB_r output)
@@ -665,30 +700,9 @@ static int gen_trunk_backward(dg_generator* g, int B, bool& side_on, cudaStream_
   }
   g->D = D0;
   if (batched_wgrad && !wops.empty()) {
-    if (g_tune[4] && F == 16 && fused_bwd) {
-      // TMA-fed kernel: every layer (Ci = 16k input channels) as power-of-two channel blocks, two launches for all
-      // of them; bias gradients = column sums of the dz buffers in one more launch
-      std::vector<WgradOp> blk;
-      blk.reserve(wops.size() * 2);
-      for (const WgradOp& w : wops) {
-        int c0 = 0;
-        while (c0 < w.Ci) {
-          int cb = 64;
-          while (cb > w.Ci - c0) cb >>= 1;
-          WgradOp o = w;
-          o.x.coff = w.x.coff + c0; o.Ci = cb; o.dbias = nullptr;
-          o.dw_ci_total = w.Ci; o.dw_ci_off = c0;
-          blk.push_back(o);
-          c0 += cb;
-        }
-      }
-      DG_TRY(wgrad_ws_batched(blk.data(), (int)blk.size(), g->wgws_table_dev, g->wgws_shadow, 2, st));
-      const Layer& l0 = g->layers[g->idx_db(0, 0, 1)];
-      DG_TRY(colsum_dense_blocks((void* const*)g->d_ptrs_dev, g->R * 3, (size_t)B * Hc * Hc, g->gpk + l0.pkb_off, st));
-    } else {
-      // all 15R dense-conv weight + bias gradients in one tcgen05 launch
-      DG_TRY(wgrad_umma_batched(wops.data(), (int)wops.size(), g->wg_table_dev, g->wg_shadow, 2, st));
-    }
+    // (TMA-fed path: already launched range by range above.)  All remaining dense-conv weight + bias gradients in one
+    // tcgen05 launch of the cp.async kernel.
+    DG_TRY(wgrad_umma_batched(wops.data(), (int)wops.size(), g->wg_table_dev, g->wg_shadow, 2, st));
   }
   return 0;
 }

@@ -479,8 +479,13 @@ int pack_trunk_slices(const float* pk_first_dense, void* dst_bf16, int n_db, int
   return 0;
 }
 
+// RRDBs [r0, r0 + R) of the trunk (all pointers are those of the WHOLE trunk): g_in = dL/d(output of RRDB r0 + R - 1),
+// g_out = dL/d(input of RRDB r0); chaining calls from the last RRDB range to the first reproduces the single launch.
 int trunk_bwd_fused(const void* g_in, void* g_out, void* const* fwd_bufs_dev, void* const* d_bufs_dev, const void* w_slices,
-                    int R, int B, cudaStream_t st) {
+                    int R, int B, cudaStream_t st, int r0) {
+  fwd_bufs_dev += 3 * r0;
+  d_bufs_dev += 3 * r0;
+  w_slices = (const bf16*)w_slices + (size_t)3 * r0 * T_DB_ELEMS_;
   static bool attr_set = false;
   if (!attr_set) {
     DG_CUDA(cudaFuncSetAttribute(trunk_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));

@@ -444,7 +444,8 @@ int wgrad_ws(const WgradOp& op, cudaStream_t st) {
 
 
 size_t wgrad_ws_batch_bytes(int n_ops) {
-  return (size_t)n_ops * (sizeof(WwArgs) + 2 * sizeof(CUtensorMap) + sizeof(int)) + 256;
+  // a multiple of 256 so that consecutive tables in one allocation keep their tensor maps 64-byte aligned
+  return (((size_t)n_ops * (sizeof(WwArgs) + 2 * sizeof(CUtensorMap) + sizeof(int)) + 256) + 255) & ~(size_t)255;
 }
 
 // Table layout: [CUtensorMap x 2n (64-byte aligned)] [WwArgs x n] [int x n: op indices grouped by mode]

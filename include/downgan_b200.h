@@ -288,8 +288,10 @@ int dg_profile_report(double* out, int n_classes);
  * (1, default) or never (0: every tcgen05 conv on the weights-stationary kernel, the round-1 behaviour).
  * key 17: the TMA producer of the weights-stationary conv kernel fills its ring before the CTA stages its weights and
  * synchronises (1) or after (0, default: measured -0.5 % on the cfg-2 step, profiles/README.md).
+ * key 18 = k (1..4): the fused trunk backward runs as k launches over RRDB ranges; the dense convs' weight gradients of a range
+ * go to the side stream and overlap the next range's data gradients (default 2; 1 = one launch, weight gradients afterwards).
  * Returns the previous value, or DG_ERR_INVALID for an unknown key. */
-#define DG_TUNE_KEYS 18
+#define DG_TUNE_KEYS 19
 int dg_set_tuning(int key, int value);
 
 #ifdef __cplusplus
