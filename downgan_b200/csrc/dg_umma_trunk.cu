@@ -22,10 +22,11 @@ using namespace um;
 constexpr int TF = 16;            // filters
 constexpr int TW = 16;            // coarse grid edge
 constexpr int TPW = TW + 2;       // padded width
-constexpr int TNMT = 3;           // M-tiles: 3*128 >= 16*18-2
+constexpr int TNMT = 3;           // M-tiles: 128 + 128 + 64 rows >= the 16*18 = 288 padded positions (the third tile is an M = 64 MMA)
+constexpr int T_THREADS = 256;    // 8 warps: warps 0-3 drain M-tile 0 (and the 32 live rows of M-tile 2), warps 4-7 M-tile 1
 constexpr int T_COLS_MT = 5 * TF; // TMEM columns per M-tile: one 16-column accumulator per layer of the block
 constexpr int T_TMEM_COLS = 256;  // 3 * 80 = 240 -> power of two
-constexpr int TPBPOS = 424;       // positions per plane incl. over-read slack (3*128 + 2*18 + 2 -> 424)
+constexpr int TPBPOS = 424;       // positions per plane incl. over-read slack (2*128 + 64 + 2*18 + 2 = 358 <= 424)
 constexpr int TPB = TPBPOS * 16;  // plane stride in bytes
 constexpr int T_X_BYTES = 10 * TPB;
 constexpr int T_W_BYTES = 9 * 80 * TF * 2;
@@ -92,7 +93,7 @@ __device__ __forceinline__ void unpack8(uint4 q, float* v) {
 // completes first); 2: one thread, tap-major (chains interleaved).  Every M-tile commits to its own mbarrier.
 __device__ __forceinline__ void trunk_issue_round(int order, int warp, uint32_t tmem, uint32_t sX, uint32_t wb, int j, int Nj,
                                                   uint64_t* mbar) {
-  const uint32_t idj = instr_desc(128, Nj);
+  const uint32_t id128 = instr_desc(128, Nj), id64 = instr_desc(64, Nj);
   const uint32_t wplane = Nj * 16;
   const uint64_t bd0 = smem_desc(wb, wplane, 128);
   const uint32_t accf = (j > 0) ? 1u : 0u;
@@ -100,6 +101,7 @@ __device__ __forceinline__ void trunk_issue_round(int order, int warp, uint32_t 
     if (warp < TNMT) {
       if (elect_one_sync_t()) {
         const uint64_t ad0 = smem_desc(sX + 2 * j * TPB + (warp * 128) * 16, TPB, 128);
+        const uint32_t idj = (warp == 2) ? id64 : id128;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap)
           umma_f16(tmem + warp * T_COLS_MT + j * TF, ad0 + (uint64_t)((tap / 3) * TPW + tap % 3), bd0 + (uint64_t)((tap * 2 * wplane) >> 4), idj,
@@ -116,6 +118,7 @@ __device__ __forceinline__ void trunk_issue_round(int order, int warp, uint32_t 
 #pragma unroll
         for (int mt = 0; mt < TNMT; ++mt) {
           const uint64_t ad0 = smem_desc(sX + 2 * j * TPB + (mt * 128) * 16, TPB, 128);
+          const uint32_t idj = (mt == 2) ? id64 : id128;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap)
             umma_f16(tmem + mt * T_COLS_MT + j * TF, ad0 + (uint64_t)((tap / 3) * TPW + tap % 3), bd0 + (uint64_t)((tap * 2 * wplane) >> 4), idj,
@@ -129,7 +132,7 @@ __device__ __forceinline__ void trunk_issue_round(int order, int warp, uint32_t 
 #pragma unroll
           for (int mt = 0; mt < TNMT; ++mt)
             umma_f16(tmem + mt * T_COLS_MT + j * TF, ad0 + (uint64_t)(mt * 128 + (tap / 3) * TPW + tap % 3),
-                     bd0 + (uint64_t)((tap * 2 * wplane) >> 4), idj, (tap > 0) ? 1u : accf);
+                     bd0 + (uint64_t)((tap * 2 * wplane) >> 4), (mt == 2) ? id64 : id128, (tap > 0) ? 1u : accf);
 #pragma unroll
         for (int mt = 0; mt < TNMT; ++mt) umma_commit(smem_u32(&mbar[mt]));
       }
@@ -138,7 +141,36 @@ __device__ __forceinline__ void trunk_issue_round(int order, int warp, uint32_t 
   }
 }
 
-__global__ void __launch_bounds__(128) trunk_fwd_kernel(const TrunkArgs a) {
+// Which accumulator rows a thread drains.  Slot 0: row 32*(warp%4) + lane of M-tile warp/4 (M = 128: row i = TMEM lane i).
+// Slot 1 (warps 0 and 1 only): M-tile 2 is an M = 64 MMA whose row i lives in TMEM lane 32*(i/16) + i%16
+// (tools/probes/wgrad_desc_probe.cu), so lanes 0-15 of warp w hold rows 16w..16w+15 = padded positions 256 + 16w + lane;
+// rows 32..63 of that tile lie past the image and are never read.
+struct TrunkSlots {
+  int pos[2], pix[2];
+  bool valid[2], has2;
+  uint32_t tcol[2];   // TMEM address (lane quarter | column of layer 0) of the slot's accumulator row
+  int tile[2];
+};
+__device__ __forceinline__ TrunkSlots trunk_slots(int warp, int lane) {
+  TrunkSlots s;
+  const int qd = warp & 3, h = warp >> 2;
+  const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+  s.has2 = (h == 0 && qd < 2);
+  const int q[2] = {h * 128 + qd * 32 + lane, 256 + 16 * qd + lane};
+  s.tile[0] = h; s.tile[1] = 2;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int y = q[i] / TPW, x = q[i] - y * TPW;
+    s.valid[i] = (x < TW) && (y < TW);
+    s.pos[i] = q[i] + TPW + 1;
+    s.pix[i] = s.valid[i] ? y * TW + x : 0;
+    s.tcol[i] = lane_base + s.tile[i] * T_COLS_MT;
+  }
+  s.valid[1] = s.valid[1] && s.has2 && lane < 16;
+  return s;
+}
+
+__global__ void __launch_bounds__(T_THREADS) trunk_fwd_kernel(const TrunkArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t mbar[TNMT];  // one per M-tile: its epilogue starts while the other tiles' MMAs run
   __shared__ uint32_t tmem_slot;
@@ -150,36 +182,25 @@ __global__ void __launch_bounds__(128) trunk_fwd_kernel(const TrunkArgs a) {
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), T_TMEM_COLS);
   if (tid == 32) { for (int i = 0; i < TNMT; ++i) mbar_init(smem_u32(&mbar[i]), 1); }
   // zero the whole concat tile: halo ring and pad columns are the convolution's zero padding
-  for (int i = tid; i < T_X_BYTES / 16; i += 128) st_shared16(sX + i * 16, make_uint4(0, 0, 0, 0));
+  for (int i = tid; i < T_X_BYTES / 16; i += T_THREADS) st_shared16(sX + i * 16, make_uint4(0, 0, 0, 0));
   __syncthreads();
   // image -> planes 0,1 (interior positions), weights of layer 0 -> buffer 0
-  for (int i = tid; i < 256 * 2; i += 128) {
+  for (int i = tid; i < 256 * 2; i += T_THREADS) {
     const int pix = i >> 1, pl = i & 1;
     const int y = pix >> 4, x = pix & 15;
     cp_async16(sX + pl * TPB + ((y + 1) * TPW + x + 1) * 16,
                a.x_in + ((size_t)n * 256 + pix) * a.in_pitch + a.in_coff + pl * 8, 16);
   }
-  for (int i = tid; i < 18 * 5 * TF; i += 128) cp_async16(sW + i * 16, reinterpret_cast<const uint4*>(a.w) + i, 16);
+  for (int i = tid; i < 18 * 5 * TF; i += T_THREADS) cp_async16(sW + i * 16, reinterpret_cast<const uint4*>(a.w) + i, 16);
   cp_async_wait_all();
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const TrunkSlots S = trunk_slots(warp, lane);
 
-  // this thread's three output positions (one per M-tile)
-  int pos[TNMT], pix[TNMT];
-  bool valid[TNMT];
-#pragma unroll
-  for (int mt = 0; mt < TNMT; ++mt) {
-    const int q = mt * 128 + tid;
-    const int y = q / TPW, x = q - y * TPW;
-    valid[mt] = (x < TW) && (y < TW);
-    pos[mt] = q + TPW + 1;
-    pix[mt] = y * TW + x;
-  }
-  uint4 xr[TNMT][2];  // RRDB input at this thread's positions (bf16 x 16)
+  uint4 xr[2][2];  // RRDB input at this thread's positions (bf16 x 16)
   const int total = a.R * 15;
   size_t w_elem = 0;  // element offset of the current slice's weight image
   // Input-stationary schedule: as soon as slice j of the concat buffer (x, o1..o4) exists, ONE round
@@ -193,12 +214,12 @@ __global__ void __launch_bounds__(128) trunk_fwd_kernel(const TrunkArgs a) {
     const uint32_t wb = sW + (L & 1) * T_W_BYTES;
     if (k == 1 && d == 0) {
 #pragma unroll
-      for (int mt = 0; mt < TNMT; ++mt) {
-        xr[mt][0] = ld_shared16(sX + pos[mt] * 16);
-        xr[mt][1] = ld_shared16(sX + TPB + pos[mt] * 16);
+      for (int sl = 0; sl < 2; ++sl) {
+        xr[sl][0] = ld_shared16(sX + S.pos[sl] * 16);
+        xr[sl][1] = ld_shared16(sX + TPB + S.pos[sl] * 16);
       }
     }
-    // ---- MMA round of slice j: warp w issues M-tile w (9 taps, K = 16 channels, N = Nj)
+    // ---- MMA round of slice j (9 taps, K = 16 channels, N = Nj per M-tile)
     TR_TRACE(0);
     trunk_issue_round(a.order, warp, tmem, sX, wb, j, Nj, mbar);
     TR_TRACE(1);
@@ -208,64 +229,67 @@ __global__ void __launch_bounds__(128) trunk_fwd_kernel(const TrunkArgs a) {
       const int Nn = (k == 5) ? 5 * TF : Nj - TF;
       const uint4* src = reinterpret_cast<const uint4*>(a.w + w_next);
       const uint32_t dst = sW + ((L + 1) & 1) * T_W_BYTES;
-      for (int i = tid; i < 18 * Nn; i += 128) cp_async16(dst + i * 16, src + i, 16);
+      for (int i = tid; i < 18 * Nn; i += T_THREADS) cp_async16(dst + i * 16, src + i, 16);
     }
     float bias[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) bias[j] = __ldg(a.bias + (size_t)L * 16 + j);
-    // ---- epilogue, M-tile by M-tile as their MMAs complete
+    for (int q = 0; q < 16; ++q) bias[q] = __ldg(a.bias + (size_t)L * 16 + q);
+    // ---- epilogue of this thread's rows, M-tile by M-tile as their MMAs complete
     const bool saving = a.db_bufs && n < a.save_count;  // activations are kept for the first save_count samples only
     bf16* save_cur = saving ? a.db_bufs[db] : nullptr;
     bf16* save_next = (saving && db + 1 < a.R * 3) ? a.db_bufs[db + 1] : nullptr;
 #pragma unroll
-    for (int mt = 0; mt < TNMT; ++mt) {
-      mbar_wait(smem_u32(&mbar[mt]), L & 1);
-      TR_TRACE(2 + mt);
+    for (int sl = 0; sl < 2; ++sl) {
+      if (sl == 1 && !S.has2) break;  // warp-uniform
+      mbar_wait(smem_u32(&mbar[S.tile[sl]]), L & 1);
+      TR_TRACE(2 + 2 * sl);
       tc_fence_after();
       float v[16];
-      tmem_ld16(tmem + lane_base + mt * T_COLS_MT + j * TF, v);
-      if (!valid[mt]) continue;
+      tmem_ld16(tmem + S.tcol[sl] + j * TF, v);
+      if (S.valid[sl]) {
+        const int pos = S.pos[sl], pix = S.pix[sl];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] += bias[j];
-      if (k < 5) {
+        for (int q = 0; q < 16; ++q) v[q] += bias[q];
+        if (k < 5) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * G_SLOPE;
-        const uint4 lo = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-        const uint4 hi = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
-        st_shared16(sX + (2 * k) * TPB + pos[mt] * 16, lo);
-        st_shared16(sX + (2 * k + 1) * TPB + pos[mt] * 16, hi);
-        if (save_cur) {
-          uint4* g = reinterpret_cast<uint4*>(save_cur + ((size_t)n * 256 + pix[mt]) * 80 + 16 * k);
-          g[0] = lo; g[1] = hi;
-        }
-      } else {
-        float xo[16];
-        unpack8(ld_shared16(sX + pos[mt] * 16), xo);
-        unpack8(ld_shared16(sX + TPB + pos[mt] * 16), xo + 8);
+          for (int q = 0; q < 16; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * G_SLOPE;
+          const uint4 lo = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+          const uint4 hi = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+          st_shared16(sX + (2 * k) * TPB + pos * 16, lo);
+          st_shared16(sX + (2 * k + 1) * TPB + pos * 16, hi);
+          if (save_cur) {
+            uint4* g = reinterpret_cast<uint4*>(save_cur + ((size_t)n * 256 + pix) * 80 + 16 * k);
+            g[0] = lo; g[1] = hi;
+          }
+        } else {
+          float xo[16];
+          unpack8(ld_shared16(sX + pos * 16), xo);
+          unpack8(ld_shared16(sX + TPB + pos * 16), xo + 8);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaf(RES, v[j], xo[j]);
-        if (d == 2) {
-          float xq[16];
-          unpack8(xr[mt][0], xq);
-          unpack8(xr[mt][1], xq + 8);
+          for (int q = 0; q < 16; ++q) v[q] = fmaf(RES, v[q], xo[q]);
+          if (d == 2) {
+            float xq[16];
+            unpack8(xr[sl][0], xq);
+            unpack8(xr[sl][1], xq + 8);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fmaf(RES, v[j], xq[j]);
-        }
-        const uint4 lo = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-        const uint4 hi = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
-        st_shared16(sX + pos[mt] * 16, lo);
-        st_shared16(sX + TPB + pos[mt] * 16, hi);
-        if (L + 1 == total) {
-          uint4* g = reinterpret_cast<uint4*>(a.y_out + ((size_t)n * 256 + pix[mt]) * a.out_pitch);
-          g[0] = lo; g[1] = hi;
-        } else if (save_next) {
-          uint4* g = reinterpret_cast<uint4*>(save_next + ((size_t)n * 256 + pix[mt]) * 80);
-          g[0] = lo; g[1] = hi;
+            for (int q = 0; q < 16; ++q) v[q] = fmaf(RES, v[q], xq[q]);
+          }
+          const uint4 lo = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+          const uint4 hi = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+          st_shared16(sX + pos * 16, lo);
+          st_shared16(sX + TPB + pos * 16, hi);
+          if (L + 1 == total) {
+            uint4* g = reinterpret_cast<uint4*>(a.y_out + ((size_t)n * 256 + pix) * a.out_pitch);
+            g[0] = lo; g[1] = hi;
+          } else if (save_next) {
+            uint4* g = reinterpret_cast<uint4*>(save_next + ((size_t)n * 256 + pix) * 80);
+            g[0] = lo; g[1] = hi;
+          }
         }
       }
+      TR_TRACE(3 + 2 * sl);
     }
     w_elem = w_next;
-    TR_TRACE(5);
     cp_async_wait_all();
     fence_proxy_async();
     tc_fence_before();
@@ -295,7 +319,7 @@ struct TrunkBwdArgs {
   int order;
 };
 
-__global__ void __launch_bounds__(128) trunk_bwd_kernel(const TrunkBwdArgs a) {
+__global__ void __launch_bounds__(T_THREADS) trunk_bwd_kernel(const TrunkBwdArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t mbar[TNMT];  // one per M-tile: its epilogue starts while the other tiles' MMAs run
   __shared__ uint32_t tmem_slot;
@@ -307,37 +331,27 @@ __global__ void __launch_bounds__(128) trunk_bwd_kernel(const TrunkBwdArgs a) {
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), T_TMEM_COLS);
   if (tid == 32) { for (int i = 0; i < TNMT; ++i) mbar_init(smem_u32(&mbar[i]), 1); }
-  for (int i = tid; i < T_X_BYTES / 16; i += 128) st_shared16(sX + i * 16, make_uint4(0, 0, 0, 0));
+  for (int i = tid; i < T_X_BYTES / 16; i += T_THREADS) st_shared16(sX + i * 16, make_uint4(0, 0, 0, 0));
   // weights of the LAST block's slice 0 -> buffer 0
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.w + (size_t)(n_db - 1) * T_DB_ELEMS_);
-    for (int i = tid; i < 18 * 5 * TF; i += 128) cp_async16(sW + i * 16, src + i, 16);
+    for (int i = tid; i < 18 * 5 * TF; i += T_THREADS) cp_async16(sW + i * 16, src + i, 16);
   }
-  int pos[TNMT], pix[TNMT];
-  bool valid[TNMT];
-#pragma unroll
-  for (int mt = 0; mt < TNMT; ++mt) {
-    const int q = mt * 128 + tid;
-    const int y = q / TPW, x = q - y * TPW;
-    valid[mt] = (x < TW) && (y < TW);
-    pos[mt] = q + TPW + 1;
-    pix[mt] = valid[mt] ? y * TW + x : 0;
-  }
+  const TrunkSlots S = trunk_slots(warp, lane);
   // incoming gradient at this thread's positions (bf16 x 16 per position)
-  uint4 gin[TNMT][2], gr[TNMT][2];
+  uint4 gin[2][2], gr[2][2];
 #pragma unroll
-  for (int mt = 0; mt < TNMT; ++mt) {
-    const uint4* g = reinterpret_cast<const uint4*>(a.g_in + ((size_t)n * 256 + pix[mt]) * TF);
-    gin[mt][0] = valid[mt] ? g[0] : make_uint4(0, 0, 0, 0);
-    gin[mt][1] = valid[mt] ? g[1] : make_uint4(0, 0, 0, 0);
-    gr[mt][0] = gr[mt][1] = make_uint4(0, 0, 0, 0);
+  for (int sl = 0; sl < 2; ++sl) {
+    const uint4* g = reinterpret_cast<const uint4*>(a.g_in + ((size_t)n * 256 + S.pix[sl]) * TF);
+    gin[sl][0] = S.valid[sl] ? g[0] : make_uint4(0, 0, 0, 0);
+    gin[sl][1] = S.valid[sl] ? g[1] : make_uint4(0, 0, 0, 0);
+    gr[sl][0] = gr[sl][1] = make_uint4(0, 0, 0, 0);
   }
   cp_async_wait_all();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
 
   int L = 0;
   for (int db = n_db - 1; db >= 0; --db) {
@@ -347,23 +361,23 @@ __global__ void __launch_bounds__(128) trunk_bwd_kernel(const TrunkBwdArgs a) {
     bf16* dbuf = a.d_bufs[db];
     if (d == 2) {
 #pragma unroll
-      for (int mt = 0; mt < TNMT; ++mt) { gr[mt][0] = gin[mt][0]; gr[mt][1] = gin[mt][1]; }
+      for (int sl = 0; sl < 2; ++sl) { gr[sl][0] = gin[sl][0]; gr[sl][1] = gin[sl][1]; }
     }
     // slice 0 of D: dz5 = 0.2 * s_in * g
 #pragma unroll
-    for (int mt = 0; mt < TNMT; ++mt) {
-      if (!valid[mt]) continue;
+    for (int sl = 0; sl < 2; ++sl) {
+      if (!S.valid[sl]) continue;
       float g[16];
-      unpack8(gin[mt][0], g);
-      unpack8(gin[mt][1], g + 8);
+      unpack8(gin[sl][0], g);
+      unpack8(gin[sl][1], g + 8);
       const float sc = RES * s_in;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) g[j] *= sc;
+      for (int q = 0; q < 16; ++q) g[q] *= sc;
       const uint4 lo = make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7]));
       const uint4 hi = make_uint4(pack2(g[8], g[9]), pack2(g[10], g[11]), pack2(g[12], g[13]), pack2(g[14], g[15]));
-      st_shared16(sX + pos[mt] * 16, lo);
-      st_shared16(sX + TPB + pos[mt] * 16, hi);
-      uint4* gd = reinterpret_cast<uint4*>(dbuf + ((size_t)n * 256 + pix[mt]) * 80);
+      st_shared16(sX + S.pos[sl] * 16, lo);
+      st_shared16(sX + TPB + S.pos[sl] * 16, hi);
+      uint4* gd = reinterpret_cast<uint4*>(dbuf + ((size_t)n * 256 + S.pix[sl]) * 80);
       gd[0] = lo; gd[1] = hi;
     }
     fence_proxy_async();
@@ -382,50 +396,51 @@ __global__ void __launch_bounds__(128) trunk_bwd_kernel(const TrunkBwdArgs a) {
         const int Nn = (j == 4) ? 5 * TF : Nj - TF;
         const uint4* src = reinterpret_cast<const uint4*>(a.w + w_next);
         const uint32_t dst = sW + ((L + 1) & 1) * T_W_BYTES;
-        for (int i = tid; i < 18 * Nn; i += 128) cp_async16(dst + i * 16, src + i, 16);
+        for (int i = tid; i < 18 * Nn; i += T_THREADS) cp_async16(dst + i * 16, src + i, 16);
       }
       // mask source for this round (issued before the wait so the latency hides behind the MMAs)
-      uint4 mk[TNMT][2];
+      uint4 mk[2][2];
       if (t < 5) {
 #pragma unroll
-        for (int mt = 0; mt < TNMT; ++mt) {
-          const uint4* m = reinterpret_cast<const uint4*>(fbuf + ((size_t)n * 256 + pix[mt]) * 80 + TF * (5 - t));
-          mk[mt][0] = m[0]; mk[mt][1] = m[1];
+        for (int sl = 0; sl < 2; ++sl) {
+          const uint4* m = reinterpret_cast<const uint4*>(fbuf + ((size_t)n * 256 + S.pix[sl]) * 80 + TF * (5 - t));
+          if (sl == 0 || S.has2) { mk[sl][0] = m[0]; mk[sl][1] = m[1]; }
         }
       }
 #pragma unroll
-      for (int mt = 0; mt < TNMT; ++mt) {
-        mbar_wait(smem_u32(&mbar[mt]), L & 1);
+      for (int sl = 0; sl < 2; ++sl) {
+        if (sl == 1 && !S.has2) break;  // warp-uniform
+        mbar_wait(smem_u32(&mbar[S.tile[sl]]), L & 1);
         tc_fence_after();
         float v[16];
-        tmem_ld16(tmem + lane_base + mt * T_COLS_MT + j * TF, v);
-        if (!valid[mt]) continue;
+        tmem_ld16(tmem + S.tcol[sl] + j * TF, v);
+        if (!S.valid[sl]) continue;
         if (t < 5) {
           float m[16];
-          unpack8(mk[mt][0], m);
-          unpack8(mk[mt][1], m + 8);
+          unpack8(mk[sl][0], m);
+          unpack8(mk[sl][1], m + 8);
 #pragma unroll
           for (int q = 0; q < 16; ++q) v[q] *= (m[q] > 0.f ? 1.f : G_SLOPE);
           const uint4 lo = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
           const uint4 hi = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
-          st_shared16(sX + (2 * t) * TPB + pos[mt] * 16, lo);
-          st_shared16(sX + (2 * t + 1) * TPB + pos[mt] * 16, hi);
-          uint4* gd = reinterpret_cast<uint4*>(dbuf + ((size_t)n * 256 + pix[mt]) * 80 + TF * t);
+          st_shared16(sX + (2 * t) * TPB + S.pos[sl] * 16, lo);
+          st_shared16(sX + (2 * t + 1) * TPB + S.pos[sl] * 16, hi);
+          uint4* gd = reinterpret_cast<uint4*>(dbuf + ((size_t)n * 256 + S.pix[sl]) * 80 + TF * t);
           gd[0] = lo; gd[1] = hi;
         } else {
           float g[16];
-          unpack8(gin[mt][0], g);
-          unpack8(gin[mt][1], g + 8);
+          unpack8(gin[sl][0], g);
+          unpack8(gin[sl][1], g + 8);
 #pragma unroll
           for (int q = 0; q < 16; ++q) v[q] = fmaf(s_in, g[q], v[q]);
           if (d == 0) {
-            unpack8(gr[mt][0], g);
-            unpack8(gr[mt][1], g + 8);
+            unpack8(gr[sl][0], g);
+            unpack8(gr[sl][1], g + 8);
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] += g[q];
           }
-          gin[mt][0] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-          gin[mt][1] = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+          gin[sl][0] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+          gin[sl][1] = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
         }
       }
       w_elem = w_next;
@@ -437,10 +452,10 @@ __global__ void __launch_bounds__(128) trunk_bwd_kernel(const TrunkBwdArgs a) {
     }
   }
 #pragma unroll
-  for (int mt = 0; mt < TNMT; ++mt) {
-    if (!valid[mt]) continue;
-    uint4* g = reinterpret_cast<uint4*>(a.g_out + ((size_t)n * 256 + pix[mt]) * TF);
-    g[0] = gin[mt][0]; g[1] = gin[mt][1];
+  for (int sl = 0; sl < 2; ++sl) {
+    if (!S.valid[sl]) continue;
+    uint4* g = reinterpret_cast<uint4*>(a.g_out + ((size_t)n * 256 + S.pix[sl]) * TF);
+    g[0] = gin[sl][0]; g[1] = gin[sl][1];
   }
   if (warp == 0) tmem_dealloc(tmem, T_TMEM_COLS);
 }
@@ -499,7 +514,7 @@ int trunk_bwd_fused(const void* g_in, void* g_out, void* const* fwd_bufs_dev, vo
   a.w = (const bf16*)w_slices; a.R = R; a.B = B; a.order = g_tune[3];
   const double px = (double)B * 256;
   Prof prof(PC_DENSE_UMMA, 2.0 * px * 16.0 * 9.0 * 16.0 * 15.0 * 3.0 * R, px * 80.0 * 2.0 * 2.0 * 3.0 * R, st);
-  trunk_bwd_kernel<<<B, 128, T_SMEM, st>>>(a);
+  trunk_bwd_kernel<<<B, T_THREADS, T_SMEM, st>>>(a);
   DG_LAUNCH_CHECK();
   return 0;
 }
@@ -527,7 +542,7 @@ int trunk_fwd_fused(const void* x_in, int in_pitch, int in_coff, void* y_out, in
   if (tracing) { cudaMalloc(&a.trace, 32 * 8 * 8); cudaMemset(a.trace, 0, 32 * 8 * 8); }
   const double px = (double)B * 256;
   Prof prof(PC_DENSE_UMMA, 2.0 * px * 16.0 * 9.0 * 16.0 * 15.0 * 3.0 * R, px * 16.0 * 2.0 * 2.0, st);
-  trunk_fwd_kernel<<<B, 128, T_SMEM, st>>>(a);
+  trunk_fwd_kernel<<<B, T_THREADS, T_SMEM, st>>>(a);
   DG_LAUNCH_CHECK();
   if (tracing) {
     unsigned long long h[32 * 8];
@@ -537,10 +552,10 @@ int trunk_fwd_fused(const void* x_in, int in_pitch, int in_coff, void* y_out, in
     double sum[7] = {0};
     for (int l = 0; l < 32; ++l) {
       const unsigned long long* e = h + l * 8;
-      // [issue, wait mt0, wait mt1, wait mt2 (incl. epilogues before), epilogue tail, sync]
+      // [issue, ->M-tile 0 ready, its epilogue, ->M-tile 2 ready, its epilogue, sync] seen by thread 0 (warp 0 drains tiles 0 and 2)
       for (int k = 0; k < 6; ++k) sum[k] += (double)(e[k + 1] - e[k]);
     }
-    fprintf(stderr, "[trunk trace] order %d, layers 30..61 of CTA 0, mean ns: issue %.0f | ->mt0 ready %.0f | epi0+->mt1 %.0f | epi1+->mt2 %.0f | epi2 %.0f | sync %.0f | layer %.0f\n",
+    fprintf(stderr, "[trunk trace] order %d, layers 30..61 of CTA 0, mean ns: issue %.0f | ->mt0 ready %.0f | epi0 %.0f | ->mt2 ready %.0f | epi2 %.0f | sync %.0f | layer %.0f\n",
             a.order, sum[0] / 32, sum[1] / 32, sum[2] / 32, sum[3] / 32, sum[4] / 32, sum[5] / 32, (double)(h[31 * 8 + 6] - h[0]) / 32);
   }
   return 0;
