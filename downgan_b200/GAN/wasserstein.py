@@ -77,6 +77,18 @@ class _FlatAdam:
                                             _lib.stream_ptr()))
         self.module.mark_params_changed()
 
+    def step_fused(self, bucket, grad_scale: float) -> None:
+        """Data parallel: sum-all-reduce of the symmetric gradient bucket + this Adam step in one kernel (dp.FusedBucket)."""
+        flat = self.module.flat_params()
+        if self.exp_avg is None or self.exp_avg.data_ptr() == 0 or self.exp_avg.numel() != flat.numel():
+            self.exp_avg = torch.zeros_like(flat)
+            self.exp_avg_sq = torch.zeros_like(flat)
+        g = self._group()
+        self.step_count += 1
+        b1, b2 = g["betas"]
+        bucket.step(flat, self.exp_avg, self.exp_avg_sq, g["lr"], b1, b2, g["eps"], self.step_count, grad_scale)
+        self.module.mark_params_changed()
+
     def sync_to_optimizer(self) -> None:
         """Mirror the fused state into ``optimizer.state`` so ``optimizer.state_dict()`` is meaningful."""
         if self.optimizer is None or self.exp_avg is None:
@@ -107,7 +119,7 @@ class WassersteinGAN:
         self.last_generator: Optional[torch.Tensor] = None  # 8 floats on device, see GENERATOR_SCALARS
         self._c_scal = None
         self._g_scal = None
-        self.lookahead = True  # _train_epoch computes the fakes of the critic steps between two generator updates in one pass
+        self.lookahead = os.environ.get("DG_NO_LOOKAHEAD", "0") != "1"  # _train_epoch computes the fakes of the critic steps between two generator updates in one pass
         # data parallel: classifier-gradient all-reduce started while the conv weight gradients still run (DG_OVERLAP_AR=1).
         # Off by default: measured 0.4 % slower than one all-reduce per iteration on 2 GPUs (two collectives + one more call
         # cost more than hiding 3.3 MB over NVLink saves), results identical (tools/dp_overlap_check.py).
@@ -154,12 +166,15 @@ class WassersteinGAN:
             g, c = self._handles(coarse)
             if self._c_scal is None or self._c_scal.device != self.device:
                 self._c_scal = torch.zeros(8, device=self.device)
-            grads = self.C.flat_grads()
-            hyp = self._hyper()
-            lib = _lib.load()
             # data parallel: the classifier gradients (74 % of the bucket) are final before the conv weight gradients,
             # which still run on the handle's side stream - their all-reduce starts while those finish
             overlap = dp.world_size() > 1 and self.overlap_allreduce
+            # default exchange: the flat gradients are written into a symmetric-memory bucket and ONE kernel does the
+            # sum over NVLink peer memory + Adam (dp.FusedBucket); None = one rank, switched off, or unavailable -> NCCL
+            bucket = None if overlap else dp.fused_bucket(self.C)
+            grads = self.C.flat_grads()
+            hyp = self._hyper()
+            lib = _lib.load()
             _lib.check(lib.dg_critic_defer_conv_grads(c, 1 if overlap else 0))
             if _fake_offset is None:
                 _lib.check(lib.dg_critic_step(g, c, hyp, coarse.data_ptr(), fine.data_ptr(), alpha.data_ptr(), b,
@@ -173,9 +188,12 @@ class WassersteinGAN:
                 _lib.check(lib.dg_critic_step_finish(c, grads.data_ptr(), _lib.stream_ptr()))
                 scale = self._allreduce(grads[:off])
                 work.wait()
-            else:
+            elif bucket is None:
                 scale = self._allreduce(grads)
-            self._c_adam.step(grads, scale)
+            if bucket is not None:
+                self._c_adam.step_fused(bucket, 1.0 / dp.world_size())
+            else:
+                self._c_adam.step(grads, scale)
         self.last_critic = self._c_scal
 
     def _generator_lookahead(self, coarse_all: torch.Tensor, save_first: int = 0, first: Optional[tuple] = None) -> None:
@@ -204,6 +222,7 @@ class WassersteinGAN:
             g, c = self._handles(coarse)
             if self._g_scal is None or self._g_scal.device != self.device:
                 self._g_scal = torch.zeros(8, device=self.device)
+            bucket = dp.fused_bucket(self.G)
             grads = self.G.flat_grads()
             hyp = self._hyper()
             if _saved_forward:
@@ -212,8 +231,11 @@ class WassersteinGAN:
             else:
                 _lib.check(_lib.load().dg_generator_step(g, c, hyp, coarse.data_ptr(), fine.data_ptr(), b,
                                                          grads.data_ptr(), self._g_scal.data_ptr(), _lib.stream_ptr()))
-            scale = self._allreduce(grads)
-            self._g_adam.step(grads, scale)
+            if bucket is not None:
+                self._g_adam.step_fused(bucket, 1.0 / dp.world_size())
+            else:
+                scale = self._allreduce(grads)
+                self._g_adam.step(grads, scale)
         self.last_generator = self._g_scal
 
     def _metrics_batch(self, coarse, fine, _fake_offset: Optional[int] = None) -> torch.Tensor:

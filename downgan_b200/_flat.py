@@ -68,6 +68,18 @@ class FlatParamsMixin:
         self.flat_params()
         return self._flat_grad
 
+    def use_grad_bucket(self, bucket: torch.Tensor) -> None:
+        """Make `bucket` (same size / device, e.g. a symmetric-memory tensor for the fused data-parallel exchange,
+        downgan_b200/dp.py) the flat gradient buffer; `p.grad` views are re-pointed if they were bound."""
+        flat = self.flat_params()
+        if bucket.numel() != flat.numel() or bucket.device != flat.device or bucket.dtype != torch.float32:
+            raise ValueError("gradient bucket does not match the flat parameter buffer")
+        bound = self._param_list()[0].grad is not None
+        bucket.copy_(self._flat_grad)
+        self._flat_grad = bucket
+        if bound:
+            self.bind_grads()
+
     def param_offsets(self) -> List[int]:
         self.flat_params()
         return list(self._offsets)

@@ -38,6 +38,14 @@ class Hyper(C.Structure):
 
 
 _P = C.c_void_p
+
+
+class DpPeers(C.Structure):
+    """dg_dp_peers (include/downgan_b200.h): peer-mapped gradient buckets and flag blocks of every rank."""
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("grad_ptrs", C.c_void_p * 8), ("flag_ptrs", C.c_void_p * 8),
+                ("grad_multicast", C.c_void_p)]
+
+
 _SIGNATURES = {
     # name: (restype, argtypes)
     "dg_last_error": (C.c_char_p, []),
@@ -65,6 +73,8 @@ _SIGNATURES = {
     "dg_l1_loss": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P, _P, _P]),
     "dg_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                C.c_int, C.c_float, _P]),
+    "dg_dp_allreduce_adam": (C.c_int, [C.POINTER(DpPeers), _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
+                                       C.c_int, C.c_float, C.c_uint, _P]),
     "dg_critic_step": (C.c_int, [_P, _P, C.POINTER(Hyper), _P, _P, _P, C.c_int, _P, _P, _P]),
     "dg_generator_step": (C.c_int, [_P, _P, C.POINTER(Hyper), _P, _P, C.c_int, _P, _P, _P]),
     "dg_critic_defer_conv_grads": (C.c_int, [_P, C.c_int]),

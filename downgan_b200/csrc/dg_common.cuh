@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 #include <string>
@@ -21,6 +22,12 @@ void set_error(const char* fmt, ...);
 const char* last_error();
 extern std::atomic<long long> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+// DG_SYNC_CHECK=1 (diagnostic): every launch check synchronises the device, so an asynchronous fault is reported at the
+// launch site of the kernel that caused it, whatever stream or launch API it used.
+inline bool sync_check() {
+  static const bool on = getenv("DG_SYNC_CHECK") != nullptr;
+  return on;
+}
 
 #define DG_CUDA(expr)                                                                   \
   do {                                                                                  \
@@ -48,7 +55,7 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 #define DG_LAUNCH_CHECK()                                                                \
   do {                                                                                   \
     dg::count_launch();                                                                  \
-    cudaError_t e__ = cudaPeekAtLastError();                                             \
+    cudaError_t e__ = dg::sync_check() ? cudaDeviceSynchronize() : cudaPeekAtLastError(); \
     if (e__ != cudaSuccess) {                                                            \
       dg::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
       return DG_ERR_CUDA;                                                                \

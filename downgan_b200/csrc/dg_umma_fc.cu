@@ -243,8 +243,19 @@ __global__ void __launch_bounds__(FCU_THREADS) fc_wgrad_umma_kernel(const FcuArg
   const uint32_t tmem = tmem_slot;
   if (tid == 0) {
     const uint32_t idesc = instr_desc(128, FCU_KT, 1, 1);
-    uint64_t ad = smem_desc(sA, 128, PB), bd = smem_desc(sB, 128, PB);
-    for (int ks = 0; ks < a.rows / 16; ++ks, ad += 16, bd += 16) umma_f16(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+    // Descriptors are rebuilt from 32-bit parts per K-step and the loop is not unrolled: with 64-bit descriptor increments
+    // ptxas 12.9 unrolled this loop by four and dropped the instruction that writes the HIGH word of the B descriptor pair
+    // (both descriptors share it), so the MMA took a stale kernel-parameter word as its stride field - an illegal shared
+    // memory access whose appearance depended on the address of `x` (tools/sass_desc_check.py finds the pattern; it runs in
+    // tests/test_abi.py on every build).
+    const uint32_t hi = ((PB >> 4) & 0x3FFFu) | (1u << 14);
+    const uint32_t lo_a = ((sA >> 4) & 0x3FFFu) | (8u << 16), lo_b = ((sB >> 4) & 0x3FFFu) | (8u << 16);
+#pragma unroll 1
+    for (int ks = 0; ks < a.rows / 16; ++ks) {
+      const uint64_t ad = ((uint64_t)hi << 32) | (uint64_t)(lo_a + 16u * ks);
+      const uint64_t bd = ((uint64_t)hi << 32) | (uint64_t)(lo_b + 16u * ks);
+      umma_f16(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+    }
     umma_commit(smem_u32(&mbar));
   }
   __syncwarp();

@@ -145,6 +145,23 @@ int dg_l1_loss(const float* a, const float* b, int64_t n, float scale, float* lo
 int dg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                  float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
 
+/* ---- data-parallel optimizer step (one process per GPU; replaces the host's dist.all_reduce(flat_grads) followed by
+ * C_optimizer.step() / G_optimizer.step(), wasserstein.py:55,83 under data parallelism): ONE kernel sums the flat gradient
+ * bucket over all ranks through NVLink peer memory (two-shot: every rank reduces one shard from all buckets and publishes
+ * it to all buckets; NVSwitch multimem.ld_reduce / multimem.st when grad_multicast is set) and applies Adam with
+ * grad_scale (1/world).  Every rank must call it in the same step with the same epoch (a counter the caller increments
+ * per call and per flag block, starting at 1).  grad_ptrs[r] / flag_ptrs[r]: rank r's bucket / flag block as mapped into
+ * THIS process (symmetric memory; [rank] are the local ones); a flag block is 32 zero-initialised uint32.  The local bucket
+ * holds the global sum afterwards.  world <= 8 (one node).  Waits inside the kernel are bounded (trap after ~60 s). */
+typedef struct dg_dp_peers {
+  int rank, world;
+  void* grad_ptrs[8];
+  void* flag_ptrs[8];
+  void* grad_multicast; /* multicast mapping of the bucket, or NULL: plain peer loads / stores */
+} dg_dp_peers;
+int dg_dp_allreduce_adam(const dg_dp_peers* peers, float* params, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                         float beta1, float beta2, float eps, int step, float grad_scale, unsigned int epoch, void* stream);
+
 /* ---- fused iterations ---------------------------------------------------
  * _critic_train_iteration (wasserstein.py:27-52, up to but excluding
  * C_optimizer.step): generator forward (no graph), critic on real / fake /

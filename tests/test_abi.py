@@ -113,3 +113,22 @@ def test_product_does_not_import_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", s, flags=re.M):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_sass_descriptor_pairs_are_written():
+    """tools/sass_desc_check.py on every built object: each tcgen05.mma descriptor operand is a 64-bit uniform register pair, and
+    both halves must be written by the kernel's own arithmetic.  (Round 2: ptxas dropped the high-word update of one pair in an
+    unrolled loop of fc_wgrad_umma_kernel; the MMA then read a stale parameter word as its stride - an illegal shared-memory
+    access that came and went with the address of an input buffer.)"""
+    import glob
+    import shutil
+    import subprocess
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    objs = sorted(glob.glob(os.path.join(root, "downgan_b200", "csrc", "*.o")))
+    if not objs:
+        pytest.skip("no object files (library built elsewhere)")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "sass_desc_check.py"), *objs], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
