@@ -140,6 +140,10 @@ struct WgradOp {
   // channel-block ops (dg_umma_wgrad_ws.cu): this op covers input channels [dw_ci_off, dw_ci_off + Ci) of a layer with
   // dw_ci_total input channels; dw rows are tap * dw_ci_total + dw_ci_off + ci   (0 / 0: the op is the whole layer)
   int dw_ci_total = 0, dw_ci_off = 0;
+  // column-strip ops (dg_umma_wgrad_ws.cu): Wout / Win are the widths of ONE strip of a layer whose maps are Wout_full
+  // (Wout_full * stride) columns wide; the strip starts at output column col0.  x and dy still point at the full tensors.
+  // dW is accumulated, so the strips of a layer simply add up.  (0 / 0: the op covers whole rows.)
+  int Wout_full = 0, col0 = 0;
 };
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }

@@ -124,6 +124,27 @@ int run_wgrad(const WgradOp& w0, cudaStream_t st) {
       return 0;
     }
   }
+  // Maps too wide for one TMA box / one shared-memory stage (the 256-wide layers of cfg-4: conv3.0, the critic's stride-2
+  // layers on 256x256 .. 64x64 maps at 32 .. 128 channels): 2 or 4 column strips, each a launch of the TMA-fed kernel that
+  // adds into the same dW.
+  if (g_tune[2] && w.x.bf && w.dy.bf && w.dw_ci_total == 0 && w.Wout_full == 0 && !wgrad_ws_supported(w) && w.Ci >= 16 && w.Ci <= 128 &&
+      (w.Ci & (w.Ci - 1)) == 0 && w.Co % 16 == 0) {
+    for (int ns = 2; ns <= 8; ns *= 2) {
+      if (w.Wout % ns) break;
+      WgradOp o = w;
+      o.Wout_full = w.Wout; o.Wout = w.Wout / ns; o.Win = w.Win / ns; o.col0 = 0; o.dbias = nullptr;
+      if (!wgrad_ws_supported(o)) continue;
+      for (int k = 0; k < ns; ++k) {
+        o.col0 = k * o.Wout;
+        DG_TRY(wgrad_ws(o, st));
+      }
+      if (w.dbias) {
+        const int nb = (w.dbias_B > 0 && w.dbias_B < w.B) ? w.dbias_B : w.B;
+        DG_TRY(colsum(w.dy, (size_t)nb * w.Hout * w.Wout, w.Co, w.dbias, st));
+      }
+      return 0;
+    }
+  }
   // bias gradient over a leading part of the batch: only the first-layer tcgen05 kernel folds it in; elsewhere it is
   // a column sum over those samples
   const bool ws_path = g_tune[2] && wgrad_ws_supported(w);

@@ -155,8 +155,8 @@ __device__ __forceinline__ void wgrad_ws_body(const CUtensorMap* mapx_p, const C
 #pragma unroll
         for (int sub = 0; sub < (STRIDE2 ? 4 : 1); ++sub) {
           int cx, cy;
-          if (STRIDE2) { cx = -2 + (sub & 1); cy = 2 * (y0 - 1) + (sub >> 1); }
-          else { cx = -1; cy = y0 - 1; }
+          if (STRIDE2) { cx = 2 * op.col0 - 2 + (sub & 1); cy = 2 * (y0 - 1) + (sub >> 1); }
+          else { cx = op.col0 - 1; cy = y0 - 1; }
           for (int blk = 0; blk < a.nblkx; ++blk)
             tma_load_4d(sx + (sub * a.nblkx + blk) * a.xreg, mapx_p, blk * 64, cx, cy, n, full_bar(s));
         }
@@ -349,23 +349,26 @@ bool plan_ww(const WgradOp& op, WwArgs& a) {
 }
 
 struct MapKeyW {
-  const void* base; int C, W, H, B, pitch, bc, bw, bh, es;
+  const void* base; int C, W, H, B, pitch, bc, bw, bh, es, Wrow;
   bool operator==(const MapKeyW& o) const {
     return base == o.base && C == o.C && W == o.W && H == o.H && B == o.B && pitch == o.pitch && bc == o.bc && bw == o.bw && bh == o.bh &&
-           es == o.es;
+           es == o.es && Wrow == o.Wrow;
   }
 };
 std::vector<std::pair<MapKeyW, CUtensorMap>> g_maps_w;
 std::mutex g_maps_w_mu;
 
 // NHWC view {C, W, H, B} (bf16); box = bc channels x bw x bh (traversal extents) with element stride es on W and H
-int get_map_w(const TV& t, int C, int W, int H, int B, int bc, int bw, int bh, int es, CUtensorMap* out) {
-  MapKeyW k{(const bf16*)t.p + t.coff, C, W, H, B, t.pitch, bc, bw, bh, es};
+// Wrow > W: the view is a column strip [col0, col0 + W) of rows that are Wrow positions long (t already points at col0);
+// columns past the strip read as zero (out-of-bounds fill), rows keep the full pitch
+int get_map_w(const TV& t, int C, int W, int H, int B, int bc, int bw, int bh, int es, CUtensorMap* out, int Wrow = 0) {
+  if (Wrow <= 0) Wrow = W;
+  MapKeyW k{(const bf16*)t.p + t.coff, C, W, H, B, t.pitch, bc, bw, bh, es, Wrow};
   std::lock_guard<std::mutex> lock(g_maps_w_mu);
   for (auto& e : g_maps_w)
     if (e.first == k) { *out = e.second; return 0; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)t.pitch * 2, (cuuint64_t)W * t.pitch * 2, (cuuint64_t)H * W * t.pitch * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)t.pitch * 2, (cuuint64_t)Wrow * t.pitch * 2, (cuuint64_t)H * Wrow * t.pitch * 2};
   cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
   const CUtensorMapSwizzle swz = bc == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : (bc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
@@ -396,8 +399,17 @@ int wgrad_ws(const WgradOp& op, cudaStream_t st) {
   const int s = op.stride;
   const int hrows = (s == 1) ? 2 : 1;
   CUtensorMap mx, md;
-  DG_TRY(get_map_w(op.x, op.Ci, op.Win, op.Hin, op.B, std::min(op.Ci, 64), a.PW * s, (a.TH + hrows) * s, s, &mx));
-  DG_TRY(get_map_w(op.dy, op.Co, op.Wout, op.Hout, op.B, a.NT, a.PW, a.TH, 1, &md));
+  if (op.Wout_full > 0) {
+    // column strip: x keeps the whole rows (the strip's halo columns are real neighbours, only the image border is zero
+    // fill; the kernel starts its boxes at column col0 * stride - 1), dy is the strip alone
+    TV dys = op.dy;
+    dys.coff += op.col0 * op.dy.pitch;
+    DG_TRY(get_map_w(op.x, op.Ci, op.Wout_full * s, op.Hin, op.B, std::min(op.Ci, 64), a.PW * s, (a.TH + hrows) * s, s, &mx));
+    DG_TRY(get_map_w(dys, op.Co, op.Wout, op.Hout, op.B, a.NT, a.PW, a.TH, 1, &md, op.Wout_full));
+  } else {
+    DG_TRY(get_map_w(op.x, op.Ci, op.Win, op.Hin, op.B, std::min(op.Ci, 64), a.PW * s, (a.TH + hrows) * s, s, &mx));
+    DG_TRY(get_map_w(op.dy, op.Co, op.Wout, op.Hout, op.B, a.NT, a.PW, a.TH, 1, &md));
+  }
   const int n_chunks = op.Co / a.NT;
   const size_t smem = (size_t)a.nstage * a.stage_bytes + 1024;
   const int cps = (2 * (smem + 1024) <= 227 * 1024) ? 2 : 1;
@@ -463,6 +475,7 @@ int wgrad_ws_batched(const WgradOp* ops, int n, void* table_dev, std::vector<uns
     WwArgs a;
     if (!plan_ww(ops[i], a)) { set_error("wgrad_ws_batched: op %d unsupported", i); return DG_ERR_INVALID; }
     if (ops[i].Co != a.NT) { set_error("wgrad_ws_batched: op %d needs output-channel chunks", i); return DG_ERR_INVALID; }
+    if (ops[i].Wout_full > 0) { set_error("wgrad_ws_batched: op %d is a column strip", i); return DG_ERR_INVALID; }
     long long S = std::max(1, std::min(S_per_op, a.tiles_total));
     a.tiles_per_cta = (int)((a.tiles_total + S - 1) / S);
     S = (a.tiles_total + a.tiles_per_cta - 1) / a.tiles_per_cta;

@@ -54,6 +54,8 @@ CONV_CASES = [
     (2, 2, 16, 16, 16, 1), (2, 7, 16, 16, 16, 1), (3, 16, 16, 16, 16, 1), (2, 80, 16, 16, 16, 1),
     (2, 16, 64, 32, 32, 1), (1, 16, 2, 64, 64, 1), (2, 16, 16, 64, 64, 2), (2, 32, 32, 32, 32, 2),
     (1, 128, 128, 16, 16, 2), (1, 48, 16, 8, 8, 1), (1, 5, 3, 7, 9, 1), (2, 24, 40, 12, 20, 2),
+    # cfg-4 layers whose rows do not fit one TMA box / shared-memory stage: weight gradients run as column strips
+    (1, 32, 32, 256, 256, 1), (1, 32, 32, 256, 256, 2), (2, 64, 64, 128, 128, 2), (2, 128, 128, 64, 64, 2),
 ]
 
 
