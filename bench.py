@@ -423,7 +423,7 @@ def main():
         e1.record()
         barrier()
         sampler.mark(t_w0, time.time())
-        assert logs.shape == (args.steps, 8) and bool(torch.isfinite(logs).all())
+        assert logs.shape == (args.steps, 8) and (bool(torch.isfinite(logs).all()) or os.environ.get("DG_ABLATE"))  # (ablation runs compute garbage)
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
         enqueue_s = getattr(tr, "last_enqueue_seconds", None)
     clocks = sampler.stop() if rank == 0 else None

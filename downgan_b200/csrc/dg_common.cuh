@@ -24,6 +24,14 @@ extern std::atomic<long long> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 // DG_SYNC_CHECK=1 (diagnostic): every launch check synchronises the device, so an asynchronous fault is reported at the
 // launch site of the kernel that caused it, whatever stream or launch API it used.
+// DG_ABLATE=<bit mask> (diagnostic, tools/ablate.sh): the launchers of the named kernel families return without launching, so
+// a bench run shows how much of the LIVE step (streams overlapped) each family really costs - results are garbage.
+// bit 0 wgrad_ws, 1 wgrad_im2col (first layer), 2 trunk forward, 3 trunk backward, 4 batched dense wgrads, 5 conv_l1,
+// 6 classifier tcgen05 kernels, 7 conv_ig, 8 conv_ws, 9 pack / unpack / adam, 10 column sums
+inline bool ablate(int bit) {
+  static const int mask = getenv("DG_ABLATE") ? atoi(getenv("DG_ABLATE")) : 0;
+  return (mask >> bit) & 1;
+}
 inline bool sync_check() {
   static const bool on = getenv("DG_SYNC_CHECK") != nullptr;
   return on;

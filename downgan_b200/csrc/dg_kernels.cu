@@ -436,6 +436,7 @@ __global__ void __launch_bounds__(256) colsum_small_kernel(const float* __restri
   if (threadIdx.x == 0) g_colsum_done = 0;
 }
 int colsum(TV dy, size_t pixels, int C, float* out, cudaStream_t st) {
+  if (ablate(10)) return 0;
   DG_CHECK(C <= COLSUM_MAX_C, "colsum: %d channels > %d", C, COLSUM_MAX_C);
   if (!dy.bf && (C == 1 || C == 2 || C == 4) && dy.pitch == C && dy.coff == 0 && ((uintptr_t)dy.p & 15) == 0 && ((pixels * C) & 3) == 0 &&
       pixels >= 4096) {
@@ -497,6 +498,7 @@ __global__ void __launch_bounds__(320) colsum_dense_kernel(void* const* __restri
   }
 }
 int colsum_dense_blocks(void* const* d_bufs_dev, int n_blocks, size_t rows, float* out, cudaStream_t st) {
+  if (ablate(10)) return 0;
   if (n_blocks <= 0) return 0;
   const unsigned gx = 8;
   const size_t rpc = (rows + gx - 1) / gx;
@@ -598,6 +600,7 @@ static inline int pack_blocks(int max_elems) {
 }
 int pack_weights(const float* params, float* packed, void* packed_umma, const PackDesc* tab, int n, int max_elems, cudaStream_t st,
                  void* packed_ig) {
+  if (ablate(9)) return 0;
   if (n == 0) return 0;
   pack_kernel<<<dim3(pack_blocks(max_elems), n), 256, 0, st>>>(params, packed, (bf16*)packed_umma, tab, 0, n, nullptr, nullptr, nullptr,
                                                                (bf16*)packed_ig, nullptr);
@@ -607,6 +610,7 @@ int pack_weights(const float* params, float* packed, void* packed_umma, const Pa
 // forward and data-gradient tables of one network in ONE launch
 int pack_weights2(const float* params, float* packed, void* packed_umma, const PackDesc* tab, int n, int max_elems, float* packed2,
                   void* packed_umma2, const PackDesc* tab2, int n2, int max_elems2, cudaStream_t st, void* packed_ig, void* packed_ig2) {
+  if (ablate(9)) return 0;
   if (n == 0 || n2 == 0) {
     DG_TRY(pack_weights(params, packed, packed_umma, tab, n, max_elems, st, packed_ig));
     return pack_weights(params, packed2, packed_umma2, tab2, n2, max_elems2, st, packed_ig2);
@@ -618,6 +622,7 @@ int pack_weights2(const float* params, float* packed, void* packed_umma, const P
   return 0;
 }
 int unpack_wgrads(const float* packed, float* grads, const PackDesc* tab, int n, int max_elems, cudaStream_t st) {
+  if (ablate(9)) return 0;
   if (n == 0) return 0;
   pack_kernel<<<dim3(pack_blocks(max_elems), n), 256, 0, st>>>(packed, grads, nullptr, tab, 1, n, nullptr, nullptr, nullptr, nullptr, nullptr);
   DG_LAUNCH_CHECK();
@@ -1283,6 +1288,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 }
 int adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int step,
          float gscale, cudaStream_t st) {
+  if (ablate(9)) return 0;
   Prof prof(PC_ADAM, 0.0, (double)n * 28.0, st);
   const double bc1 = 1.0 - pow((double)b1, (double)step);
   const double bc2 = 1.0 - pow((double)b2, (double)step);

@@ -563,6 +563,7 @@ bool conv_ig_preferred(const ConvOp& op) {
 }
 
 int conv_ig(const ConvOp& op, cudaStream_t st) {
+  if (ablate(7)) return 0;
   IgArgs a;
   if (!plan_ig(op, a)) { set_error("conv_ig: unsupported shape"); return DG_ERR_INVALID; }
   CUtensorMap ma, mb;

@@ -259,6 +259,7 @@ bool conv_l1_supported(const ConvOp& op) {
 }
 
 int conv_l1(const ConvOp& op, cudaStream_t st) {
+  if (ablate(5)) return 0;
   C1Args a;
   if (!plan_c1(op, a)) { set_error("conv_l1: unsupported shape"); return DG_ERR_INVALID; }
   const size_t smem = (size_t)C1_NSTAGE * a.stage_bytes + 1024;

@@ -640,6 +640,7 @@ bool umma_ws_supported(const ConvOp& op) {
 }
 
 int conv_umma_ws(const ConvOp& op, cudaStream_t st) {
+  if (ablate(8)) return 0;
   WsArgs a;
   int cps = 1;
   if (!plan_ws(op, a, cps)) { set_error("conv_umma_ws: unsupported shape"); return DG_ERR_INVALID; }

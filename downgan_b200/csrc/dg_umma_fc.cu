@@ -296,6 +296,7 @@ bool fc_umma_supported(int NB, int K, int N, int x_bf) {
 
 // y += x w^T (y zeroed by the caller)
 int fc_fwd_umma(const void* x, const float* w, float* y, int NB, int K, int N, cudaStream_t st) {
+  if (ablate(6)) return 0;
   FcuArgs a{};
   a.x = x; a.w = w; a.y = y; a.NB = NB; a.K = K; a.N = N; a.rows = fcu_round(NB, 128);
   const size_t smem = (size_t)16 * a.rows * 16 + (size_t)16 * FCU_NP * 16 + 256;
@@ -308,6 +309,7 @@ int fc_fwd_umma(const void* x, const float* w, float* y, int NB, int K, int N, c
 
 // dx = (dz w) * lrelu'(mask), bf16 dx and mask
 int fc_dgrad_umma(const float* dz, const float* w, void* dx, int NB, int K, int N, const void* mask, float slope, cudaStream_t st) {
+  if (ablate(6)) return 0;
   FcuArgs a{};
   a.x = mask; a.w = w; a.dz = dz; a.dx = dx; a.NB = NB; a.K = K; a.N = N; a.rows = fcu_round(NB, 128); a.slope = slope;
   const size_t smem = (size_t)(FCU_NP / 8) * a.rows * 16 + (size_t)16 * FCU_NP * 16 + 256;
@@ -337,6 +339,7 @@ static void fcu_check(const char* what, const void* p, size_t bytes) {
 
 // dw += dz^T x
 int fc_wgrad_umma(const float* dz, const void* x, float* dw, int NB, int K, int N, cudaStream_t st) {
+  if (ablate(6)) return 0;
   static const bool chk = getenv("DG_FC_CHECK") != nullptr;
   if (chk) {
     fprintf(stderr, "[fc check] fc_wgrad_umma NB %d K %d N %d\n", NB, K, N);

@@ -23,7 +23,7 @@ constexpr int TF = 16;            // filters
 constexpr int TW = 16;            // coarse grid edge
 constexpr int TPW = TW + 2;       // padded width
 constexpr int TNMT = 3;           // M-tiles: 128 + 128 + 64 rows >= the 16*18 = 288 padded positions (the third tile is an M = 64 MMA)
-constexpr int T_THREADS = 256;    // 8 warps: warps 0-3 drain M-tile 0 (and the 32 live rows of M-tile 2), warps 4-7 M-tile 1
+constexpr int T_THREADS = 320;    // 10 warps: warps 0-3 drain M-tile 0, warps 4-7 M-tile 1, warps 8-9 the 32 live rows of M-tile 2
 constexpr int T_COLS_MT = 5 * TF; // TMEM columns per M-tile: one 16-column accumulator per layer of the block
 constexpr int T_TMEM_COLS = 256;  // 3 * 80 = 240 -> power of two
 constexpr int TPBPOS = 424;       // positions per plane incl. over-read slack (2*128 + 64 + 2*18 + 2 = 358 <= 424)
@@ -141,36 +141,29 @@ __device__ __forceinline__ void trunk_issue_round(int order, int warp, uint32_t 
   }
 }
 
-// Which accumulator rows a thread drains.  Slot 0: row 32*(warp%4) + lane of M-tile warp/4 (M = 128: row i = TMEM lane i).
-// Slot 1 (warps 0 and 1 only): M-tile 2 is an M = 64 MMA whose row i lives in TMEM lane 32*(i/16) + i%16
-// (tools/probes/wgrad_desc_probe.cu), so lanes 0-15 of warp w hold rows 16w..16w+15 = padded positions 256 + 16w + lane;
-// rows 32..63 of that tile lie past the image and are never read.
-struct TrunkSlots {
-  int pos[2], pix[2];
-  bool valid[2], has2;
-  uint32_t tcol[2];   // TMEM address (lane quarter | column of layer 0) of the slot's accumulator row
-  int tile[2];
+// Which accumulator row a thread drains: warp group h = warp / 4 owns M-tile h.  M-tiles 0 and 1 are M = 128 MMAs (row i =
+// TMEM lane i: warp w reads rows 32*(w%4) + lane).  M-tile 2 is an M = 64 MMA whose row i lives in TMEM lane 32*(i/16) + i%16
+// (tools/probes/wgrad_desc_probe.cu), so lanes 0-15 of warps 8 and 9 (TMEM lane quarters 0 and 1) hold rows 0..31 = padded
+// positions 256..287; its rows 32..63 lie past the image and are never read.
+struct TrunkSlot {
+  int pos, pix, tile;
+  bool valid;
+  uint32_t tcol;   // TMEM address (lane quarter | column of layer 0) of the thread's accumulator row
 };
-__device__ __forceinline__ TrunkSlots trunk_slots(int warp, int lane) {
-  TrunkSlots s;
+__device__ __forceinline__ TrunkSlot trunk_slot(int warp, int lane) {
+  TrunkSlot s;
   const int qd = warp & 3, h = warp >> 2;
-  const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
-  s.has2 = (h == 0 && qd < 2);
-  const int q[2] = {h * 128 + qd * 32 + lane, 256 + 16 * qd + lane};
-  s.tile[0] = h; s.tile[1] = 2;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int y = q[i] / TPW, x = q[i] - y * TPW;
-    s.valid[i] = (x < TW) && (y < TW);
-    s.pos[i] = q[i] + TPW + 1;
-    s.pix[i] = s.valid[i] ? y * TW + x : 0;
-    s.tcol[i] = lane_base + s.tile[i] * T_COLS_MT;
-  }
-  s.valid[1] = s.valid[1] && s.has2 && lane < 16;
+  s.tile = h;
+  const int q = (h < 2) ? h * 128 + qd * 32 + lane : 256 + 16 * qd + lane;
+  const int y = q / TPW, x = q - y * TPW;
+  s.valid = (x < TW) && (y < TW) && (h < 2 || lane < 16);
+  s.pos = q + TPW + 1;
+  s.pix = s.valid ? y * TW + x : 0;
+  s.tcol = ((uint32_t)(qd * 32) << 16) + h * T_COLS_MT;
   return s;
 }
 
-__global__ void __launch_bounds__(T_THREADS) trunk_fwd_kernel(const TrunkArgs a) {
+__global__ void __launch_bounds__(T_THREADS, 2) trunk_fwd_kernel(const TrunkArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t mbar[TNMT];  // one per M-tile: its epilogue starts while the other tiles' MMAs run
   __shared__ uint32_t tmem_slot;
@@ -198,9 +191,9 @@ __global__ void __launch_bounds__(T_THREADS) trunk_fwd_kernel(const TrunkArgs a)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const TrunkSlots S = trunk_slots(warp, lane);
+  const TrunkSlot S = trunk_slot(warp, lane);
 
-  uint4 xr[2][2];  // RRDB input at this thread's positions (bf16 x 16)
+  uint4 xr[2];  // RRDB input at this thread's position (bf16 x 16)
   const int total = a.R * 15;
   size_t w_elem = 0;  // element offset of the current slice's weight image
   // Input-stationary schedule: as soon as slice j of the concat buffer (x, o1..o4) exists, ONE round
@@ -213,11 +206,8 @@ __global__ void __launch_bounds__(T_THREADS) trunk_fwd_kernel(const TrunkArgs a)
     const int Nj = TF * (5 - j);
     const uint32_t wb = sW + (L & 1) * T_W_BYTES;
     if (k == 1 && d == 0) {
-#pragma unroll
-      for (int sl = 0; sl < 2; ++sl) {
-        xr[sl][0] = ld_shared16(sX + S.pos[sl] * 16);
-        xr[sl][1] = ld_shared16(sX + TPB + S.pos[sl] * 16);
-      }
+      xr[0] = ld_shared16(sX + S.pos * 16);
+      xr[1] = ld_shared16(sX + TPB + S.pos * 16);
     }
     // ---- MMA round of slice j (9 taps, K = 16 channels, N = Nj per M-tile)
     TR_TRACE(0);
@@ -238,16 +228,14 @@ __global__ void __launch_bounds__(T_THREADS) trunk_fwd_kernel(const TrunkArgs a)
     const bool saving = a.db_bufs && n < a.save_count;  // activations are kept for the first save_count samples only
     bf16* save_cur = saving ? a.db_bufs[db] : nullptr;
     bf16* save_next = (saving && db + 1 < a.R * 3) ? a.db_bufs[db + 1] : nullptr;
-#pragma unroll
-    for (int sl = 0; sl < 2; ++sl) {
-      if (sl == 1 && !S.has2) break;  // warp-uniform
-      mbar_wait(smem_u32(&mbar[S.tile[sl]]), L & 1);
-      TR_TRACE(2 + 2 * sl);
+    {
+      mbar_wait(smem_u32(&mbar[S.tile]), L & 1);
+      TR_TRACE(2);
       tc_fence_after();
       float v[16];
-      tmem_ld16(tmem + S.tcol[sl] + j * TF, v);
-      if (S.valid[sl]) {
-        const int pos = S.pos[sl], pix = S.pix[sl];
+      tmem_ld16(tmem + S.tcol + j * TF, v);
+      if (S.valid) {
+        const int pos = S.pos, pix = S.pix;
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] += bias[q];
         if (k < 5) {
@@ -269,8 +257,8 @@ __global__ void __launch_bounds__(T_THREADS) trunk_fwd_kernel(const TrunkArgs a)
           for (int q = 0; q < 16; ++q) v[q] = fmaf(RES, v[q], xo[q]);
           if (d == 2) {
             float xq[16];
-            unpack8(xr[sl][0], xq);
-            unpack8(xr[sl][1], xq + 8);
+            unpack8(xr[0], xq);
+            unpack8(xr[1], xq + 8);
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] = fmaf(RES, v[q], xq[q]);
           }
@@ -287,7 +275,7 @@ __global__ void __launch_bounds__(T_THREADS) trunk_fwd_kernel(const TrunkArgs a)
           }
         }
       }
-      TR_TRACE(3 + 2 * sl);
+      TR_TRACE(3); TR_TRACE(4); TR_TRACE(5);
     }
     w_elem = w_next;
     cp_async_wait_all();
@@ -319,7 +307,7 @@ struct TrunkBwdArgs {
   int order;
 };
 
-__global__ void __launch_bounds__(T_THREADS) trunk_bwd_kernel(const TrunkBwdArgs a) {
+__global__ void __launch_bounds__(T_THREADS, 2) trunk_bwd_kernel(const TrunkBwdArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t mbar[TNMT];  // one per M-tile: its epilogue starts while the other tiles' MMAs run
   __shared__ uint32_t tmem_slot;
@@ -337,15 +325,14 @@ __global__ void __launch_bounds__(T_THREADS) trunk_bwd_kernel(const TrunkBwdArgs
     const uint4* src = reinterpret_cast<const uint4*>(a.w + (size_t)(n_db - 1) * T_DB_ELEMS_);
     for (int i = tid; i < 18 * 5 * TF; i += T_THREADS) cp_async16(sW + i * 16, src + i, 16);
   }
-  const TrunkSlots S = trunk_slots(warp, lane);
-  // incoming gradient at this thread's positions (bf16 x 16 per position)
-  uint4 gin[2][2], gr[2][2];
-#pragma unroll
-  for (int sl = 0; sl < 2; ++sl) {
-    const uint4* g = reinterpret_cast<const uint4*>(a.g_in + ((size_t)n * 256 + S.pix[sl]) * TF);
-    gin[sl][0] = S.valid[sl] ? g[0] : make_uint4(0, 0, 0, 0);
-    gin[sl][1] = S.valid[sl] ? g[1] : make_uint4(0, 0, 0, 0);
-    gr[sl][0] = gr[sl][1] = make_uint4(0, 0, 0, 0);
+  const TrunkSlot S = trunk_slot(warp, lane);
+  // incoming gradient at this thread's position (bf16 x 16)
+  uint4 gin[2], gr[2];
+  {
+    const uint4* g = reinterpret_cast<const uint4*>(a.g_in + ((size_t)n * 256 + S.pix) * TF);
+    gin[0] = S.valid ? g[0] : make_uint4(0, 0, 0, 0);
+    gin[1] = S.valid ? g[1] : make_uint4(0, 0, 0, 0);
+    gr[0] = gr[1] = make_uint4(0, 0, 0, 0);
   }
   cp_async_wait_all();
   tc_fence_before();
@@ -359,25 +346,20 @@ __global__ void __launch_bounds__(T_THREADS) trunk_bwd_kernel(const TrunkBwdArgs
     const float s_in = (d == 2) ? RES : 1.f;
     const bf16* fbuf = a.fwd_bufs[db];
     bf16* dbuf = a.d_bufs[db];
-    if (d == 2) {
-#pragma unroll
-      for (int sl = 0; sl < 2; ++sl) { gr[sl][0] = gin[sl][0]; gr[sl][1] = gin[sl][1]; }
-    }
+    if (d == 2) { gr[0] = gin[0]; gr[1] = gin[1]; }
     // slice 0 of D: dz5 = 0.2 * s_in * g
-#pragma unroll
-    for (int sl = 0; sl < 2; ++sl) {
-      if (!S.valid[sl]) continue;
+    if (S.valid) {
       float g[16];
-      unpack8(gin[sl][0], g);
-      unpack8(gin[sl][1], g + 8);
+      unpack8(gin[0], g);
+      unpack8(gin[1], g + 8);
       const float sc = RES * s_in;
 #pragma unroll
       for (int q = 0; q < 16; ++q) g[q] *= sc;
       const uint4 lo = make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7]));
       const uint4 hi = make_uint4(pack2(g[8], g[9]), pack2(g[10], g[11]), pack2(g[12], g[13]), pack2(g[14], g[15]));
-      st_shared16(sX + S.pos[sl] * 16, lo);
-      st_shared16(sX + TPB + S.pos[sl] * 16, hi);
-      uint4* gd = reinterpret_cast<uint4*>(dbuf + ((size_t)n * 256 + S.pix[sl]) * 80);
+      st_shared16(sX + S.pos * 16, lo);
+      st_shared16(sX + TPB + S.pos * 16, hi);
+      uint4* gd = reinterpret_cast<uint4*>(dbuf + ((size_t)n * 256 + S.pix) * 80);
       gd[0] = lo; gd[1] = hi;
     }
     fence_proxy_async();
@@ -399,48 +381,43 @@ __global__ void __launch_bounds__(T_THREADS) trunk_bwd_kernel(const TrunkBwdArgs
         for (int i = tid; i < 18 * Nn; i += T_THREADS) cp_async16(dst + i * 16, src + i, 16);
       }
       // mask source for this round (issued before the wait so the latency hides behind the MMAs)
-      uint4 mk[2][2];
+      uint4 mk[2];
       if (t < 5) {
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          const uint4* m = reinterpret_cast<const uint4*>(fbuf + ((size_t)n * 256 + S.pix[sl]) * 80 + TF * (5 - t));
-          if (sl == 0 || S.has2) { mk[sl][0] = m[0]; mk[sl][1] = m[1]; }
-        }
+        const uint4* m = reinterpret_cast<const uint4*>(fbuf + ((size_t)n * 256 + S.pix) * 80 + TF * (5 - t));
+        mk[0] = m[0]; mk[1] = m[1];
       }
-#pragma unroll
-      for (int sl = 0; sl < 2; ++sl) {
-        if (sl == 1 && !S.has2) break;  // warp-uniform
-        mbar_wait(smem_u32(&mbar[S.tile[sl]]), L & 1);
+      {
+        mbar_wait(smem_u32(&mbar[S.tile]), L & 1);
         tc_fence_after();
         float v[16];
-        tmem_ld16(tmem + S.tcol[sl] + j * TF, v);
-        if (!S.valid[sl]) continue;
-        if (t < 5) {
+        tmem_ld16(tmem + S.tcol + j * TF, v);
+        if (!S.valid) {
+        } else if (t < 5) {
           float m[16];
-          unpack8(mk[sl][0], m);
-          unpack8(mk[sl][1], m + 8);
+          unpack8(mk[0], m);
+          unpack8(mk[1], m + 8);
 #pragma unroll
           for (int q = 0; q < 16; ++q) v[q] *= (m[q] > 0.f ? 1.f : G_SLOPE);
           const uint4 lo = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
           const uint4 hi = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
-          st_shared16(sX + (2 * t) * TPB + S.pos[sl] * 16, lo);
-          st_shared16(sX + (2 * t + 1) * TPB + S.pos[sl] * 16, hi);
-          uint4* gd = reinterpret_cast<uint4*>(dbuf + ((size_t)n * 256 + S.pix[sl]) * 80 + TF * t);
+          st_shared16(sX + (2 * t) * TPB + S.pos * 16, lo);
+          st_shared16(sX + (2 * t + 1) * TPB + S.pos * 16, hi);
+          uint4* gd = reinterpret_cast<uint4*>(dbuf + ((size_t)n * 256 + S.pix) * 80 + TF * t);
           gd[0] = lo; gd[1] = hi;
         } else {
           float g[16];
-          unpack8(gin[sl][0], g);
-          unpack8(gin[sl][1], g + 8);
+          unpack8(gin[0], g);
+          unpack8(gin[1], g + 8);
 #pragma unroll
           for (int q = 0; q < 16; ++q) v[q] = fmaf(s_in, g[q], v[q]);
           if (d == 0) {
-            unpack8(gr[sl][0], g);
-            unpack8(gr[sl][1], g + 8);
+            unpack8(gr[0], g);
+            unpack8(gr[1], g + 8);
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] += g[q];
           }
-          gin[sl][0] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-          gin[sl][1] = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+          gin[0] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+          gin[1] = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
         }
       }
       w_elem = w_next;
@@ -451,11 +428,9 @@ __global__ void __launch_bounds__(T_THREADS) trunk_bwd_kernel(const TrunkBwdArgs
       tc_fence_after();
     }
   }
-#pragma unroll
-  for (int sl = 0; sl < 2; ++sl) {
-    if (!S.valid[sl]) continue;
-    uint4* g = reinterpret_cast<uint4*>(a.g_out + ((size_t)n * 256 + S.pix[sl]) * TF);
-    g[0] = gin[sl][0]; g[1] = gin[sl][1];
+  if (S.valid) {
+    uint4* g = reinterpret_cast<uint4*>(a.g_out + ((size_t)n * 256 + S.pix) * TF);
+    g[0] = gin[0]; g[1] = gin[1];
   }
   if (warp == 0) tmem_dealloc(tmem, T_TMEM_COLS);
 }
@@ -498,6 +473,7 @@ int pack_trunk_slices(const float* pk_first_dense, void* dst_bf16, int n_db, int
 // g_out = dL/d(input of RRDB r0); chaining calls from the last RRDB range to the first reproduces the single launch.
 int trunk_bwd_fused(const void* g_in, void* g_out, void* const* fwd_bufs_dev, void* const* d_bufs_dev, const void* w_slices,
                     int R, int B, cudaStream_t st, int r0) {
+  if (ablate(3)) return 0;
   fwd_bufs_dev += 3 * r0;
   d_bufs_dev += 3 * r0;
   w_slices = (const bf16*)w_slices + (size_t)3 * r0 * T_DB_ELEMS_;
@@ -525,6 +501,7 @@ bool trunk_fused_supported(int F, int Hc, int R, int bf) { return bf && F == TF 
 // concat-buffer pointers (pitch 80) or nullptr when the activations need not be kept.
 int trunk_fwd_fused(const void* x_in, int in_pitch, int in_coff, void* y_out, int out_pitch, void* const* db_bufs_dev,
                     const void* w_umma, const float* bias, int R, int B, int save_count, cudaStream_t st) {
+  if (ablate(2)) return 0;
   static bool attr_set = false;
   if (!attr_set) {
     DG_CUDA(cudaFuncSetAttribute(trunk_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
@@ -552,7 +529,7 @@ int trunk_fwd_fused(const void* x_in, int in_pitch, int in_coff, void* y_out, in
     double sum[7] = {0};
     for (int l = 0; l < 32; ++l) {
       const unsigned long long* e = h + l * 8;
-      // [issue, ->M-tile 0 ready, its epilogue, ->M-tile 2 ready, its epilogue, sync] seen by thread 0 (warp 0 drains tiles 0 and 2)
+      // [issue, ->M-tile 0 ready, its epilogue, -, -, sync] seen by thread 0 (warp 0 drains M-tile 0)
       for (int k = 0; k < 6; ++k) sum[k] += (double)(e[k + 1] - e[k]);
     }
     fprintf(stderr, "[trunk trace] order %d, layers 30..61 of CTA 0, mean ns: issue %.0f | ->mt0 ready %.0f | epi0 %.0f | ->mt2 ready %.0f | epi2 %.0f | sync %.0f | layer %.0f\n",

@@ -454,6 +454,7 @@ bool wgrad_im2col_supported(const WgradOp& op) {
 }
 
 int wgrad_im2col(const WgradOp& op, cudaStream_t st) {
+  if (ablate(1)) return 0;
   IcArgs a;
   if (!plan_ic(op, a)) { set_error("wgrad_im2col: unsupported shape"); return DG_ERR_INVALID; }
   static bool attr_set = false;

@@ -394,6 +394,7 @@ bool wgrad_ws_supported(const WgradOp& op) {
 }
 
 int wgrad_ws(const WgradOp& op, cudaStream_t st) {
+  if (ablate(0)) return 0;
   WwArgs a;
   if (!plan_ww(op, a)) { set_error("wgrad_ws: unsupported shape"); return DG_ERR_INVALID; }
   const int s = op.stride;
@@ -462,6 +463,7 @@ size_t wgrad_ws_batch_bytes(int n_ops) {
 
 // Table layout: [CUtensorMap x 2n (64-byte aligned)] [WwArgs x n] [int x n: op indices grouped by mode]
 int wgrad_ws_batched(const WgradOp* ops, int n, void* table_dev, std::vector<unsigned char>& shadow, int S_per_op, cudaStream_t st) {
+  if (ablate(4)) return 0;
   if (n <= 0) return 0;
   const size_t maps_bytes = (size_t)n * 2 * sizeof(CUtensorMap), args_bytes = (size_t)n * sizeof(WwArgs);
   std::vector<unsigned char> tab(maps_bytes + args_bytes + (size_t)n * sizeof(int));
