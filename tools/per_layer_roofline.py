@@ -33,16 +33,22 @@ def conv(l, nb, kind):
 
 
 def schedule():
+    """Launch order of one critic iteration (round 2: the real + fake rows of the layer 0-2 weight gradients are launched
+    during the input-gradient chain, the interpolates' rows during the JVP chain)."""
     s = [("build [real;fake;interp]", 0.0, 3 * B * 128 * 128 * 2 * 4 + 2 * B * 128 * 128 * 2 * 4)]
     s += [(f"L{l} fwd (3B)",) + conv(l, 3 * B, "fwd") for l in range(8)]
     s += [("fc1 fwd (3B)", 2.0 * 3 * B * FC_IN * FC_H, 3 * B * FC_IN * 2 + FC_IN * FC_H * 4), ("classifier head", 0.0, 3 * B * FC_H * 12)]
     s += [("fc1 dgrad (3B)", 2.0 * 3 * B * FC_IN * FC_H, 2 * 3 * B * FC_IN * 2 + FC_IN * FC_H * 4)]
-    s += [(f"L{l} dgrad (3B)",) + conv(l, 3 * B, "dgrad") for l in range(7, 0, -1)]
+    s += [(f"L{l} dgrad (3B)",) + conv(l, 3 * B, "dgrad") for l in range(7, 2, -1)]
+    s += [("L2 wgrad (real+fake, 2B)",) + conv(2, 2 * B, "wgrad"), ("L2 dgrad (3B)",) + conv(2, 3 * B, "dgrad")]
+    s += [("L1 wgrad (real+fake, 2B)",) + conv(1, 2 * B, "wgrad"), ("L1 dgrad (3B)",) + conv(1, 3 * B, "dgrad")]
+    s += [("L0 wgrad (real+fake, 2B)",) + conv(0, 2 * B, "wgrad")]
     ci, co, hi, ho = LAY[0]
     s += [("L0 dgrad (interp, B)", 2.0 * B * hi * hi * 2 * 9 * 16, B * hi * hi * (16 * 2 + 2 * 4))]
     s += [("GP norms + finish (one launch)", 0.0, B * 128 * 128 * 2 * 4), ("GP scale (u)", 0.0, 2 * B * 128 * 128 * 2 * 4)]
     for l in range(8):
-        s += [(f"L{l} wgrad (3B)",) + conv(l, 3 * B, "wgrad"), (f"L{l} JVP (B)",) + conv(l, B, "jvp")]
+        nb = B if l <= 2 else 3 * B
+        s += [(f"L{l} wgrad ({'interp, B' if l <= 2 else '3B'})",) + conv(l, nb, "wgrad"), (f"L{l} JVP (B)",) + conv(l, B, "jvp")]
     s += [("fc1 wgrad (3B)", 2.0 * 3 * B * FC_IN * FC_H, 3 * B * FC_IN * 2 + 2 * FC_IN * FC_H * 4),
           ("fc1 JVP (B)", 2.0 * B * FC_IN * FC_H, B * FC_IN * 2 + FC_IN * FC_H * 4), ("fc1 JVP finish", 0.0, 0.0),
           ("small classifier grads", 0.0, 0.0), ("unpack gradients", 0.0, 2 * 1112313 * 4), ("Adam", 0.0, 1112313 * 28),

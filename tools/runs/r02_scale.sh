@@ -1,16 +1,19 @@
 #!/bin/bash
-# round 2, 8-GPU call: data-parallel parity test (2 GPUs), 8-GPU bench with the classifier all-reduce overlapped (DG_OVERLAP_AR=1) and not
+# round 2, 8-GPU call: 8-GPU bench with the fused exchange kernel (default, NVSwitch multimem), with plain peer loads and with NCCL
 O=gpurun_out/r02_scale; mkdir -p $O
 nvidia-smi --query-gpu=index,name --format=csv > $O/gpus.txt 2>&1
-timeout 300 python -m pytest tests/test_gpu_dp.py -m gpu -q -rA -s > $O/pytest_dp.log 2>&1; echo "dp test rc=$?" >> $O/status.txt
 N=$(nvidia-smi -L | wc -l)
-for ov in 0 1; do
-  DG_OVERLAP_AR=$ov timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
-      bench.py --gpus $N --steps 100 --warmup 10 --no-profile --no-cpu-baseline > $O/bench_${N}gpu_overlap$ov.json 2> $O/bench_${N}gpu_overlap$ov.err
-  echo "bench N=$N overlap=$ov rc=$?" >> $O/status.txt
-done
+run() {
+  local name=$1; shift
+  env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+      bench.py --gpus $N --steps 100 --warmup 10 --no-profile --no-cpu-baseline > $O/bench_${N}gpu_$name.json 2> $O/bench_${N}gpu_$name.err
+  echo "bench N=$N $name rc=$?" >> $O/status.txt
+}
+run fused_multimem DG_DP_FUSED=1 DG_DP_MULTICAST=1
+run nccl DG_DP_FUSED=0
+run fused_p2p DG_DP_FUSED=1 DG_DP_MULTICAST=0
 timeout 300 python bench.py --steps 100 --warmup 10 --no-profile --no-cpu-baseline > $O/bench_1gpu.json 2> $O/bench_1gpu.err; echo "bench N=1 rc=$?" >> $O/status.txt
-cat $O/status.txt; tail -4 $O/pytest_dp.log
+cat $O/status.txt; grep -h "downgan_b200.dp" $O/*.err | head -3
 python - <<PY
 import json, glob
 for f in sorted(glob.glob("$O/bench_*.json")):
