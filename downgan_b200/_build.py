@@ -8,7 +8,7 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libdowngan_b200.so")
-SOURCES = ["dg_kernels.cu", "dg_model.cu", "dg_umma_conv.cu", "dg_umma_conv_ws.cu", "dg_umma_conv_l1.cu", "dg_umma_wgrad.cu", "dg_umma_wgrad_ws.cu", "dg_skinny.cu", "dg_umma_trunk.cu", "dg_umma_wgrad_im2col.cu", "dg_umma_fc.cu", "dg_data.cu", "dg_umma_conv_ig.cu", "dg_dp.cu"]
+SOURCES = ["dg_kernels.cu", "dg_model.cu", "dg_umma_conv.cu", "dg_umma_conv_ws.cu", "dg_umma_conv_l1.cu", "dg_umma_wgrad.cu", "dg_umma_wgrad_ws.cu", "dg_skinny.cu", "dg_umma_trunk.cu", "dg_umma_wgrad_im2col.cu", "dg_umma_fc.cu", "dg_data.cu", "dg_umma_conv_ig.cu", "dg_dp.cu", "dg_umma_conv_l1p.cu"]
 HEADERS = ["dg_common.cuh", os.path.join("..", "..", "include", "downgan_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

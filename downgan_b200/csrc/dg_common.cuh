@@ -240,6 +240,8 @@ bool umma_ws_supported(const ConvOp& op);
 // tcgen05 forward conv of the few-channel fp32 boundary layer (dg_umma_conv_l1.cu)
 bool conv_l1_supported(const ConvOp& op);
 int conv_l1(const ConvOp& op, cudaStream_t st);
+bool conv_l1p_supported(const ConvOp& op);  // planar variant without the im2col build (dg_umma_conv_l1p.cu)
+int conv_l1p(const ConvOp& op, cudaStream_t st);
 // TMA-fed weight gradient on swizzled NHWC tiles (dg_umma_wgrad_ws.cu)
 bool wgrad_ws_supported(const WgradOp& op);
 int wgrad_ws(const WgradOp& op, cudaStream_t st);

@@ -162,6 +162,7 @@ int run_wgrad(const WgradOp& w0, cudaStream_t st) {
 
 int run_conv(const ConvOp& op, cudaStream_t st) {
   static const bool ws = !(getenv("DG_CONV_WS") && atoi(getenv("DG_CONV_WS")) == 0);
+  if (g_tune[6] && g_tune[20] && conv_l1p_supported(op)) return conv_l1p(op, st);
   if (g_tune[6] && conv_l1_supported(op)) return conv_l1(op, st);
   if (op.Co < 16 && op.narrow_ok && ws && g_tune[0] && g_tune[7] && op.w_umma && umma_ws_supported(op))
     return conv_umma_ws(op, st);  // narrow output on tensor cores
@@ -900,7 +901,7 @@ struct dg_critic {
   void* keep[9] = {nullptr};               // parity instrumentation (dg_set_tuning(15, 1)): the interpolates' activations a[1..8]
   int keep_batch = 0;
   float *sumsq = nullptr, *coef = nullptr, *norms = nullptr, *scal = nullptr;
-  SideStream side;
+  SideStream side, side2;
   int defer_conv = 0;           // dg_critic_defer_conv_grads: the fused iteration returns before its conv weight gradients are final
   bool pending_finish = false;  // ... and dg_critic_step_finish has not been called yet
   static constexpr int N_CONV_ENTRIES = 9;  // tab_fwd order: 8 conv weights, features.0.bias, then the 4 classifier tensors
@@ -1054,12 +1055,14 @@ extern "C" int dg_critic_create(const dg_critic_config* cfg, dg_critic** out) {
   CA(c->metric_scratch, metric_scratch_bytes());
 #undef CA
   if ((s = c->side.create(1)) != 0) { dg_critic_destroy(c); return s; }
+  if ((s = c->side2.create(0)) != 0) { dg_critic_destroy(c); return s; }  // (no column sums run on the second side stream)
   *out = c;
   return 0;
 }
 extern "C" int dg_critic_destroy(dg_critic* c) {
   if (!c) return 0;
   c->side.destroy();
+  c->side2.destroy();
   for (void* p : c->pool) cudaFree(p);
   delete c;
   return 0;
@@ -1110,8 +1113,11 @@ static int critic_layer_wgrad(dg_critic* c, int i, int s0, int n, int bias_n, bo
   w.dw = c->gpk + l.pk_off;
   if (i == 0 && bias_n > 0) { w.dbias = c->gpk + c->pk_b0; w.dbias_B = bias_n; }
   if (!side) return run_wgrad(w, st);
-  DG_TRY(c->side.fork(st));
-  return run_wgrad(w, c->side.s);
+  // tuning key 19: the late layers' weight gradients alternate between two side streams, so two of these latency-bound
+  // launches run beside each other (and beside the JVP chain on the caller's stream)
+  SideStream& ss = (g_tune[19] && c->side2.s && i >= 3 && (i & 1)) ? c->side2 : c->side;
+  DG_TRY(ss.fork(st));
+  return run_wgrad(w, ss.s);
 }
 
 // Input-gradient chain for samples [s0, s0 + NB) seeded by c->seed; layer-1 data
@@ -1266,7 +1272,7 @@ static int critic_second_order_and_wgrads(dg_critic* c, int B, cudaStream_t st, 
                 c->a9 + (size_t)n0 * FC_HIDDEN, st));
   if (two_chain) {
     for (int i = 0; i < 8; ++i) DG_TRY(layer_wgrad(i));
-    DG_TRY(c->side.join(st));
+    DG_TRY(c->side.join(st)); DG_TRY(c->side2.join(st));
   }
   // classifier.0.bias, classifier.2.weight (incl. the GP term sum_b v_fc) and classifier.2.bias in one launch
   DG_TRY(critic_small_grads(c->dz9, c->seed, c->a9, c->vfc, n0, B, FC_HIDDEN, c->gpk + c->pk_fc1b, c->gpk + c->pk_fc2w,
@@ -1274,7 +1280,7 @@ static int critic_second_order_and_wgrads(dg_critic* c, int B, cudaStream_t st, 
   if (!two_chain) {
     if (!side_on)
       for (int i = 0; i < 8; ++i) DG_TRY(layer_wgrad(i));
-    if (!defer_join) DG_TRY(c->side.join(st));  // deferred: dg_critic_step_finish joins
+    if (!defer_join) DG_TRY(c->side.join(st)); DG_TRY(c->side2.join(st));  // deferred: dg_critic_step_finish joins
   }
   return 0;
 }
@@ -1295,7 +1301,7 @@ extern "C" int dg_critic_fwd(dg_critic* c, const float* x, int batch, float* sco
 extern "C" int dg_critic_activation(dg_critic* c, int which, int s0, int batch, float* out, void* stream) {
   DG_CHECK(c && out, "dg_critic_activation: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  DG_TRY(c->side.join(st));
+  DG_TRY(c->side.join(st)); DG_TRY(c->side2.join(st));
   if (which >= 101 && which <= 108) {
     const int i = which - 101;
     DG_CHECK(s0 >= 0 && batch >= 1 && s0 + batch <= c->keep_batch,
@@ -1470,7 +1476,7 @@ extern "C" int dg_critic_step_finish(dg_critic* c, float* c_grads_flat, void* st
   DG_CHECK(c && c_grads_flat, "dg_critic_step_finish: null argument");
   if (!c->pending_finish) { set_error("dg_critic_step_finish: no deferred critic iteration"); return DG_ERR_STATE; }
   cudaStream_t st = (cudaStream_t)stream;
-  DG_TRY(c->side.join(st));
+  DG_TRY(c->side.join(st)); DG_TRY(c->side2.join(st));
   DG_TRY(unpack_wgrads(c->gpk, c_grads_flat, c->tab_fwd, dg_critic::N_CONV_ENTRIES, c->max_fwd, st));
   c->pending_finish = false;
   return 0;
@@ -1651,7 +1657,7 @@ extern "C" int dg_metrics(dg_generator* g, dg_critic* c, const float* coarse, in
     if (g->side.dirty && !(fake_offset >= g->ready_lo && fake_offset + batch <= g->ready_hi)) DG_TRY(g->side.join(st));
     fake = g->fake + (size_t)fake_offset * g->Hf * g->Hf * g->Cout;
   }
-  DG_TRY(c->side.join(st));
+  DG_TRY(c->side.join(st)); DG_TRY(c->side2.join(st));
   DG_TRY(build_critic_input(fine, fake, 0, nullptr, c->a0, batch, c->nc, c->Hf, c->Hf, 2, st));  // [real ; fake], no interpolates
   DG_TRY(critic_forward_internal(c, 2 * batch, st));
   const long long n = (long long)batch * c->Hf * c->Hf * c->nc;
@@ -1725,11 +1731,12 @@ extern "C" int dg_conv3x3_fwd(const float* x, const float* w, const float* bias,
   const int ho = (hin - 1) / stride + 1, wo = (win - 1) / stride + 1;
   float* pk; void *xi, *yo; bf16 *pku, *pkig = nullptr;
   DG_TRY(prim_setup(s, precision, w, ci, co, 0, &pk, st, &pku, &pkig));
-  DG_TRY(dev_alloc(s.pool, &xi, (size_t)batch * hin * win * ci * esz));
+  const int xbf = bf && ci > 3;  // 1- to 3-channel inputs stay fp32 as at the networks' boundaries (first-layer kernels)
+  DG_TRY(dev_alloc(s.pool, &xi, (size_t)batch * hin * win * ci * (xbf ? 2 : 4)));
   DG_TRY(dev_alloc(s.pool, &yo, (size_t)batch * ho * wo * co * esz));
-  DG_TRY(nchw_to_nhwc(x, tv(xi, bf, ci), batch, ci, hin, win, st));
+  DG_TRY(nchw_to_nhwc(x, tv(xi, xbf, ci), batch, ci, hin, win, st));
   ConvOp op;
-  op.x = tv(xi, bf, ci); op.Hin = hin; op.Win = win; op.Ci = ci;
+  op.x = tv(xi, xbf, ci); op.Hin = hin; op.Win = win; op.Ci = ci;
   op.y = tv(yo, bf, co); op.Hout = ho; op.Wout = wo; op.Co = co;
   op.B = batch; op.w = pk; op.bias = bias; op.stride = stride; op.w_umma = pku; op.w_ig = pkig;
   if (slope != 1.f) { op.act = ACT_LRELU; op.slope = slope; }

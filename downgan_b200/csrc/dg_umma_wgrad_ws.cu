@@ -285,8 +285,10 @@ bool plan_ww(const WgradOp& op, WwArgs& a) {
   const int mode = (s == 2) ? (op.Ci <= 32 ? W_S2_FOLD : W_S2_TAPS) : (3 * op.Ci <= 128 ? W_S1_FOLD : W_S1_TAPS);
   const int units = (mode == W_S1_FOLD) ? 3 : (mode == W_S2_FOLD ? 6 : 9);
   int NT = 0;
+  // TMEM columns of a CTA (DG_WW_TMEM, default 512): <= 256 lets a second tcgen05 CTA share the SM while this one runs
+  static const int tmem_limit = getenv("DG_WW_TMEM") ? atoi(getenv("DG_WW_TMEM")) : 512;
   for (int cand : {64, 32, 16})
-    if (op.Co % cand == 0 && units * cand <= 512) { NT = cand; break; }
+    if (op.Co % cand == 0 && units * cand <= tmem_limit) { NT = cand; break; }
   if (NT == 0) return false;
   const int PW = (s == 1) ? op.Wout + 2 : op.Wout + 1;
   if (PW * s > 256) return false;  // TMA box extent (traversal) per dimension

@@ -307,8 +307,11 @@ int dg_profile_report(double* out, int n_classes);
  * synchronises (1) or after (0, default: measured -0.5 % on the cfg-2 step, profiles/README.md).
  * key 18 = k (1..4): the fused trunk backward runs as k launches over RRDB ranges; the dense convs' weight gradients of a range
  * go to the side stream and overlap the next range's data gradients (default 2; 1 = one launch, weight gradients afterwards).
+ * key 19: the critic's late-layer weight gradients alternate between two side streams (1) or share one (0, default).
+ * key 20: the 1- / 2-channel first-layer convolutions run on the planar kernel without an im2col build (1;
+ * csrc/dg_umma_conv_l1p.cu: faster alone, measured 1.4 % slower in the overlapped cfg-2 step) or on the im2col kernel (0, default).
  * Returns the previous value, or DG_ERR_INVALID for an unknown key. */
-#define DG_TUNE_KEYS 19
+#define DG_TUNE_KEYS 21
 int dg_set_tuning(int key, int value);
 
 #ifdef __cplusplus

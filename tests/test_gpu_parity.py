@@ -22,6 +22,7 @@ import torch.nn.functional as F
 
 from oracle import networks as onet
 from oracle import trainer as otr
+from downgan_b200 import _lib
 from downgan_b200.synthetic import synth_batch
 
 import parity_util as pu
@@ -56,6 +57,8 @@ CONV_CASES = [
     (1, 128, 128, 16, 16, 2), (1, 48, 16, 8, 8, 1), (1, 5, 3, 7, 9, 1), (2, 24, 40, 12, 20, 2),
     # cfg-4 layers whose rows do not fit one TMA box / shared-memory stage: weight gradients run as column strips
     (1, 32, 32, 256, 256, 1), (1, 32, 32, 256, 256, 2), (2, 64, 64, 128, 128, 2), (2, 128, 128, 64, 64, 2),
+    # 1- / 2-channel fp32 inputs on maps >= 32 wide: the planar first-layer kernel (dg_umma_conv_l1p.cu)
+    (2, 2, 16, 128, 128, 1), (1, 1, 16, 64, 32, 1), (1, 2, 32, 32, 256, 1), (3, 2, 16, 48, 64, 1),
 ]
 
 
@@ -82,6 +85,25 @@ def test_conv_primitives(case, precision):
     dy_in = dy.bfloat16().float() if precision == "bf16" else dy
     db_ref = dy_in.double().sum((0, 2, 3))
     assert float((db.double().cpu() - db_ref).abs().max() / dy_in.abs().sum((0, 2, 3)).max()) < 1e-5
+
+
+@pytest.mark.parametrize("case", [(2, 2, 16, 128, 128), (1, 1, 16, 64, 32), (1, 2, 32, 32, 256), (3, 2, 16, 48, 64)])
+def test_planar_first_layer_kernel(case):
+    """csrc/dg_umma_conv_l1p.cu (dg_set_tuning(20, 1); off by default, see its header): forward of the 1- / 2-channel fp32
+    layers without an im2col build, against torch."""
+    b, ci, co, h, w = case
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(b, ci, h, w, generator=g)
+    wt = torch.randn(co, ci, 3, 3, generator=g) / (3 * ci ** 0.5)
+    bias = torch.randn(co, generator=g)
+    y_ref = F.leaky_relu(F.conv2d(x, wt, bias, padding=1), 0.2)
+    prev = lib.dg_set_tuning(20, 1)
+    try:
+        y = pu.conv_fwd(x, wt, bias, 1, 0.2, "bf16")
+    finally:
+        lib.dg_set_tuning(20, prev)
+    assert pu.rel(y, y_ref) < 1.5e-2
 
 
 # ---------------------------------------------------------------- forward passes
