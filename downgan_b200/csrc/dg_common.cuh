@@ -175,7 +175,13 @@ struct PackDesc {
   int dst_row_off;     // row (input channel of the dgrad op) where this slice starts
   int dst_CoP;         // CoP of the destination op
   int umma;            // 1: also emit the bf16 tcgen05 B-operand image (same element offset) while packing
+  int ps;              // 1: the layer feeds nn.PixelShuffle(2).  Its data-gradient dz is kept (i,j)-major - channel
+                       // (2i + j) * Co/4 + c instead of 4c + 2i + j - so that the inverse-shuffle store of the layer above is one
+                       // contiguous 32-byte store per pixel.  Consequences handled here: the weight / bias GRADIENTS come out in
+                       // that column order (un-permuted while unpacking, modes 0 and 5) and the data-gradient weight image has its
+                       // rows in that order (mode 1, packing).
 };
+__host__ __device__ inline unsigned ps_perm(unsigned co, unsigned Co) { return (co & 3u) * (Co >> 2) + (co >> 2); }
 // packed_ig (optional): also emit the K-major bf16 image [tap][CoP][rows] of the streaming implicit-GEMM kernel for d.umma entries
 int pack_weights(const float* params, float* packed, void* packed_umma, const PackDesc* table_dev, int n, int max_elems, cudaStream_t st,
                  void* packed_ig = nullptr);

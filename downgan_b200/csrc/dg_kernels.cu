@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_direct_kernel(ConvOp op) {
     } else {
       // inverse addressing for the data-gradient of a pixel-shuffled activation
       const size_t q = ((size_t)n * (op.Hout >> 1) + (yo >> 1)) * (op.Wout >> 1) + (xo >> 1);
-      idx = q * op.y.pitch + op.y.coff + 4 * co + 2 * (yo & 1) + (xo & 1);
+      idx = q * op.y.pitch + op.y.coff + (2 * (yo & 1) + (xo & 1)) * op.Co + co;  // (i,j)-major, see PackDesc::ps
     }
     stv(op.y.p, op.y.bf, idx, v);
   }
@@ -561,8 +561,8 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src
   const float* s_base = src + (unpack ? d.dst_off : d.src_off);
   float* d_base = dst + (unpack ? d.src_off : d.dst_off);
   for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    if (d.mode == 5) {  // bias copy
-      d_base[e] = s_base[e];
+    if (d.mode == 5) {  // bias copy (unpacking a pixel-shuffle layer's gradient: (i,j)-major columns back to 4c + 2i + j)
+      d_base[e] = s_base[(unpack && d.ps) ? ps_perm(e, (unsigned)d.Co) : e];
       continue;
     }
     const unsigned r = e / 9u, tap = e - 9u * r;
@@ -574,8 +574,8 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src
       tp = 8u - tap; row = (unsigned)d.dst_row_off + co; col = ci; R = (unsigned)d.CoP /*rows_total*/; cols = (unsigned)d.dst_CoP;
     } else {
       s_idx = e;  // (co*Ci + ci)*9 + tap
-      if (d.mode == 0) { tp = tap; row = ci; col = co; R = (unsigned)d.Ci; }
-      else if (d.mode == 1) { tp = 8u - tap; row = co; col = ci; R = (unsigned)d.Co; }  // CoP = round16(Ci)
+      if (d.mode == 0) { tp = tap; row = ci; col = (unpack && d.ps) ? ps_perm(co, (unsigned)d.Co) : co; R = (unsigned)d.Ci; }
+      else if (d.mode == 1) { tp = 8u - tap; row = d.ps ? ps_perm(co, (unsigned)d.Co) : co; col = ci; R = (unsigned)d.Co; }  // CoP = round16(Ci)
       else { tp = tap; row = co; col = ci; R = (unsigned)d.Co; }                          // mode 2
       cols = (unsigned)d.CoP;
     }

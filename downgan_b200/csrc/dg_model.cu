@@ -307,18 +307,21 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
   g->use_ig = g->bf && (F >= 32 || g->Hf > 254);
   // ---- packed layouts + tables
   std::vector<PackDesc> tf, td;
+  auto is_up = [&](long li) { return (li >= g->idx_up(0) && li < g->idx_up(0) + g->U) ? 1 : 0; };  // layers feeding nn.PixelShuffle
   long long pk = 0, pkd = 0;
   int maxf = 1, maxd = 1;
   for (auto& l : g->layers) {
     l.pk_off = pk; pk += (long long)packed_w_elems(l.Ci, l.Co);
     PackDesc d{}; d.src_off = l.w_off; d.dst_off = l.pk_off; d.Ci = l.Ci; d.Co = l.Co; d.CoP = round_up(l.Co, 16); d.mode = 0;
     d.umma = g->bf && umma_img_ok(l.Ci, l.Co);
+    d.ps = is_up(&l - g->layers.data());
     tf.push_back(d);
     maxf = std::max(maxf, l.Ci * l.Co * 9);
   }
   for (auto& l : g->layers) {
     l.pkb_off = pk; pk += round_up(l.Co, 16);
     PackDesc d{}; d.src_off = l.b_off; d.dst_off = l.pkb_off; d.Co = l.Co; d.Ci = 1; d.mode = 5;
+    d.ps = is_up(&l - g->layers.data());
     tf.push_back(d);
   }
   g->pk_elems = pk;
@@ -328,6 +331,7 @@ extern "C" int dg_generator_create(const dg_generator_config* cfg, dg_generator*
     l.pkd_off = pkd; pkd += (long long)packed_w_elems(l.Co, l.Ci);
     PackDesc d{}; d.src_off = l.w_off; d.dst_off = l.pkd_off; d.Ci = l.Ci; d.Co = l.Co; d.CoP = round_up(l.Ci, 16); d.mode = 1;
     d.umma = g->bf && umma_ok(l.Co, l.Ci);
+    d.ps = is_up(li);
     td.push_back(d);
     maxd = std::max(maxd, l.Ci * l.Co * 9);
   };

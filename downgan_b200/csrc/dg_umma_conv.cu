@@ -129,9 +129,7 @@ __device__ __forceinline__ void epilogue16(const ConvOp& op, float* v, int n, in
     }
   } else {  // inverse shuffle: data-gradient w.r.t. the pre-shuffle activation
     const size_t qq = ((size_t)n * (op.Hout >> 1) + (yo >> 1)) * (op.Wout >> 1) + (xo >> 1);
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      st1(op.y, qq * op.y.pitch + op.y.coff + 4 * (nc + j) + 2 * (yo & 1) + (xo & 1), v[j]);
+    store16(op.y, qq * op.y.pitch + op.y.coff + (2 * (yo & 1) + (xo & 1)) * op.Co + nc, v);  // (i,j)-major, see PackDesc::ps
   }
 }
 

@@ -456,16 +456,10 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_ws_kernel(const __grid_con
             const int sq = colp / a.Fsh, cc0 = colp - sq * a.Fsh;
             const size_t qq = ((size_t)cur.n * (2 * op.Hout) + 2 * cur.yo + (sq >> 1)) * (2 * op.Wout) + 2 * cur.xo + (sq & 1);
             st16f(op.y, qq * op.y.pitch + op.y.coff + cc0, v);
-          } else {  // inverse shuffle: data-gradient w.r.t. the pre-shuffle activation
+          } else {  // inverse shuffle: data-gradient w.r.t. the pre-shuffle activation, kept (i,j)-major (PackDesc::ps):
+            // the 16 channels of this piece are contiguous in the (2i + j) block of the coarse pixel - one 32-byte store
             const size_t qq = ((size_t)cur.n * (op.Hout >> 1) + (cur.yo >> 1)) * (op.Wout >> 1) + (cur.xo >> 1);
-            const size_t base = qq * op.y.pitch + op.y.coff + 2 * (cur.yo & 1) + (cur.xo & 1);
-            if (op.y.bf) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) ((bf16*)op.y.p)[base + 4 * (co0 + nc + j)] = __float2bfloat16_rn(v[j]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) ((float*)op.y.p)[base + 4 * (co0 + nc + j)] = v[j];
-            }
+            st16f(op.y, qq * op.y.pitch + op.y.coff + (2 * (cur.yo & 1) + (cur.xo & 1)) * op.Co + co0 + nc, v);
           }
         }
         cur = nxt; m0 = nm0; m1 = nm1;
@@ -505,7 +499,7 @@ bool plan_ws(const ConvOp& op, WsArgs& a, int& ctas_per_sm) {
     return t.bf ? (t.pitch % 8 == 0 && t.coff % 8 == 0) : (t.pitch % 4 == 0 && t.coff % 4 == 0);
   };
   if (!aligned(op.r1) || !aligned(op.r2) || !aligned(op.mask)) return false;
-  if (op.shuffle != SHUF_UNPIXEL && !narrow && !aligned(op.y)) return false;
+  if (!narrow && !aligned(op.y)) return false;
   const int perm = op.shuffle == SHUF_PIXEL;
   if (perm && (op.Co % 64)) return false;  // Co/4 shuffled channels in whole 16-column pieces
   const int Ht = (mode == S2_DGRAD) ? op.Hin : op.Hout, Wt = (mode == S2_DGRAD) ? op.Win : op.Wout;

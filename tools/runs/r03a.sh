@@ -1,0 +1,13 @@
+#!/bin/bash
+O=gpurun_out/r03a; mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -q -x > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/status.txt
+run() { local name=$1; shift; env "$@" timeout 300 python bench.py --no-cpu-baseline --no-profile > $O/bench_$name.json 2> $O/$name.err; echo "bench $name rc=$?" >> $O/status.txt; }
+run a
+run b
+cat $O/status.txt; tail -3 $O/pytest.log
+python - <<PY
+import json, glob
+for f in sorted(glob.glob("$O/bench_*.json")):
+    d = json.loads(open(f).read().strip().splitlines()[-1])
+    print(f, "value", round(d["value"], 1), "ms/step", round(d["ms_per_step"], 4), "e2e", round(d["e2e"]["value"], 1))
+PY
