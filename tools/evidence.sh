@@ -15,10 +15,14 @@ timeout 300 python bench.py > $O/bench_200.json 2> $O/bench_200.err; echo "bench
 timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
     --profile-from-start off --csv --log-file $O/launches.csv python tools/cycle.py > $O/cycle.log 2>&1; echo "ncu list rc=$?" >> $O/status.txt
 if [ "$MODE" = full ]; then
-  timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off \
-      -k regex:conv_ws_kernel -s 30 -c 1 -f -o $O/conv_ws_c30 python tools/cycle.py > $O/ncu_full_ws.log 2>&1; echo "ncu ws rc=$?" >> $O/status.txt
+  # full captures: the longest launch of the dominant class (critic layer 1 data gradient: conv_ws_kernel<2, 1>), the streaming
+  # conv kernel and the fused trunk forward
+  timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off --kernel-name-base demangled \
+      -k regex:"conv_ws_kernel<\(int\)2, \(int\)1>" -s 1 -c 1 -f -o $O/conv_ws_l1dgrad python tools/cycle.py > $O/ncu_full_ws.log 2>&1; echo "ncu ws rc=$?" >> $O/status.txt
   timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off \
       -k regex:conv_ig_kernel -s 2 -c 1 -f -o $O/conv_ig_c2 python tools/cycle.py > $O/ncu_full_ig.log 2>&1; echo "ncu ig rc=$?" >> $O/status.txt
+  timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off \
+      -k regex:trunk_fwd_kernel -s 0 -c 1 -f -o $O/trunk_fwd python tools/cycle.py > $O/ncu_full_trunk.log 2>&1; echo "ncu trunk rc=$?" >> $O/status.txt
   for c in cfg3 cfg4 cfg5; do
     timeout 600 python bench.py --config $c > $O/bench_$c.json 2> $O/bench_$c.err; echo "$c rc=$?" >> $O/status.txt
   done

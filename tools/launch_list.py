@@ -39,10 +39,11 @@ for r in rows[start:]:
     elif m == "dram__bytes_write.sum":
         e["wr"] = v
 L = list(by_id.values())
-# cycles are delimited by the generator step's trunk_bwd_kernel; take the launches between the last two of them
+# --cycle: the list holds several cycles (bench.py under ncu), delimited by the generator step's trunk_bwd_kernel launches
+# (two per step since the backward runs in RRDB ranges); default / --all: the list IS one cycle (tools/cycle.py)
 idx = [i for i, l in enumerate(L) if l["name"].startswith("trunk_bwd_kernel")]
-if len(idx) >= 2 and "--all" not in sys.argv:
-    L = L[idx[-2]:idx[-1]]
+if len(idx) >= 4 and "--cycle" in sys.argv:
+    L = L[idx[-4]:idx[-2]]
 tot = sum(l["us"] for l in L)
 have_dram = any(l["rd"] is not None for l in L)
 agg = OrderedDict()
