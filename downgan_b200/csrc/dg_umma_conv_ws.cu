@@ -367,30 +367,24 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_ws_kernel(const __grid_con
         const size_t p = ((size_t)pc.n * op.Hout + pc.yo) * op.Wout + pc.xo;
         return reinterpret_cast<const uint4*>((const bf16*)op.mask.p + p * op.mask.pitch + op.mask.coff + co0 + pc.nc);
       };
-      // LeakyReLU masks are prefetched TWO pieces ahead (the ncu source page of the layer-1 data gradient put 17 % of all
-      // stall samples on the first use of a mask that was prefetched one piece ahead: a piece takes ~0.25 us, a global load
-      // under load ~1 us): m = this piece, q1 = the warp's next piece, q2 = the one after; pieces are re-decoded when used
-      auto load_mask = [&](int p, uint4& a0, uint4& a1) {
-        a0 = make_uint4(0, 0, 0, 0); a1 = a0;
-        if (pre_mask && p < npieces) {
-          const Piece pc = decode(p);
-          if (pc.valid) { const uint4* mp = mask_ptr(pc); a0 = mp[0]; a1 = mp[1]; }
-        }
-      };
-      uint4 m0, m1, q10, q11;
-      load_mask(half, m0, m1);
-      load_mask(half + 2, q10, q11);
+      Piece cur = decode(half < npieces ? half : 0);
+      if (half >= npieces) cur.valid = false;
+      uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;
+      if (pre_mask && cur.valid) { const uint4* mp = mask_ptr(cur); m0 = mp[0]; m1 = mp[1]; }
       if (tid == WS_EPI_WARP0 * 32) WS_TRACE(2, it, 0);
       mbar_wait_ws(tfull_bar(q), ((uint32_t)(it >> 1)) & 1u);
       if (tid == WS_EPI_WARP0 * 32) WS_TRACE(2, it, 1);
       tc_fence_after();
       const uint32_t acc0 = tmem + lane_base + q * a.acc_cols;
       for (int p = half; p < npieces; p += 2) {
-        const Piece cur = decode(p);
         uint32_t raw[16];
         tmem_ld16_raw(acc0 + cur.col, raw);
-        uint4 q20, q21;
-        load_mask(p + 4, q20, q21);
+        Piece nxt = cur;
+        uint4 nm0 = m0, nm1 = m1;
+        if (p + 2 < npieces) {
+          nxt = decode(p + 2);
+          if (pre_mask && nxt.valid) { const uint4* mp = mask_ptr(nxt); nm0 = mp[0]; nm1 = mp[1]; }
+        }
         tmem_ld_wait();
         if (cur.valid) {
           float v[16];
@@ -468,7 +462,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_ws_kernel(const __grid_con
             st16f(op.y, qq * op.y.pitch + op.y.coff + (2 * (cur.yo & 1) + (cur.xo & 1)) * op.Co + co0 + nc, v);
           }
         }
-        m0 = q10; m1 = q11; q10 = q20; q11 = q21;
+        cur = nxt; m0 = nm0; m1 = nm1;
       }
       tc_fence_before();
       __syncwarp();
