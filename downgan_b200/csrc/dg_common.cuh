@@ -135,6 +135,13 @@ struct ConvOp {
   const void* w_umma = nullptr;  // packed bf16 weights for the tcgen05 kernel (null -> direct kernel)
   int narrow_ok = 0;             // Co < 16: w_umma holds a zero-padded 16-column image (set only where one is packed)
   const void* w_ig = nullptr;    // K-major bf16 weight image [tap][CoP][Ci] for the streaming implicit-GEMM kernel (null: not packed)
+  // LeakyReLU sign bits (critic, bf16 mode): the data-gradient / JVP epilogues only need the SIGN of the saved activation, so
+  // the forward epilogues that support it also store one uint16 per (pixel, 16-channel group) - bit j = channel 16k + j is
+  // positive - and the mask epilogues read those 2 bytes instead of 32 bytes of bf16 activations.  Both pointers are already
+  // offset to the op's first sample; words are indexed [pixel][Co / 16] like the store location.  Kernels that do not
+  // implement them ignore the fields (bits_in: they use `mask`; bits_out: conv_writes_bits() tells the caller).
+  unsigned short* bits_out = nullptr;      // ACT_LRELU ops
+  const unsigned short* bits_in = nullptr; // ACT_MASK ops
 };
 
 struct WgradOp {

@@ -160,15 +160,21 @@ int run_wgrad(const WgradOp& w0, cudaStream_t st) {
   return wgrad_direct(w, st);
 }
 
-int run_conv(const ConvOp& op, cudaStream_t st) {
+// wrote_bits (optional): set to whether the kernel that took the op stores ConvOp::bits_out (the im2col first-layer kernel and the
+// weights-stationary kernel do; the others ignore the field)
+int run_conv(const ConvOp& op, cudaStream_t st, bool* wrote_bits = nullptr) {
   static const bool ws = !(getenv("DG_CONV_WS") && atoi(getenv("DG_CONV_WS")) == 0);
+  if (wrote_bits) *wrote_bits = false;
   if (g_tune[6] && g_tune[20] && conv_l1p_supported(op)) return conv_l1p(op, st);
-  if (g_tune[6] && conv_l1_supported(op)) return conv_l1(op, st);
+  if (g_tune[6] && conv_l1_supported(op)) { if (wrote_bits) *wrote_bits = op.bits_out != nullptr; return conv_l1(op, st); }
   if (op.Co < 16 && op.narrow_ok && ws && g_tune[0] && g_tune[7] && op.w_umma && umma_ws_supported(op))
     return conv_umma_ws(op, st);  // narrow output on tensor cores
   if (conv_skinny_supported(op)) return conv_skinny(op, st);
   if (op.w_ig && conv_ig_preferred(op)) return conv_ig(op, st);  // late critic layers / wide dense layers: streaming implicit GEMM
-  if (ws && g_tune[0] && op.w_umma && umma_ws_supported(op)) return conv_umma_ws(op, st);
+  if (ws && g_tune[0] && op.w_umma && umma_ws_supported(op)) {
+    if (wrote_bits) *wrote_bits = op.bits_out != nullptr && op.act == ACT_LRELU && op.shuffle == SHUF_NONE && op.Co % 16 == 0;
+    return conv_umma_ws(op, st);
+  }
   if (op.w_umma && umma_supported(op)) return conv_umma(op, st);
   log_fallback("conv", op.Ci, op.Co, op.Hout, op.Wout, op.B, op.stride, op.x.bf);
   return conv_direct(op, st);
@@ -898,6 +904,13 @@ struct dg_critic {
   void* a[9] = {nullptr};    // a[1..8]
   float *a9 = nullptr, *scores = nullptr, *seed = nullptr, *dz9 = nullptr, *vfc = nullptr;
   void* dz[9] = {nullptr};   // dz[1..8]
+  unsigned short* bits[9] = {nullptr};  // bits[l]: LeakyReLU sign bits of a[l] (ConvOp::bits_out), bf16 mode, l = 1..8
+  bool bits_ok[9] = {false};            // the last forward over these samples really wrote bits[l] (depends on the kernel chosen)
+  // sign bits of a[l] for samples starting at s0, or null (not written / switched off by dg_set_tuning(21, 0))
+  const unsigned short* bits_at(int l, int s0) const {
+    if (!bits[l] || !bits_ok[l] || !g_tune[21]) return nullptr;
+    return bits[l] + (size_t)s0 * pix(l - 1) * (size_t)(L[l - 1].Co >> 4);
+  }
   float *g = nullptr, *u = nullptr;        // (maxB,Hf,Hf,nc) fp32
   void *v0 = nullptr, *v1 = nullptr;       // JVP ping-pong
   double* metric_scratch = nullptr;        // block partials of the MAE / MSE reduction (dg_metrics)
@@ -1041,6 +1054,7 @@ extern "C" int dg_critic_create(const dg_critic_config* cfg, dg_critic** out) {
     const size_t e = c->pix(i) * c->L[i].Co;
     CA(c->a[i + 1], NB * e * c->esz);
     CA(c->dz[i + 1], NB * e * c->esz);
+    if (c->bf && c->L[i].Co % 16 == 0) CA(c->bits[i + 1], NB * (e / 16) * sizeof(unsigned short));
     vmax = std::max(vmax, e);
   }
   CA(c->a9, NB * FC_HIDDEN * sizeof(float));
@@ -1093,7 +1107,10 @@ static int critic_forward_internal(dg_critic* c, int NB, cudaStream_t st, int s0
     op.B = NB; op.w = c->pk + l.pk_off; op.bias = (i == 0) ? c->pk + c->pk_b0 : nullptr;
     if (c->bf) { op.w_umma = c->pk_u + l.pk_off; op.w_ig = c->pk_ig + l.pk_off; }
     op.stride = l.stride; op.act = ACT_LRELU; op.slope = C_SLOPE;
-    DG_TRY(run_conv(op, st));
+    if (c->bits[i + 1] && g_tune[21]) op.bits_out = c->bits[i + 1] + (size_t)s0 * c->pix(i) * (size_t)(l.Co >> 4);
+    bool wrote = false;
+    DG_TRY(run_conv(op, st, &wrote));
+    c->bits_ok[i + 1] = wrote && (s0 == 0 || c->bits_ok[i + 1]);  // a later sample range keeps the flag only if every range wrote
     x = op.y;
   }
   float* a9 = c->a9 + (size_t)s0 * FC_HIDDEN;
@@ -1150,6 +1167,7 @@ static int critic_backward_chain(dg_critic* c, int NB, int n0, int n1, float* g_
     if (c->bf) { op.w_umma = c->pkd_u + l.pkd_off; op.w_ig = c->pkd_ig + l.pkd_off; }
     op.transposed = (l.stride == 2);
     op.act = ACT_MASK; op.slope = C_SLOPE; op.mask = tv_batch(c->act(c->a[i], l.Ci), c->pix(i - 1), s0);
+    op.bits_in = c->bits_at(i, s0);
     DG_TRY(run_conv(op, st));
     if (early && i - 1 <= early_max_layer) DG_TRY(critic_layer_wgrad(c, i - 1, s0, en, en, early == 1, st));
   }
@@ -1206,6 +1224,7 @@ static int critic_gp_second_order(dg_critic* c, int n0, int B, cudaStream_t st) 
     op.B = B; op.w = c->pk + l.pk_off; op.bias = nullptr; op.stride = l.stride;
     if (c->bf) { op.w_umma = c->pk_u + l.pk_off; op.w_ig = c->pk_ig + l.pk_off; }
     op.act = ACT_MASK; op.slope = C_SLOPE; op.mask = tv_batch(c->act(c->a[i + 1], l.Co), c->pix(i), n0);
+    op.bits_in = c->bits_at(i + 1, n0);
     DG_TRY(run_conv(op, st));
     v = op.y;
   }
@@ -1266,6 +1285,7 @@ static int critic_second_order_and_wgrads(dg_critic* c, int B, cudaStream_t st, 
     op.B = B; op.w = c->pk + l.pk_off; op.bias = nullptr; op.stride = l.stride;
     if (c->bf) { op.w_umma = c->pk_u + l.pk_off; op.w_ig = c->pk_ig + l.pk_off; }
     op.act = ACT_MASK; op.slope = C_SLOPE; op.mask = op.y;
+    op.bits_in = c->bits_at(i + 1, n0);  // (the in-place JVP then never reads the activation it overwrites)
     DG_TRY(run_conv(op, st));
     v = op.y;
   }

@@ -199,17 +199,31 @@ __global__ void __launch_bounds__(C1_THREADS, 2) conv_l1_kernel(const C1Args a) 
       for (int mt = 0; mt < 2; ++mt) {
         const size_t p = (size_t)(p0 + mt * 128 + lq * 32 + lane);
         uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;
+        uint32_t mbits = 0;
         if (op.act == ACT_MASK) {
-          const uint4* mp = reinterpret_cast<const uint4*>((const bf16*)op.mask.p + p * op.mask.pitch + op.mask.coff + co0);
-          m0 = mp[0]; m1 = mp[1];
+          if (op.bits_in) {
+            mbits = op.bits_in[p * (size_t)(op.Co >> 4) + (co0 >> 4)];
+          } else {
+            const uint4* mp = reinterpret_cast<const uint4*>((const bf16*)op.mask.p + p * op.mask.pitch + op.mask.coff + co0);
+            m0 = mp[0]; m1 = mp[1];
+          }
         }
         float v[16];
         tmem_ld16(tmem + lane_base + q * 32 + mt * 16, v);
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] += sbias[j];
         if (op.act == ACT_LRELU) {
+          if (op.bits_out) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
+            op.bits_out[p * (size_t)(op.Co >> 4) + (co0 >> 4)] = (unsigned short)w;
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * op.slope;
+        } else if (op.act == ACT_MASK && op.bits_in) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= ((mbits >> j) & 1u) ? 1.f : op.slope;
         } else if (op.act == ACT_MASK) {
           const uint32_t w[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll

@@ -343,7 +343,8 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_ws_kernel(const __grid_con
     const uint32_t lane_base = (uint32_t)(lq * 32) << 16;
     const int ppr_log = 31 - __clz(a.NT >> 4);  // 16-column pieces per (m-tile, class) = 1 << ppr_log
     const int npieces = (a.n_mt * ncls) << ppr_log;
-    const bool pre_mask = (op.act == ACT_MASK) && op.mask.bf;
+    const bool mask_bits = (op.act == ACT_MASK) && op.bits_in != nullptr;
+    const bool pre_mask = (op.act == ACT_MASK) && (op.mask.bf || mask_bits);
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int q = it & 1;
@@ -367,10 +368,20 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_ws_kernel(const __grid_con
         const size_t p = ((size_t)pc.n * op.Hout + pc.yo) * op.Wout + pc.xo;
         return reinterpret_cast<const uint4*>((const bf16*)op.mask.p + p * op.mask.pitch + op.mask.coff + co0 + pc.nc);
       };
+      // sign-bit masks (ConvOp::bits_in): one 2-byte word per piece, carried in m0.x
+      auto load_mask = [&](const Piece& pc, uint4& a0, uint4& a1) {
+        if (mask_bits) {
+          const size_t p = ((size_t)pc.n * op.Hout + pc.yo) * op.Wout + pc.xo;
+          a0.x = op.bits_in[p * (size_t)(op.Co >> 4) + ((co0 + pc.nc) >> 4)];
+        } else {
+          const uint4* mp = mask_ptr(pc);
+          a0 = mp[0]; a1 = mp[1];
+        }
+      };
       Piece cur = decode(half < npieces ? half : 0);
       if (half >= npieces) cur.valid = false;
       uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;
-      if (pre_mask && cur.valid) { const uint4* mp = mask_ptr(cur); m0 = mp[0]; m1 = mp[1]; }
+      if (pre_mask && cur.valid) load_mask(cur, m0, m1);
       if (tid == WS_EPI_WARP0 * 32) WS_TRACE(2, it, 0);
       mbar_wait_ws(tfull_bar(q), ((uint32_t)(it >> 1)) & 1u);
       if (tid == WS_EPI_WARP0 * 32) WS_TRACE(2, it, 1);
@@ -383,7 +394,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_ws_kernel(const __grid_con
         uint4 nm0 = m0, nm1 = m1;
         if (p + 2 < npieces) {
           nxt = decode(p + 2);
-          if (pre_mask && nxt.valid) { const uint4* mp = mask_ptr(nxt); nm0 = mp[0]; nm1 = mp[1]; }
+          if (pre_mask && nxt.valid) load_mask(nxt, nm0, nm1);
         }
         tmem_ld_wait();
         if (cur.valid) {
@@ -413,6 +424,12 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_ws_kernel(const __grid_con
             for (int j = 0; j < 16; ++j) v[j] = fmaf(op.s2, t[j], v[j]);
           }
           if (op.act == ACT_LRELU) {
+            if (op.bits_out) {  // sign bits of this piece for the data-gradient / JVP epilogues (plain NHWC stores only)
+              uint32_t w = 0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
+              op.bits_out[pix * (size_t)(op.Co >> 4) + ((co0 + nc) >> 4)] = (unsigned short)w;
+            }
             if (op.slope >= 0.f && op.slope <= 1.f) {  // max(v, slope*v) == LeakyReLU for 0 <= slope <= 1
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], v[j] * op.slope);
@@ -421,7 +438,10 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_ws_kernel(const __grid_con
               for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * op.slope;
             }
           } else if (op.act == ACT_MASK) {
-            if (pre_mask) {
+            if (mask_bits) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] *= ((m0.x >> j) & 1u) ? 1.f : op.slope;
+            } else if (pre_mask) {
               const uint32_t w[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
