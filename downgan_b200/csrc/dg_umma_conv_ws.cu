@@ -61,6 +61,7 @@ struct WsArgs {
   unsigned over;     // tail pad: bytes the last M-tile's rows may read past the last box region
   unsigned long long* trace;  // debug timeline (DG_WS_TRACE=1), null otherwise
   int early;                  // 1: the producer fills the ring before the weight staging / block barrier (dg_set_tuning(17, .))
+  int bits_tile;              // 1: sign-bit masks of a whole tile are fetched before the wait for its MMAs (dg_set_tuning(21, 2))
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -381,7 +382,25 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_ws_kernel(const __grid_con
       Piece cur = decode(half < npieces ? half : 0);
       if (half >= npieces) cur.valid = false;
       uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;
-      if (pre_mask && cur.valid) load_mask(cur, m0, m1);
+      // bits_tile: the sign words of ALL this warp's pieces of the tile (2 bytes each, up to eight) are requested here, before
+      // the wait for the tile's MMAs, and carried packed in two 64-bit registers - no load sits between an accumulator read
+      // and its store any more
+      const bool tile_bits = mask_bits && a.bits_tile && npieces <= 16;
+      unsigned long long pkA = 0ull, pkB = 0ull;
+      if (tile_bits) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int p = half + 2 * k;
+          if (p < npieces) {
+            const Piece pc = decode(p);
+            if (pc.valid) {
+              const size_t px = ((size_t)pc.n * op.Hout + pc.yo) * op.Wout + pc.xo;
+              const unsigned long long w = op.bits_in[px * (size_t)(op.Co >> 4) + ((co0 + pc.nc) >> 4)];
+              if (k < 4) pkA |= w << (16 * k); else pkB |= w << (16 * (k - 4));
+            }
+          }
+        }
+      } else if (pre_mask && cur.valid) load_mask(cur, m0, m1);
       if (tid == WS_EPI_WARP0 * 32) WS_TRACE(2, it, 0);
       mbar_wait_ws(tfull_bar(q), ((uint32_t)(it >> 1)) & 1u);
       if (tid == WS_EPI_WARP0 * 32) WS_TRACE(2, it, 1);
@@ -394,7 +413,12 @@ __global__ void __launch_bounds__(WS_THREADS, 2) conv_ws_kernel(const __grid_con
         uint4 nm0 = m0, nm1 = m1;
         if (p + 2 < npieces) {
           nxt = decode(p + 2);
-          if (pre_mask && nxt.valid) load_mask(nxt, nm0, nm1);
+          if (pre_mask && !tile_bits && nxt.valid) load_mask(nxt, nm0, nm1);
+        }
+        if (tile_bits) {
+          const int k = (p - half) >> 1;
+          m0.x = (uint32_t)((k < 4 ? pkA >> (16 * k) : pkB >> (16 * (k - 4))) & 0xFFFFull);
+          nm0 = m0;
         }
         tmem_ld_wait();
         if (cur.valid) {
@@ -658,6 +682,7 @@ int conv_umma_ws(const ConvOp& op, cudaStream_t st) {
   WsArgs a;
   int cps = 1;
   if (!plan_ws(op, a, cps)) { set_error("conv_umma_ws: unsupported shape"); return DG_ERR_INVALID; }
+  a.bits_tile = g_tune[21] >= 2;
   const size_t smem = (size_t)a.w_off + (size_t)9 * op.Ci * a.NT * 2 + a.over + 1024;
   const long long total = (long long)op.B * op.Hout * op.Wout;
   const double taps = op.transposed ? 2.25 : 9.0;

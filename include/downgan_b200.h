@@ -311,7 +311,9 @@ int dg_profile_report(double* out, int n_classes);
  * key 20: the 1- / 2-channel first-layer convolutions run on the planar kernel without an im2col build (1;
  * csrc/dg_umma_conv_l1p.cu: faster alone, measured 1.4 % slower in the overlapped cfg-2 step) or on the im2col kernel (0, default).
  * key 21: the critic's forward epilogues store LeakyReLU sign bits (2 bytes per pixel and 16 channels) and its data-gradient / JVP
- * epilogues read them instead of the saved bf16 activations (1, default) or not (0).
+ * epilogues read them instead of the saved bf16 activations (1, default) or not (0); 2 = as 1, and the weights-stationary kernel
+ * fetches the sign words of a whole tile before it waits for the tile's MMAs (measured slower: the extra address arithmetic
+ * lengthens the epilogue warps' instruction chains, 43.1 k vs 43.9 k samples/s).
  * Returns the previous value, or DG_ERR_INVALID for an unknown key. */
 #define DG_TUNE_KEYS 22
 int dg_set_tuning(int key, int value);
