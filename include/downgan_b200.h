@@ -314,8 +314,10 @@ int dg_profile_report(double* out, int n_classes);
  * epilogues read them instead of the saved bf16 activations (1, default) or not (0); 2 = as 1, and the weights-stationary kernel
  * fetches the sign words of a whole tile before it waits for the tile's MMAs (measured slower: the extra address arithmetic
  * lengthens the epilogue warps' instruction chains, 43.1 k vs 43.9 k samples/s).
+ * key 22: the weights-stationary conv kernel uses its specialised epilogue (no bias / residual / shuffle checks) where the
+ * layer allows it (1, default) or always the general one (0).
  * Returns the previous value, or DG_ERR_INVALID for an unknown key. */
-#define DG_TUNE_KEYS 22
+#define DG_TUNE_KEYS 23
 int dg_set_tuning(int key, int value);
 
 #ifdef __cplusplus
