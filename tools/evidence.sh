@@ -18,7 +18,7 @@ if [ "$MODE" = full ]; then
   # full captures: the longest launch of the dominant class (critic layer 1 data gradient: conv_ws_kernel<2, 1>), the streaming
   # conv kernel and the fused trunk forward
   timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off --kernel-name-base demangled \
-      -k regex:"conv_ws_kernel<\(int\)2, \(int\)1>" -s 1 -c 1 -f -o $O/conv_ws_l1dgrad python tools/cycle.py > $O/ncu_full_ws.log 2>&1; echo "ncu ws rc=$?" >> $O/status.txt
+      -k regex:"conv_ws_kernel<\(int\)2, \(int\)1," -s 1 -c 1 -f -o $O/conv_ws_l1dgrad python tools/cycle.py > $O/ncu_full_ws.log 2>&1; echo "ncu ws rc=$?" >> $O/status.txt
   timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off \
       -k regex:conv_ig_kernel -s 2 -c 1 -f -o $O/conv_ig_c2 python tools/cycle.py > $O/ncu_full_ig.log 2>&1; echo "ncu ig rc=$?" >> $O/status.txt
   timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off \
