@@ -4,8 +4,11 @@ Same class name, constructor and method names as the reference trainer;
 ``_critic_train_iteration`` / ``_generator_train_iteration`` return ``None``
 and mutate parameters and optimizer state.  Underneath, each iteration is ONE
 call into ``libdowngan_b200.so`` (``dg_critic_step`` / ``dg_generator_step``)
-followed by an optional NCCL all-reduce of the flat gradient buffer (data
-parallel, one process per GPU) and one fused Adam launch (``dg_adam_step``).
+followed by one optimizer launch: ``dg_adam_step`` on one GPU; under data
+parallelism (one process per GPU) ``dg_dp_allreduce_adam``, this repo's kernel
+that sums the symmetric-memory gradient bucket over NVLink and applies Adam
+(``dp.FusedBucket``; NCCL all-reduce + ``dg_adam_step`` when it is unavailable
+or switched off with ``DG_DP_FUSED=0``).
 
 Differences from the reference that do not change results:
   * the generator backward of the critic iteration (wasserstein.py:52) is
