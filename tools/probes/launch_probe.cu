@@ -54,6 +54,35 @@ int main() {
   printf("with carveout=100 on both:\n");
   for (int kb : {16, 100, 200})
     printf("  smem %3d KB alt plain       %.2f us per pair\n", kb, timeit([&] { k_smem<<<148, 256, kb * 1024>>>(d); k_plain<<<148, 256>>>(d); }, N));
+  // the same chains captured into a CUDA graph: GPU-side spacing of dependent kernels without the host's launch cost
+  {
+    cudaStream_t cs; cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+    auto graph_time = [&](int variant, int len) {
+      cudaGraph_t g; cudaGraphExec_t ge;
+      cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+      for (int i = 0; i < len; ++i) {
+        if (variant == 0) k_plain<<<148, 256, 0, cs>>>(d);
+        else if (variant == 1) { k_smem<<<148, 256, 100 * 1024, cs>>>(d); k_plain<<<148, 256, 0, cs>>>(d); }
+        else k_tmem<<<148, 256, 100 * 1024, cs>>>(d, 64);
+      }
+      cudaStreamEndCapture(cs, &g);
+      cudaGraphInstantiate(&ge, g, 0);
+      cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+      cudaGraphLaunch(ge, cs); cudaStreamSynchronize(cs);
+      cudaEventRecord(a, cs);
+      for (int r = 0; r < 5; ++r) cudaGraphLaunch(ge, cs);
+      cudaEventRecord(b, cs); cudaEventSynchronize(b);
+      float ms; cudaEventElapsedTime(&ms, a, b);
+      cudaGraphExecDestroy(ge); cudaGraphDestroy(g);
+      return 1e3f * ms / (5 * len);
+    };
+    printf("CUDA graph, chain of 400 dependent launches (grid 148):\n");
+    printf("  plain                       %.2f us per launch\n", graph_time(0, 400));
+    printf("  smem 100 KB alt plain       %.2f us per pair\n", graph_time(1, 200));
+    printf("  tmem 64 cols, smem 100 KB   %.2f us per launch\n", graph_time(2, 400));
+    // stream launches with the host kept far ahead of the GPU by a long first kernel are not needed: the graph numbers
+    // bound what a stream can do
+  }
   // events around every launch (what the library's profiler does)
   cudaEvent_t e[2]; cudaEventCreate(&e[0]); cudaEventCreate(&e[1]);
   float acc = 0;
