@@ -209,3 +209,29 @@ def test_deferred_conv_gradients_equal_plain_step():
     oc = otr.critic_loss_and_grads(_g_sd, CFG2_G, _c_sd, CFG2_C, coarse, fine, alpha, otr.Hyper())
     ref = torch.cat([v.reshape(-1) for v in oc["grads"].values()])
     assert abs(pu.rel(g1, ref) - pu.rel(g0, ref)) < 1e-3
+
+
+@pytest.mark.parametrize("key,value", [(19, 1), (20, 1), (21, 0), (21, 2), (22, 0), (18, 1), (18, 4)])
+def test_kernel_selection_switches_keep_the_results(key, value):
+    """Every alternative kernel path behind dg_set_tuning (second critic side stream, planar first-layer kernel, bf16 masks /
+    whole-tile sign words instead of per-piece sign bits, general conv epilogue, trunk backward in 1 / 4 RRDB ranges) computes the
+    same critic and generator iteration as the default path: scalars and flat gradients to 1e-3 (measured: 6e-8 .. 3e-7 = the
+    atomics' run-to-run floor for every switch, i.e. identical LeakyReLU branches with sign bits and with bf16 masks; 1.8e-4 for
+    the planar first-layer kernel, whose operand rounding differs)."""
+    from downgan_b200 import _lib
+    from test_gpu_parity import _run_steps
+    lib = _lib.load()
+    gspec, cspec = onet.GeneratorSpec(filters=16, channels=2), onet.CriticSpec(coarse_dim=16, fine_dim=128, nc=2)
+    G, C, _, _ = pu.build_pair(gspec, cspec, "bf16", seed=3, critic_scale=1.9)
+    coarse, fine, alpha = synth_batch(8, 2, 16, seed=21, aseed=22)
+    sc0, cg0, sg0, gg0 = _run_steps(G, C, coarse, fine, alpha)
+    prev = lib.dg_set_tuning(key, value)
+    try:
+        sc1, cg1, sg1, gg1 = _run_steps(G, C, coarse, fine, alpha)
+    finally:
+        lib.dg_set_tuning(key, prev)
+    assert abs(float(sc1[0]) - float(sc0[0])) <= 1e-3 * abs(float(sc0[0])) and abs(float(sg1[0]) - float(sg0[0])) <= 1e-3 * abs(float(sg0[0]))
+    flat = lambda d: torch.cat([v.reshape(-1) for v in d.values()])
+    ec, eg = pu.rel(flat(cg1), flat(cg0)), pu.rel(flat(gg1), flat(gg0))
+    print(f"tuning {key}={value}: critic grads {ec:.2e}, generator grads {eg:.2e}")
+    assert ec < 1e-3 and eg < 1e-3
