@@ -640,7 +640,8 @@ static int gen_trunk_backward(dg_generator* g, int B, bool& side_on, cudaStream_
     // g_tune[18] RRDB ranges (last range first): the dense convs' weight gradients of a range only need that range's dz, so
     // they are enqueued on the side stream as soon as the range's kernel is (one image per CTA: 64 of 148 SMs at cfg-2) and run
     // beside the NEXT range's data gradients instead of after the whole chain (measured: profiles/README.md).
-    auto dense_wgrads = [&](int r_lo, int r_hi, int part, cudaStream_t s2) -> int {
+    // which: 0 = every channel block, 1 = only the 64-channel blocks (nine-tap units), 2 = only the 16- / 32-channel blocks
+    auto dense_wgrads = [&](int r_lo, int r_hi, int part, cudaStream_t s2, int which = 0, bool with_colsum = true) -> int {
       std::vector<WgradOp> blk;
       blk.reserve((size_t)(r_hi - r_lo) * 15 * 2);
       for (int r = r_hi - 1; r >= r_lo; --r)
@@ -659,14 +660,16 @@ static int gen_trunk_backward(dg_generator* g, int B, bool& side_on, cudaStream_
               WgradOp o = w;
               o.x.coff = w.x.coff + c0; o.Ci = cb; o.dbias = nullptr;
               o.dw_ci_total = w.Ci; o.dw_ci_off = c0;
-              blk.push_back(o);
+              if (which == 0 || (which == 1) == (cb == 64)) blk.push_back(o);
               c0 += cb;
             }
           }
-      if (blk.empty()) return 0;
-      if ((int)g->wgws_parts.size() <= part) g->wgws_parts.resize(part + 1);
-      char* table = (char*)g->wgws_table_dev + (size_t)part * wgrad_ws_batch_bytes(g->R * 15 * 2);
-      DG_TRY(wgrad_ws_batched(blk.data(), (int)blk.size(), table, g->wgws_parts[part], 2, s2));
+      if (!blk.empty()) {
+        if ((int)g->wgws_parts.size() <= part) g->wgws_parts.resize(part + 1);
+        char* table = (char*)g->wgws_table_dev + (size_t)part * wgrad_ws_batch_bytes(g->R * 15 * 2);
+        DG_TRY(wgrad_ws_batched(blk.data(), (int)blk.size(), table, g->wgws_parts[part], 2, s2));
+      }
+      if (!with_colsum) return 0;
       // bias gradients of the range = column sums of its dz buffers
       const Layer& l0 = g->layers[g->idx_db(r_lo, 0, 1)];
       return colsum_dense_blocks((void* const*)g->d_ptrs_dev + 3 * r_lo, (r_hi - r_lo) * 3, (size_t)B * Hc * Hc, g->gpk + l0.pkb_off, s2);
@@ -679,6 +682,12 @@ static int gen_trunk_backward(dg_generator* g, int B, bool& side_on, cudaStream_
       if (p > 0) {  // overlaps the next range's kernel
         DG_TRY(g->side.fork(st));
         DG_TRY(dense_wgrads(r_lo, r_hi, p, g->side.s));
+      } else if (g_tune[23] && nsplit < 4) {
+        // last range: nothing is left to overlap it with, so its two batched launches (64-channel blocks / narrower blocks) run
+        // beside each other on the side stream and the caller's stream instead of one after the other
+        DG_TRY(g->side.fork(st));
+        DG_TRY(dense_wgrads(r_lo, r_hi, nsplit, g->side.s, 1, false));
+        DG_TRY(dense_wgrads(r_lo, r_hi, p, st, 2, true));
       } else {
         DG_TRY(dense_wgrads(r_lo, r_hi, p, st));
       }

@@ -316,8 +316,10 @@ int dg_profile_report(double* out, int n_classes);
  * lengthens the epilogue warps' instruction chains, 43.1 k vs 43.9 k samples/s).
  * key 22: the weights-stationary conv kernel uses its specialised epilogue (no bias / residual / shuffle checks) where the
  * layer allows it (1, default) or always the general one (0).
+ * key 23: the two batched dense-block weight-gradient launches of the LAST trunk-backward range run beside each other on two
+ * streams (1, default) or one after the other (0).
  * Returns the previous value, or DG_ERR_INVALID for an unknown key. */
-#define DG_TUNE_KEYS 23
+#define DG_TUNE_KEYS 24
 int dg_set_tuning(int key, int value);
 
 #ifdef __cplusplus
