@@ -144,12 +144,12 @@ class WassersteinGAN:
     def _prep(self, t: torch.Tensor) -> torch.Tensor:
         return t.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
 
-    def _handles(self, coarse: torch.Tensor):
+    def _handles(self, coarse: torch.Tensor, lazy_critic: bool = False):
         b, _, h, _ = coarse.shape
         g = self.G.native(h, b)
         c = self.C.native(b)
         self.G.ensure_packed(g)
-        self.C.ensure_packed(c)
+        self.C.ensure_packed(c, lazy=lazy_critic)
         return g, c
 
     def _allreduce(self, grads: torch.Tensor) -> float:
@@ -166,7 +166,7 @@ class WassersteinGAN:
             if alpha is None:
                 alpha = torch.rand(b, 1, 1, 1, device=self.device)  # wasserstein.py:91
             alpha = self._prep(alpha).reshape(b)
-            g, c = self._handles(coarse)
+            g, c = self._handles(coarse, lazy_critic=True)  # the critic's re-pack runs beside the batch assembly
             if self._c_scal is None or self._c_scal.device != self.device:
                 self._c_scal = torch.zeros(8, device=self.device)
             # data parallel: the classifier gradients (74 % of the bucket) are final before the conv weight gradients,

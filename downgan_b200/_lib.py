@@ -75,6 +75,7 @@ _SIGNATURES = {
                                C.c_int, C.c_float, _P]),
     "dg_dp_allreduce_adam": (C.c_int, [C.POINTER(DpPeers), _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                        C.c_int, C.c_float, C.c_uint, _P]),
+    "dg_critic_pack_lazy": (C.c_int, [_P, _P]),
     "dg_critic_step": (C.c_int, [_P, _P, C.POINTER(Hyper), _P, _P, _P, C.c_int, _P, _P, _P]),
     "dg_generator_step": (C.c_int, [_P, _P, C.POINTER(Hyper), _P, _P, C.c_int, _P, _P, _P]),
     "dg_critic_defer_conv_grads": (C.c_int, [_P, C.c_int]),

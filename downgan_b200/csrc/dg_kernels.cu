@@ -1344,7 +1344,7 @@ CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank,
   return fn(map, dt, rank, addr, dims, strides, box, estr, il, sw, l2, oob);
 }
 }  // namespace dg
-namespace dg { int g_tune[DG_TUNE_KEYS] = {1, 1, 1, 0, 1, 0, 1, 1, 1, 1, 4, 1, 1, 3, 1, 0, 1, 0, 2, 0, 0, 1, 1, 1}; }  // see include/downgan_b200.h: dg_set_tuning
+namespace dg { int g_tune[DG_TUNE_KEYS] = {1, 1, 1, 0, 1, 0, 1, 1, 1, 1, 4, 1, 1, 3, 1, 0, 1, 0, 2, 0, 0, 1, 1, 1, 0, 1}; }  // see include/downgan_b200.h: dg_set_tuning
 extern "C" int dg_set_tuning(int key, int value) {
   if (key < 0 || key >= DG_TUNE_KEYS) { dg::set_error("dg_set_tuning: unknown key %d", key); return DG_ERR_INVALID; }
   const int prev = dg::g_tune[key];

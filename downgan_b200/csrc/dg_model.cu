@@ -908,6 +908,7 @@ struct dg_critic {
   UmmaPackDesc *utab_fwd = nullptr, *utab_dgrad = nullptr, *utab_igdgrad = nullptr;
   int n_ufwd = 0, n_udgrad = 0, max_ufwd = 1, max_udgrad = 1, n_igdgrad = 0;
   bool packed = false;
+  const float* pending_params = nullptr;  // dg_critic_pack_lazy: flat parameters to pack before the next use of the weights
   // activations for up to NBmax samples
   float* a0 = nullptr;       // NHWC fp32 input batch
   void* a[9] = {nullptr};    // a[1..8]
@@ -1102,7 +1103,20 @@ extern "C" int dg_critic_pack(dg_critic* c, const float* params, void* stream) {
   DG_TRY(pack_weights2(params, c->pk, c->pk_u, c->tab_fwd, c->n_fwd, c->max_fwd, c->pkd, c->pkd_u, c->tab_dgrad, c->n_dgrad,
                        c->max_dgrad, st, c_ig ? c->pk_ig : nullptr, c_ig ? c->pkd_ig : nullptr));
   c->packed = true;
+  c->pending_params = nullptr;
   return 0;
+}
+// Records that `params` must be packed before the weights are used next; the launch itself is issued by the next entry point
+// that needs the weights - the fused critic iteration runs it beside its batch assembly (which does not read weights) instead
+// of in front of it.  `params` must stay valid and unchanged until then (the trainer passes its flat parameter buffer).
+extern "C" int dg_critic_pack_lazy(dg_critic* c, const float* params) {
+  DG_CHECK(c && params, "dg_critic_pack_lazy: null argument");
+  c->pending_params = params;
+  return 0;
+}
+static int critic_flush_pack(dg_critic* c, cudaStream_t st) {
+  if (!c->pending_params) return 0;
+  return dg_critic_pack(c, c->pending_params, (void*)st);
 }
 
 // Critic.forward (critic.py:101-106) over samples [s0, s0 + NB) of c->a0.
@@ -1322,6 +1336,7 @@ extern "C" int dg_critic_fwd(dg_critic* c, const float* x, int batch, float* sco
   if (c && c->pending_finish) { set_error("dg_critic_fwd: dg_critic_step_finish has not been called"); return DG_ERR_STATE; }
   DG_CHECK(c && x && scores, "dg_critic_fwd: null argument");
   DG_CHECK(batch >= 1 && batch <= c->NBmax, "dg_critic_fwd: batch %d outside [1,%d]", batch, c->NBmax);
+  if (c) DG_TRY(critic_flush_pack(c, (cudaStream_t)stream));  // a pending dg_critic_pack_lazy
   if (!c->packed) { set_error("dg_critic_fwd: dg_critic_pack has not been called"); return DG_ERR_STATE; }
   cudaStream_t st = (cudaStream_t)stream;
   DG_TRY(nchw_to_nhwc(x, tv(c->a0, 0, c->nc), batch, c->nc, c->Hf, c->Hf, st));
@@ -1360,6 +1375,7 @@ extern "C" int dg_critic_bwd(dg_critic* c, const float* d_scores, float* grads_f
   if (c && c->pending_finish) { set_error("dg_critic_bwd: dg_critic_step_finish has not been called"); return DG_ERR_STATE; }
   DG_CHECK(c && d_scores, "dg_critic_bwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(critic_flush_pack(c, st));  // a pending dg_critic_pack_lazy
   const int B = c->saved_batch;
   if (B <= 0) { set_error("dg_critic_bwd: no saved forward"); return DG_ERR_STATE; }
   DG_CHECK(!d_x || B <= c->maxB, "dg_critic_bwd: d_x needs batch <= max_batch");
@@ -1380,6 +1396,7 @@ extern "C" int dg_gp(dg_critic* c, const dg_hyper* hp, const float* real, const 
   if (c && c->pending_finish) { set_error("dg_gp: dg_critic_step_finish has not been called"); return DG_ERR_STATE; }
   DG_CHECK(c && hp && real && fake && alpha && gp_out, "dg_gp: null argument");
   DG_CHECK(batch >= 1 && batch <= c->maxB, "dg_gp: batch %d outside [1,%d]", batch, c->maxB);
+  if (c) DG_TRY(critic_flush_pack(c, (cudaStream_t)stream));  // a pending dg_critic_pack_lazy
   if (!c->packed) { set_error("dg_gp: dg_critic_pack has not been called"); return DG_ERR_STATE; }
   cudaStream_t st = (cudaStream_t)stream;
   DG_TRY(build_critic_input(real, fake, 1, alpha, c->a0, batch, c->nc, c->Hf, c->Hf, 1, st));
@@ -1420,8 +1437,18 @@ static int critic_step_body(dg_generator* g, dg_critic* c, const dg_hyper* hp, c
     fine = c->fs_real;
     fake_nhwc = c->fs_fake;
   }
-  // one 3B critic batch: [real ; fake ; alpha*real + (1-alpha)*fake]   (:37-38, :91-97)
-  DG_TRY(build_critic_input(fine, fake_nhwc, 0, alpha, c->a0, B, c->nc, c->Hf, c->Hf, 0, st));
+  // one 3B critic batch: [real ; fake ; alpha*real + (1-alpha)*fake]   (:37-38, :91-97).  A pending weight pack
+  // (dg_critic_pack_lazy) runs beside it: the assembly reads no weights, so it goes to the side stream while the pack launch
+  // occupies the caller's stream (dg_set_tuning(25, 0): pack first, then assemble).
+  if (c->pending_params && g_tune[25] && c->side.s != nullptr) {
+    DG_TRY(c->side.fork(st));
+    DG_TRY(build_critic_input(fine, fake_nhwc, 0, alpha, c->a0, B, c->nc, c->Hf, c->Hf, 0, c->side.s));
+    DG_TRY(critic_flush_pack(c, st));
+    DG_TRY(c->side.join(st));
+  } else {
+    DG_TRY(critic_flush_pack(c, st));
+    DG_TRY(build_critic_input(fine, fake_nhwc, 0, alpha, c->a0, B, c->nc, c->Hf, c->Hf, 0, st));
+  }
   const bool two_chain = g_tune[9] >= 2 && c->side.s != nullptr;
   const bool head = !two_chain && g_tune[11] && critic_head_supported(B) && fc_fwd_raw_supported(c->fc_in, FC_HIDDEN);
   // g_tune[13] = k > 0: the real + fake rows of the weight gradients of layers 0 .. k-1 (the HBM-bound ones, which scale with
@@ -1482,7 +1509,7 @@ extern "C" int dg_critic_step(dg_generator* g, dg_critic* c, const dg_hyper* hp,
   DG_CHECK(g && c && hp && coarse && fine && alpha && c_grads_flat && scalars, "dg_critic_step: null argument");
   DG_CHECK(batch >= 1 && batch <= g->maxB && batch <= c->maxB, "dg_critic_step: batch %d too large", batch);
   DG_CHECK(g->Hf == c->Hf && g->Cout == c->nc, "dg_critic_step: generator output does not match critic input");
-  if (!g->packed || !c->packed) { set_error("dg_critic_step: weights not packed"); return DG_ERR_STATE; }
+  if (!g->packed || !(c->packed || c->pending_params)) { set_error("dg_critic_step: weights not packed"); return DG_ERR_STATE; }
   cudaStream_t st = (cudaStream_t)stream;
   DG_TRY(g->side.join(st));  // a deferred look-ahead chain (dg_generator_lookahead_first) may still be running
   const int B = batch;
@@ -1571,7 +1598,7 @@ extern "C" int dg_critic_step_fake(dg_generator* g, dg_critic* c, const dg_hyper
               fake_offset + batch, g->lookahead);
     return DG_ERR_STATE;
   }
-  if (!c->packed) { set_error("dg_critic_step_fake: weights not packed"); return DG_ERR_STATE; }
+  if (!(c->packed || c->pending_params)) { set_error("dg_critic_step_fake: weights not packed"); return DG_ERR_STATE; }
   cudaStream_t st = (cudaStream_t)stream;
   // fakes outside the range dg_generator_lookahead_first computed in stream order: wait for the deferred chain
   if (g->side.dirty && !(fake_offset >= g->ready_lo && fake_offset + batch <= g->ready_hi)) DG_TRY(g->side.join(st));
@@ -1627,6 +1654,7 @@ extern "C" int dg_generator_step(dg_generator* g, dg_critic* c, const dg_hyper* 
   DG_CHECK(g && c && hp && coarse && fine && g_grads_flat && scalars, "dg_generator_step: null argument");
   DG_CHECK(batch >= 1 && batch <= g->maxB && batch <= c->maxB, "dg_generator_step: batch %d too large", batch);
   DG_CHECK(g->Hf == c->Hf && g->Cout == c->nc, "dg_generator_step: generator output does not match critic input");
+  if (c) DG_TRY(critic_flush_pack(c, (cudaStream_t)stream));  // a pending dg_critic_pack_lazy
   if (!g->packed || !c->packed) { set_error("dg_generator_step: weights not packed"); return DG_ERR_STATE; }
   cudaStream_t st = (cudaStream_t)stream;
   DG_TRY(g->side.join(st));  // a deferred look-ahead chain (dg_generator_lookahead_first) may still be running
@@ -1646,6 +1674,7 @@ extern "C" int dg_generator_step_saved(dg_generator* g, dg_critic* c, const dg_h
   DG_CHECK(g && c && hp && fine && g_grads_flat && scalars, "dg_generator_step_saved: null argument");
   DG_CHECK(batch >= 1 && batch <= c->maxB, "dg_generator_step_saved: batch %d too large", batch);
   DG_CHECK(g->Hf == c->Hf && g->Cout == c->nc, "dg_generator_step_saved: generator output does not match critic input");
+  if (c) DG_TRY(critic_flush_pack(c, (cudaStream_t)stream));  // a pending dg_critic_pack_lazy
   if (!g->packed || !c->packed) { set_error("dg_generator_step_saved: weights not packed"); return DG_ERR_STATE; }
   if (g->saved_batch != batch || g->lookahead < batch) {
     set_error("dg_generator_step_saved: no saved look-ahead forward for %d samples (saved %d, look-ahead %d)", batch, g->saved_batch,
@@ -1671,6 +1700,7 @@ extern "C" int dg_metrics(dg_generator* g, dg_critic* c, const float* coarse, in
   DG_CHECK(g && c && fine && out8, "dg_metrics: null argument");
   DG_CHECK(batch >= 1 && batch <= c->maxB && batch <= g->maxB, "dg_metrics: batch %d too large", batch);
   DG_CHECK(g->Hf == c->Hf && g->Cout == c->nc, "dg_metrics: generator output does not match critic input");
+  if (c) DG_TRY(critic_flush_pack(c, (cudaStream_t)stream));  // a pending dg_critic_pack_lazy
   if (!g->packed || !c->packed) { set_error("dg_metrics: weights not packed"); return DG_ERR_STATE; }
   cudaStream_t st = (cudaStream_t)stream;
   const float* fake = nullptr;

@@ -118,10 +118,15 @@ class Critic(FlatParamsMixin, nn.Module):
         d["_dirty"] = True
         return d
 
-    def ensure_packed(self, handle: int) -> None:
+    def ensure_packed(self, handle: int, lazy: bool = False) -> None:
+        """Re-pack the weights if they changed.  `lazy` (the trainer's critic iteration): only record the request; the native
+        iteration runs the pack launch beside its batch assembly (dg_critic_pack_lazy)."""
         flat = self.flat_params()
         if self._needs_pack():
-            _lib.check(_lib.load().dg_critic_pack(handle, flat.data_ptr(), _lib.stream_ptr()))
+            if lazy:
+                _lib.check(_lib.load().dg_critic_pack_lazy(handle, flat.data_ptr()))
+            else:
+                _lib.check(_lib.load().dg_critic_pack(handle, flat.data_ptr(), _lib.stream_ptr()))
             self._dirty = False
 
     # ---- forward / backward ------------------------------------------------

@@ -107,6 +107,9 @@ int64_t dg_critic_param_offset(const dg_critic_config* cfg, int index);
  * called after every parameter change (optimizer step / load_state_dict). */
 int dg_generator_pack(dg_generator* g, const float* params_flat, void* stream);
 int dg_critic_pack(dg_critic* c, const float* params_flat, void* stream);
+/* Like dg_critic_pack, but only records `params`: the pack launch is issued by the next entry point that needs the weights;
+ * the fused critic iterations run it beside their batch assembly.  `params` must stay valid and unchanged until then. */
+int dg_critic_pack_lazy(dg_critic* c, const float* params);
 
 /* ---- Generator.forward (networks/generator.py:83-90) -------------------
  * coarse: (B, channels, H, H) NCHW fp32 -> fake: (B, n_predictands, 8H, 8H).
@@ -318,8 +321,11 @@ int dg_profile_report(double* out, int n_classes);
  * layer allows it (1, default) or always the general one (0).
  * key 23: the two batched dense-block weight-gradient launches of the LAST trunk-backward range run beside each other on two
  * streams (1, default) or one after the other (0).
+ * key 24: unused.
+ * key 25 (with dg_critic_pack_lazy): the pending weight pack runs beside the critic iteration's batch assembly (1, default) or
+ * in front of it (0).
  * Returns the previous value, or DG_ERR_INVALID for an unknown key. */
-#define DG_TUNE_KEYS 24
+#define DG_TUNE_KEYS 26
 int dg_set_tuning(int key, int value);
 
 #ifdef __cplusplus
