@@ -1489,8 +1489,15 @@ static int critic_step_body(dg_generator* g, dg_critic* c, const dg_hyper* hp, c
   DG_TRY(critic_gp_first_order(c, hp, 2 * B, B, scalars, 1, nullptr, st,
                                c->a0 + (size_t)2 * B * c->Hf * c->Hf * c->nc));  // u overwrites the interpolates
   const bool defer = c->defer_conv && !two_chain && c->n_fwd > dg_critic::N_CONV_ENTRIES;
-  DG_TRY(critic_second_order_and_wgrads(c, B, st, two_chain, early_ml, defer));
-  if (defer) {
+  // tuning key 24: the classifier gradients (74 % of the flat buffer, a transposing unpack) are final on this stream while the
+  // conv weight gradients still run on the side stream - unpack them now, join, then unpack the nine conv entries
+  const bool split_unpack = !defer && g_tune[24] && !two_chain && g_tune[9] && c->side.s != nullptr && c->n_fwd > dg_critic::N_CONV_ENTRIES;
+  DG_TRY(critic_second_order_and_wgrads(c, B, st, two_chain, early_ml, defer || split_unpack));
+  if (split_unpack) {
+    DG_TRY(unpack_wgrads(c->gpk, c_grads_flat, c->tab_fwd + dg_critic::N_CONV_ENTRIES, c->n_fwd - dg_critic::N_CONV_ENTRIES, c->max_fwd, st));
+    DG_TRY(c->side.join(st)); DG_TRY(c->side2.join(st));
+    DG_TRY(unpack_wgrads(c->gpk, c_grads_flat, c->tab_fwd, dg_critic::N_CONV_ENTRIES, c->max_fwd, st));
+  } else if (defer) {
     // the classifier gradients (74 % of the bucket) are final on this stream: unpack them now so that the caller can start
     // their all-reduce while the conv weight gradients are still running on the side stream
     DG_TRY(unpack_wgrads(c->gpk, c_grads_flat, c->tab_fwd + dg_critic::N_CONV_ENTRIES, c->n_fwd - dg_critic::N_CONV_ENTRIES, c->max_fwd, st));

@@ -321,7 +321,9 @@ int dg_profile_report(double* out, int n_classes);
  * layer allows it (1, default) or always the general one (0).
  * key 23: the two batched dense-block weight-gradient launches of the LAST trunk-backward range run beside each other on two
  * streams (1, default) or one after the other (0).
- * key 24: unused.
+ * key 24: the fused critic iteration unpacks the classifier gradients while its conv weight gradients still run on the side
+ * stream and only the nine conv entries after the join (1) or everything after the join (0, default: the extra launch costs
+ * more than it hides, 44 424 vs 44 577 samples/s in a same-box A/B).
  * key 25 (with dg_critic_pack_lazy): the pending weight pack runs beside the critic iteration's batch assembly (1, default) or
  * in front of it (0).
  * Returns the previous value, or DG_ERR_INVALID for an unknown key. */

@@ -211,7 +211,7 @@ def test_deferred_conv_gradients_equal_plain_step():
     assert abs(pu.rel(g1, ref) - pu.rel(g0, ref)) < 1e-3
 
 
-@pytest.mark.parametrize("key,value", [(19, 1), (20, 1), (21, 0), (21, 2), (22, 0), (18, 1), (18, 4), (23, 0), (25, 0)])
+@pytest.mark.parametrize("key,value", [(19, 1), (20, 1), (21, 0), (21, 2), (22, 0), (18, 1), (18, 4), (23, 0), (24, 1), (25, 0)])
 def test_kernel_selection_switches_keep_the_results(key, value):
     """Every alternative kernel path behind dg_set_tuning (second critic side stream, planar first-layer kernel, bf16 masks /
     whole-tile sign words instead of per-piece sign bits, general conv epilogue, trunk backward in 1 / 4 RRDB ranges) computes the
